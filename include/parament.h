@@ -1,0 +1,201 @@
+/*
+ * parament.h -- C-ABI of the B200-native Parament_equiprop library (libparament.so).
+ *
+ * Drop-in boundary: every entry point in section 1 has the name, argument order, argument meaning,
+ * return codes and error strings of the reference's public header
+ * (/root/reference/src/cuda/parament.h, cited per declaration as "ref parament.h:LINE"), so the
+ * unchanged pyparament ctypes wrapper (/root/reference/src/python/pyparament/parament/paramentlib.py:57-72)
+ * binds it without modification.  Section 2 are additive entry points (ensembles, device-resident
+ * operands, timing, multi-GPU slices) that the reference does not have; nothing in section 1
+ * depends on them.
+ *
+ * Conventions (same as the reference):
+ *   - complex64 / complex128 operands are interleaved (re, im) pairs == cuComplex / cuDoubleComplex
+ *     == numpy complex64 / complex128.
+ *   - matrices are dim x dim, passed as the row-major (C-order) buffers the wrapper produces
+ *     (parament.py:197-212); `out` receives the physical time-ordered propagator
+ *     U = U_{N-1} ... U_1 U_0 in the same row-major layout (parament.py:273).
+ *   - all pointer arguments of section 1 are HOST pointers owned by the caller and only read/written
+ *     during the call; calls are synchronous.
+ *   - every function returns a Parament_ErrorCode (C int) unless stated; the code of the last call is
+ *     also kept in the context (Parament_peekAtLastError).
+ *   - a context is not thread-safe; distinct contexts may be used from distinct threads.
+ */
+#ifndef PARAMENT_B200_PARAMENT_H_
+#define PARAMENT_B200_PARAMENT_H_
+
+#ifdef __cplusplus
+extern "C" {
+#else
+#include <stdbool.h>
+#endif
+
+#if defined(__GNUC__)
+#define PARAMENT_API __attribute__((visibility("default")))
+#else
+#define PARAMENT_API
+#endif
+
+/* Opaque contexts (ref parament.h:56-57). */
+struct Parament_Context_f32;
+struct Parament_Context_f64;
+
+/* Interleaved complex operands; layout-compatible with cuComplex / cuDoubleComplex. */
+#ifndef PARAMENT_NO_COMPLEX_TYPEDEFS
+typedef struct Parament_c64 { float re, im; } Parament_c64;
+typedef struct Parament_c128 { double re, im; } Parament_c128;
+#endif
+
+/* Quadrature rule selector (ref parament.h:64-69; values are part of the ABI, mirrored in constants.py:29-31). */
+typedef enum Parament_QuadratureSpec {
+    PARAMENT_QUADRATURE_NONE = 0x00000000,
+    PARAMENT_QUADRATURE_MIDPOINT = 0x01000000,
+    PARAMENT_QUADRATURE_SIMPSON = 0x02000000
+} Parament_QuadratureSpec;
+
+/* Error codes (ref parament.h:74-130; mirrored in constants.py:17-27).  Codes 30 and 60 keep their numeric
+ * value although there is no cuBLAS in this library: 30 = CUDA runtime / device initialisation failed,
+ * 60 = a kernel launch or device operation failed. */
+typedef enum Parament_ErrorCode {
+    PARAMENT_STATUS_SUCCESS = 0,
+    PARAMENT_STATUS_HOST_ALLOC_FAILED = 10,
+    PARAMENT_STATUS_DEVICE_ALLOC_FAILED = 20,
+    PARAMENT_STATUS_CUBLAS_INIT_FAILED = 30,
+    PARAMENT_STATUS_INVALID_VALUE = 50,
+    PARAMENT_STATUS_CUBLAS_FAILED = 60,
+    PARAMENT_STATUS_SELECT_SMALLER_DT = 70,
+    PARAMENT_STATUS_NO_HAMILTONIAN = 80,
+    PARAMENT_STATUS_INVALID_QUADRATURE_SELECTION = 90,
+    PARAMENT_FAIL = 1000
+} Parament_ErrorCode;
+
+/* ===================================================================================================
+ * Section 1 -- the reference's C-ABI (20 exported symbols of the reference build + device_info)
+ * =================================================================================================== */
+
+/* ref parament.h:155 (impl parament.cpp:52-128).  Creates a complex64 context on the current CUDA device.
+ * 10 on host allocation failure, 30 if no usable CUDA device, 20 on device allocation failure. */
+PARAMENT_API Parament_ErrorCode Parament_create(struct Parament_Context_f32 **handle_p);
+
+/* ref parament.h:177 (impl parament.cpp:186-205).  NULL is accepted and ignored.  Waits for the device. */
+PARAMENT_API Parament_ErrorCode Parament_destroy(struct Parament_Context_f32 *handle);
+
+/* ref parament.h:219 (impl parament.cpp:211-368).  H0: dim*dim; H1: amps consecutive dim*dim matrices.
+ * use_magnus requires quadrature_mode == SIMPSON, otherwise 90 is returned and the context is left with
+ * NO Hamiltonian (parament.cpp:220-226,365-367).  The series norm is
+ * Hnorm = rowsum(H0) + sum_k rowsum(H_k) (parament.cpp:280-284). */
+PARAMENT_API Parament_ErrorCode Parament_setHamiltonian(struct Parament_Context_f32 *handle, const Parament_c64 *H0,
+                                                        const Parament_c64 *H1, unsigned int dim, unsigned int amps,
+                                                        bool use_magnus, enum Parament_QuadratureSpec quadrature_mode);
+
+/* ref parament.h:261 (impl parament.cpp:791-851).  carr: amps arrays of pts amplitudes each, concatenated
+ * (parament.h:225-226); amps may be smaller than the count given to setHamiltonian, missing controls have
+ * zero amplitude (parament.h:228-230).  out: dim*dim.  80 without a Hamiltonian, 70 when the automatic
+ * iteration count would exceed the table (parament.cpp:386-388). */
+PARAMENT_API Parament_ErrorCode Parament_equiprop(struct Parament_Context_f32 *handle, const Parament_c64 *carr, double dt,
+                                                  unsigned int pts, unsigned int amps, Parament_c64 *out);
+
+/* ref parament.h:286 / :400 (impl parament.cpp:723-766).  Pure table look-up on H_norm*dt; -1 beyond the table. */
+PARAMENT_API int Parament_selectIterationCycles_fp32(double H_norm, double dt);
+PARAMENT_API int Parament_selectIterationCycles_fp64(double H_norm, double dt);
+
+/* ref parament.h:308 (impl parament.cpp:772-776): fix the Chebyshev degree MMAX for subsequent calls.
+ * Unlike the reference (correct only for odd MMAX >= 3) any cycles >= 1 is evaluated
+ * correctly. */
+PARAMENT_API Parament_ErrorCode Parament_setIterationCyclesManually(struct Parament_Context_f32 *handle, unsigned int cycles);
+
+/* ref parament.h:327 (impl parament.cpp:782-786): back to the table-driven choice. */
+PARAMENT_API Parament_ErrorCode Parament_automaticIterationCycles(struct Parament_Context_f32 *handle);
+
+/* ref parament.h:347 (impl parament.cpp:854-857): code of the last call on this context; does not modify it. */
+PARAMENT_API Parament_ErrorCode Parament_peekAtLastError(struct Parament_Context_f32 *handle);
+
+/* ref parament.h:357 (impl parament.cpp:859-882): static, byte-identical message strings. */
+PARAMENT_API const char *Parament_errorMessage(Parament_ErrorCode errorCode);
+
+/* complex128 variants: ref parament.h:363,368,373,379,385,390,395 (impl parament.cpp:925-954). */
+PARAMENT_API Parament_ErrorCode Parament_create_fp64(struct Parament_Context_f64 **handle_p);
+PARAMENT_API Parament_ErrorCode Parament_destroy_fp64(struct Parament_Context_f64 *handle);
+PARAMENT_API Parament_ErrorCode Parament_setHamiltonian_fp64(struct Parament_Context_f64 *handle, const Parament_c128 *H0,
+                                                             const Parament_c128 *H1, unsigned int dim, unsigned int amps,
+                                                             bool use_magnus, Parament_QuadratureSpec quadrature_mode);
+PARAMENT_API Parament_ErrorCode Parament_equiprop_fp64(struct Parament_Context_f64 *handle, const Parament_c128 *carr,
+                                                       double dt, unsigned int pts, unsigned int amps, Parament_c128 *out);
+PARAMENT_API Parament_ErrorCode Parament_setIterationCyclesManually_fp64(struct Parament_Context_f64 *handle, unsigned int cycles);
+PARAMENT_API Parament_ErrorCode Parament_automaticIterationCycles_fp64(struct Parament_Context_f64 *handle);
+PARAMENT_API Parament_ErrorCode Parament_peekAtLastError_fp64(struct Parament_Context_f64 *handle);
+
+/* ref mathhelper.h:67-68 (impl mathhelper.cpp:82-118): max over rows of the sum of |entries| of the
+ * row-major buffer. */
+PARAMENT_API double OneNorm(const Parament_c64 *mat, unsigned int dim);
+PARAMENT_API double OneNorm_fp64(const Parament_c128 *mat, unsigned int dim);
+
+/* ref deviceinfo.h:35 (impl deviceInfo.c:30-59): print the CUDA device table to stdout.  Resolved by the
+ * wrapper at import time (paramentlib.py:72). */
+PARAMENT_API void device_info(void);
+
+/* The wrapper's Parament._get_error_message() calls this name (parament.py:284); the reference never
+ * defined it.  Alias of Parament_peekAtLastError for either context type. */
+PARAMENT_API Parament_ErrorCode Parament_getLastError(void *handle);
+
+/* ===================================================================================================
+ * Section 2 -- additive entry points (not in the reference)
+ * =================================================================================================== */
+
+/* Ensemble: `batch` independent pulses through the same Hamiltonian in one call (GRAPE sweeps,
+ * BASELINE.json configs[4]).  carr: batch x amps x pts (pulse-major), out: batch x dim x dim. */
+PARAMENT_API Parament_ErrorCode Parament_equipropBatch(struct Parament_Context_f32 *handle, const Parament_c64 *carr,
+                                                       double dt, unsigned int pts, unsigned int amps, unsigned int batch,
+                                                       Parament_c64 *out);
+PARAMENT_API Parament_ErrorCode Parament_equipropBatch_fp64(struct Parament_Context_f64 *handle, const Parament_c128 *carr,
+                                                            double dt, unsigned int pts, unsigned int amps, unsigned int batch,
+                                                            Parament_c128 *out);
+
+/* Device-resident variant: carr_dev / out_dev are DEVICE pointers on the context's device; the work is
+ * enqueued on `stream` (a cudaStream_t passed as void*, NULL = the context's own stream) and the call
+ * returns without synchronising when `stream` is non-NULL.  Same layouts as Parament_equipropBatch. */
+PARAMENT_API Parament_ErrorCode Parament_equipropDevice(struct Parament_Context_f32 *handle, const Parament_c64 *carr_dev,
+                                                        double dt, unsigned int pts, unsigned int amps, unsigned int batch,
+                                                        Parament_c64 *out_dev, void *stream);
+PARAMENT_API Parament_ErrorCode Parament_equipropDevice_fp64(struct Parament_Context_f64 *handle, const Parament_c128 *carr_dev,
+                                                             double dt, unsigned int pts, unsigned int amps, unsigned int batch,
+                                                             Parament_c128 *out_dev, void *stream);
+
+/* Time-slice variant for multi-GPU runs: propagate only effective steps [step_lo, step_hi) of a pulse whose
+ * full coefficient arrays (pts points per control) are given.  Partial propagators of consecutive slices
+ * combine as P_total = P_last ... P_1 P_0 (Parament_combine).  Host pointers. */
+PARAMENT_API Parament_ErrorCode Parament_equipropSlice(struct Parament_Context_f32 *handle, const Parament_c64 *carr, double dt,
+                                                       unsigned int pts, unsigned int amps, unsigned long long step_lo,
+                                                       unsigned long long step_hi, Parament_c64 *out);
+PARAMENT_API Parament_ErrorCode Parament_equipropSlice_fp64(struct Parament_Context_f64 *handle, const Parament_c128 *carr,
+                                                            double dt, unsigned int pts, unsigned int amps,
+                                                            unsigned long long step_lo, unsigned long long step_hi,
+                                                            Parament_c128 *out);
+
+/* Ordered product of `count` dim x dim partial propagators (host pointers, parts[0] is the earliest slice):
+ * out = parts[count-1] ... parts[1] parts[0], evaluated on the device in complex128. */
+PARAMENT_API Parament_ErrorCode Parament_combine(struct Parament_Context_f32 *handle, const Parament_c64 *parts,
+                                                 unsigned int count, Parament_c64 *out);
+PARAMENT_API Parament_ErrorCode Parament_combine_fp64(struct Parament_Context_f64 *handle, const Parament_c128 *parts,
+                                                      unsigned int count, Parament_c128 *out);
+
+/* Introspection of the last equiprop on this context (either context type).  Keys:
+ *   0 device milliseconds between first and last kernel (CUDA events on the context stream)
+ *   1 number of kernels launched          2 Chebyshev degree used (MMAX actually evaluated)
+ *   3 degree the reference table selects  4 effective steps per pulse N
+ *   5 kernel family used (1 = register-resident DMMA warp kernel, 2 = shared-memory CTA kernel,
+ *                         3 = batched global-memory GEMM pipeline)
+ *   6 H2D bytes copied                    7 D2H bytes copied */
+PARAMENT_API double Parament_lastStat(void *handle, int key);
+
+/* Select the CUDA device a context lives on.  Must be called before setHamiltonian; default is device 0
+ * (reference: device 0 implicit, parament.cpp:108) or $PARAMENT_DEVICE. */
+PARAMENT_API Parament_ErrorCode Parament_setDevice(void *handle, int device);
+
+/* Library identification string, e.g. "parament-b200 0.1 (sm_100a)". */
+PARAMENT_API const char *Parament_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARAMENT_B200_PARAMENT_H_ */
