@@ -192,6 +192,10 @@ PARAMENT_API double Parament_lastStat(void *handle, int key);
  * (reference: device 0 implicit, parament.cpp:108) or $PARAMENT_DEVICE. */
 PARAMENT_API Parament_ErrorCode Parament_setDevice(void *handle, int device);
 
+/* Pipe-peak microbenchmark on the current CUDA device, used as roofline denominator by bench.py.
+ * kind: 0 FP32 FFMA TFLOP/s, 1 FP64 DFMA TFLOP/s, 2 FP64 tensor-pipe DMMA TFLOP/s, 3 HBM copy GB/s. */
+PARAMENT_API double Parament_measurePeak(int kind);
+
 /* Library identification string, e.g. "parament-b200 0.1 (sm_100a)". */
 PARAMENT_API const char *Parament_version(void);
 

@@ -1,0 +1,804 @@
+// api.cu -- C-ABI of libparament.so and the host orchestration of Parament_equiprop.
+//
+// Mirrors the reference's host layer (/root/reference/src/cuda/parament.cpp:51-954) function for function
+// at the ABI, with its own context and a different device pipeline:
+//   reference  coefficients -> transfer -> expand (X for all steps in HBM) -> MMAX batched cuBLAS GEMMs
+//              + diagonal_add -> log2(N) batched GEMMs
+//   here       coefficients -> transfer -> ONE fused chain kernel (+ one small ordered reduction) for
+//              dim <= 16, or an L2-resident chunked tensor-pipe pipeline for larger dim.
+// There is no CPU fallback: without a CUDA device Parament_create fails with code 30.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "context.hpp"
+#include "k1_warp.hpp"
+#include "k4_gemm.hpp"
+#include "series.hpp"
+
+using namespace pb;
+
+namespace {
+
+#define PB_CUDA_OK(expr) ((expr) == cudaSuccess)
+
+inline Context *as_ctx(void *h) {
+    Context *c = reinterpret_cast<Context *>(h);
+    return (c && c->magic == 0x50423230) ? c : nullptr;
+}
+
+Parament_ErrorCode fail(Context *c, Parament_ErrorCode code) {
+    if (c) c->lastError = code;
+    cudaGetLastError();   // clear a sticky-free error state
+    return code;
+}
+
+void free_dev(DeviceBuffer &b) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.bytes = 0;
+}
+
+bool ensure_dev(DeviceBuffer &b, size_t bytes) {
+    if (b.bytes >= bytes && b.ptr) return true;
+    free_dev(b);
+    if (bytes == 0) bytes = 16;
+    if (!PB_CUDA_OK(cudaMalloc(&b.ptr, bytes))) { b.ptr = nullptr; cudaGetLastError(); return false; }
+    b.bytes = bytes;
+    return true;
+}
+
+bool ensure_pinned(void *&p, size_t &have, size_t bytes) {
+    if (have >= bytes && p) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr; have = 0;
+    if (!PB_CUDA_OK(cudaMallocHost(&p, bytes))) { p = nullptr; cudaGetLastError(); return false; }
+    have = bytes;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// create / destroy                                                   (reference parament.cpp:51-205)
+// ---------------------------------------------------------------------------------------------------
+Parament_ErrorCode create_ctx(Context **out, bool fp64) {
+    if (!out) return PARAMENT_STATUS_INVALID_VALUE;
+    *out = nullptr;
+    Context *c = new (std::nothrow) Context();
+    if (!c) return PARAMENT_STATUS_HOST_ALLOC_FAILED;
+    c->fp64 = fp64;
+    int ndev = 0;
+    if (!PB_CUDA_OK(cudaGetDeviceCount(&ndev)) || ndev < 1) {
+        cudaGetLastError();
+        delete c;
+        return PARAMENT_STATUS_CUBLAS_INIT_FAILED;   // code 30: device initialisation failed
+    }
+    int dev = 0;
+    if (const char *e = getenv("PARAMENT_DEVICE")) dev = atoi(e);
+    if (dev < 0 || dev >= ndev) dev = 0;
+    c->device = dev;
+    if (!PB_CUDA_OK(cudaSetDevice(dev)) ||
+        !PB_CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, dev)) ||
+        !PB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
+        !PB_CUDA_OK(cudaEventCreate(&c->ev_start)) || !PB_CUDA_OK(cudaEventCreate(&c->ev_stop))) {
+        cudaGetLastError();
+        delete c;
+        return PARAMENT_STATUS_CUBLAS_INIT_FAILED;
+    }
+    c->lastError = PARAMENT_STATUS_SUCCESS;
+    *out = c;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+Parament_ErrorCode destroy_ctx(Context *c) {
+    if (!c) return PARAMENT_STATUS_SUCCESS;   // NULL is a no-op (parament.cpp:190-191)
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
+    free_dev(c->d_Y); free_dev(c->d_S0); free_dev(c->d_S1); free_dev(c->d_pending); free_dev(c->d_tree);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    cudaEventDestroy(c->ev_start);
+    cudaEventDestroy(c->ev_stop);
+    cudaStreamDestroy(c->stream);
+    c->magic = 0;
+    delete c;
+    cudaGetLastError();
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// setHamiltonian                                                    (reference parament.cpp:211-368)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+double one_norm_t(const T *m, unsigned int dim);
+template <>
+double one_norm_t<Parament_c64>(const Parament_c64 *m, unsigned int dim) {
+    double best = 0;   // mathhelper.cpp:82-97: float modulus, double accumulation
+    for (unsigned i = 0; i < dim; ++i) {
+        double s = 0;
+        for (unsigned j = 0; j < dim; ++j) s += (double)hypotf(m[(size_t)dim * i + j].re, m[(size_t)dim * i + j].im);
+        best = std::max(best, s);
+    }
+    return best;
+}
+template <>
+double one_norm_t<Parament_c128>(const Parament_c128 *m, unsigned int dim) {
+    double best = 0;   // mathhelper.cpp:99-114
+    for (unsigned i = 0; i < dim; ++i) {
+        double s = 0;
+        for (unsigned j = 0; j < dim; ++j) s += hypot(m[(size_t)dim * i + j].re, m[(size_t)dim * i + j].im);
+        best = std::max(best, s);
+    }
+    return best;
+}
+
+void commutator(const zc *A, const zc *B, zc *out, int n) {   // out = A B - B A
+    std::vector<zc> t((size_t)n * n, zc(0, 0));
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < n; ++k) {
+            const zc a = A[(size_t)i * n + k], b = B[(size_t)i * n + k];
+            const zc *Bk = B + (size_t)k * n, *Ak = A + (size_t)k * n;
+            zc *ti = t.data() + (size_t)i * n;
+            for (int j = 0; j < n; ++j) ti[j] += a * Bk[j] - b * Ak[j];
+        }
+    std::copy(t.begin(), t.end(), out);
+}
+
+inline int pair_index(int j, int k, int A) { return j * A - j * (j + 1) / 2 + (k - j - 1); }   // j < k
+
+// Upload the matrix table in the layout of the selected kernel family.
+bool upload_matrices(Context *c) {
+    const int n = c->dim;
+    if (c->family == 1) {
+        const int NT = c->npad / 8, NE = 2 * NT * NT;
+        std::vector<double2> frag((size_t)c->nmats * 2 * NE * 32, make_double2(0, 0));
+        for (int m = 0; m < c->nmats; ++m) {
+            const zc *M = c->mats.data() + (size_t)m * n * n;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, q = lane & 3;
+                for (int mt = 0; mt < NT; ++mt)            // AccFrag order (frag.cuh)
+                    for (int nt = 0; nt < NT; ++nt)
+                        for (int i = 0; i < 2; ++i) {
+                            const int r = 8 * mt + g, col = 8 * nt + 2 * q + i, e = (mt * NT + nt) * 2 + i;
+                            if (r < n && col < n)
+                                frag[(((size_t)m * 2 + 0) * NE + e) * 32 + lane] = make_double2(M[(size_t)r * n + col].real(), M[(size_t)r * n + col].imag());
+                        }
+                for (int kt = 0; kt < 2 * NT; ++kt)        // BFrag order
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const int r = 8 * (kt >> 1) + 2 * q + (kt & 1), col = 8 * nt + g, e = kt * NT + nt;
+                        if (r < n && col < n)
+                            frag[(((size_t)m * 2 + 1) * NE + e) * 32 + lane] = make_double2(M[(size_t)r * n + col].real(), M[(size_t)r * n + col].imag());
+                    }
+            }
+        }
+        if (!ensure_dev(c->d_H, frag.size() * sizeof(double2))) return false;
+        return PB_CUDA_OK(cudaMemcpy(c->d_H.ptr, frag.data(), frag.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    }
+    const int np = c->npad;
+    std::vector<double2> tab((size_t)c->nmats * np * np, make_double2(0, 0));
+    for (int m = 0; m < c->nmats; ++m)
+        for (int r = 0; r < n; ++r)
+            for (int col = 0; col < n; ++col) {
+                const zc v = c->mats[((size_t)m * n + r) * n + col];
+                tab[((size_t)m * np + r) * np + col] = make_double2(v.real(), v.imag());
+            }
+    if (!ensure_dev(c->d_H, tab.size() * sizeof(double2))) return false;
+    return PB_CUDA_OK(cudaMemcpy(c->d_H.ptr, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+}
+
+template <typename T>
+Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigned int dim, unsigned int amps,
+                                   bool use_magnus, int quad) {
+    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    cudaSetDevice(c->device);
+    c->have_hamiltonian = false;   // a previous Hamiltonian is dropped first (parament.cpp:216)
+    if (use_magnus && quad != PARAMENT_QUADRATURE_SIMPSON)
+        return fail(c, PARAMENT_STATUS_INVALID_QUADRATURE_SELECTION);   // parament.cpp:220-226
+    if (quad != PARAMENT_QUADRATURE_NONE && quad != PARAMENT_QUADRATURE_MIDPOINT && quad != PARAMENT_QUADRATURE_SIMPSON)
+        return fail(c, PARAMENT_STATUS_INVALID_QUADRATURE_SELECTION);
+    if (!H0 || (!H1 && amps > 0) || dim == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    c->enable_magnus = use_magnus;
+    c->quadrature = use_magnus ? PARAMENT_QUADRATURE_SIMPSON : quad;
+    c->dim = (int)dim;
+    c->amps = (int)amps;
+    const size_t nn = (size_t)dim * dim;
+    const int A = (int)amps;
+    c->nmats = 1 + A + (use_magnus ? A + A * (A - 1) / 2 : 0);
+    try {
+        c->mats.assign((size_t)c->nmats * nn, zc(0, 0));
+    } catch (const std::bad_alloc &) {
+        return fail(c, PARAMENT_STATUS_HOST_ALLOC_FAILED);
+    }
+    for (size_t e = 0; e < nn; ++e) c->mats[e] = zc((double)H0[e].re, (double)H0[e].im);
+    for (int a = 0; a < A; ++a)
+        for (size_t e = 0; e < nn; ++e) c->mats[(size_t)(1 + a) * nn + e] = zc((double)H1[(size_t)a * nn + e].re, (double)H1[(size_t)a * nn + e].im);
+
+    // Series norm: sum of the max-row-abs-sums of the buffers as passed (parament.cpp:280-284)
+    c->Hnorm = one_norm_t<T>(H0, dim);
+    for (int a = 0; a < A; ++a) c->Hnorm += one_norm_t<T>(H1 + (size_t)a * nn, dim);
+
+    if (use_magnus) {   // physical commutators [H0,H_j] and [H_j,H_k], j<k (parament.cpp:289-359)
+        const zc *h0 = c->mats.data();
+        for (int j = 0; j < A; ++j) commutator(h0, h0 + (size_t)(1 + j) * nn, c->mats.data() + (size_t)(1 + A + j) * nn, (int)dim);
+        for (int j = 0; j < A; ++j)
+            for (int k = j + 1; k < A; ++k)
+                commutator(h0 + (size_t)(1 + j) * nn, h0 + (size_t)(1 + k) * nn,
+                           c->mats.data() + (size_t)(1 + 2 * A + pair_index(j, k, A)) * nn, (int)dim);
+    }
+
+    if (dim <= 16) { c->family = 1; c->npad = dim <= 8 ? 8 : 16; }
+    else           { c->family = 3; c->npad = k4_pad((int)dim); }
+    if (!upload_matrices(c)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
+    c->have_hamiltonian = true;
+    c->lastError = PARAMENT_STATUS_SUCCESS;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// equiprop                                                          (reference parament.cpp:373-851)
+// ---------------------------------------------------------------------------------------------------
+struct CallSpec {
+    unsigned int amps;              // control arrays per pulse present in the buffer
+    unsigned int batch;             // pulses
+    size_t stride;                  // points between consecutive control arrays in the device buffer
+    unsigned long long nsteps;      // effective steps per pulse to process; step 0 starts at raw point 0
+    unsigned long long total_steps; // steps of the whole pulse (degree policy of sliced runs)
+    double dt;
+};
+
+unsigned long long effective_steps(const Context *c, unsigned long long pts) {   // parament.cpp:820-831
+    if (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) return pts >= 1 ? (pts - 1) / 2 : 0;
+    if (c->quadrature == PARAMENT_QUADRATURE_MIDPOINT) return pts >= 1 ? pts - 1 : 0;
+    return pts;
+}
+int points_per_step(const Context *c) {
+    return (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) ? 2 : 1;
+}
+int point_overlap(const Context *c) {   // extra raw points a slice needs beyond r * nsteps
+    if (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) return 1;
+    if (c->quadrature == PARAMENT_QUADRATURE_MIDPOINT) return 1;
+    return 0;
+}
+
+// Degree policy.  M_ref is what the reference's table selects (parament.cpp:376-391); complex64 contexts
+// raise the degree until the accumulated truncation error N * 2|J_{M+1}(x)| is below 1e-6 (10 % of the
+// 1e-5 tolerance), because the fp32 table only bounds the error of ONE step (DESIGN.md "Numerics").
+Parament_ErrorCode choose_degree(Context *c, double h, unsigned long long total_steps, int &M_ref, int &M_used) {
+    if (c->MMAX_manual) {
+        M_ref = M_used = c->MMAX;
+        if (M_used < 1 || M_used > kMaxDegree) return PARAMENT_STATUS_INVALID_VALUE;
+        return PARAMENT_STATUS_SUCCESS;
+    }
+    M_ref = c->fp64 ? select_cycles_fp64(c->Hnorm, h) : select_cycles_fp32(c->Hnorm, h);
+    if (M_ref < 3) return PARAMENT_STATUS_SELECT_SMALLER_DT;   // parament.cpp:386-388
+    M_used = M_ref;
+    c->MMAX = M_ref;
+    if (!c->fp64) {
+        const int cap = std::max(M_ref, select_cycles_fp64(c->Hnorm, h) > 0 ? select_cycles_fp64(c->Hnorm, h) : kMaxDegree);
+        std::vector<long double> J; long double j0m1;
+        bessel_j_table((long double)(c->Hnorm * h), cap + 1, J, j0m1);
+        const double N = (double)std::max<unsigned long long>(total_steps, 1);
+        while (M_used < cap && N * 2.0 * std::fabs((double)J[M_used + 1]) > 1e-6) ++M_used;
+    }
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) {
+    const double h = (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) ? 2.0 * s.dt : s.dt;   // parament.cpp:800-802
+    int M_ref = 0, M_used = 0;
+    Parament_ErrorCode ec = choose_degree(c, h, s.total_steps, M_ref, M_used);
+    if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+    c->stat_M_ref = M_ref;
+    c->stat_M_used = M_used;
+    memset(&p, 0, sizeof(p));
+    p.n = c->dim;
+    p.npad = c->npad;
+    p.quad = c->enable_magnus ? QUAD_SIMPSON
+             : (c->quadrature == PARAMENT_QUADRATURE_SIMPSON ? QUAD_SIMPSON
+                : (c->quadrature == PARAMENT_QUADRATURE_MIDPOINT ? QUAD_MIDPOINT : QUAD_NONE));
+    p.M = M_used;
+    p.pts = (unsigned int)s.stride;
+    p.amps_in = s.amps;
+    p.magfac = h / 12.0;
+    // sigma is rounded to double FIRST and x is derived from the rounded value in long double, so that
+    // sigma * x == 2 h holds to 1e-19: a relative error in sigma alone would stretch the time axis coherently.
+    p.sigma = 2.0 / c->Hnorm;
+    const long double x = 2.0L * (long double)h / (long double)p.sigma;
+    std::vector<long double> J; long double j0m1;
+    bessel_j_table(x, M_used, J, j0m1);
+    p.a[0] = cplx{(double)j0m1, 0.0};
+    for (int k = 1; k <= M_used; ++k) {
+        const double v = (double)J[k];
+        switch (k & 3) {   // (-i)^k, mathhelper.cpp:35-46
+            case 0: p.a[k] = cplx{v, 0.0}; break;
+            case 1: p.a[k] = cplx{0.0, -v}; break;
+            case 2: p.a[k] = cplx{-v, 0.0}; break;
+            default: p.a[k] = cplx{0.0, v}; break;
+        }
+    }
+    const int A = c->amps, Ain = (int)s.amps;
+    int nt = 0;
+    const int need = Ain + (c->enable_magnus ? Ain + Ain * (Ain - 1) / 2 : 0);
+    if (need > kMaxTerms) return PARAMENT_STATUS_INVALID_VALUE;
+    for (int j = 0; j < Ain; ++j) p.terms[nt++] = Term{TERM_PLAIN, 1 + j, j, 0};
+    if (c->enable_magnus) {
+        for (int j = 0; j < Ain; ++j) p.terms[nt++] = Term{TERM_MAG_DRIFT, 1 + A + j, j, 0};
+        for (int j = 0; j < Ain; ++j)
+            for (int k = j + 1; k < Ain; ++k) p.terms[nt++] = Term{TERM_MAG_PAIR, 1 + 2 * A + pair_index(j, k, A), j, k};
+    }
+    p.nterms = nt;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+#define PB_LAUNCH(expr)                                         \
+    do {                                                        \
+        if ((expr) != cudaSuccess) return PARAMENT_STATUS_CUBLAS_FAILED; \
+        ++c->stat_launches;                                     \
+    } while (0)
+
+// Ordered E-form tree level: dst[i] = src[2i] + src[2i+1] + src[2i+1] * src[2i]; odd leftover copied.
+Parament_ErrorCode tree_level(Context *c, const double2 *src, int count, double2 *dst, int npad, cudaStream_t st, int &out_count) {
+    const long long nn = (long long)npad * npad;
+    const int pairs = count / 2;
+    GemmArgs g{};
+    g.A = src + nn; g.strideA = 2 * nn;
+    g.B = src; g.strideB = 2 * nn;
+    g.C1 = src; g.strideC1 = 2 * nn; g.beta1 = 1.0;
+    g.C2 = src + nn; g.strideC2 = 2 * nn; g.beta2 = 1.0;
+    g.D = dst; g.strideD = nn;
+    g.gamma = cplx{0.0, 0.0};
+    g.n = npad; g.batch = pairs;
+    if (pairs > 0) PB_LAUNCH(k4_gemm(g, st));
+    if (count & 1) {
+        if (!PB_CUDA_OK(cudaMemcpyAsync(dst + (long long)pairs * nn, src + (long long)(count - 1) * nn, nn * sizeof(double2),
+                                        cudaMemcpyDeviceToDevice, st)))
+            return PARAMENT_STATUS_CUBLAS_FAILED;
+    }
+    out_count = pairs + (count & 1);
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+// Reduce `count` matrices at `buf` to one, ping-ponging with `scratch`; the result ends in buf[0].
+Parament_ErrorCode tree_reduce_all(Context *c, double2 *buf, int count, double2 *scratch, int npad, cudaStream_t st) {
+    const size_t nn = (size_t)npad * npad;
+    double2 *src = buf, *dst = scratch;
+    while (count > 1) {
+        int nc = 0;
+        Parament_ErrorCode ec = tree_level(c, src, count, dst, npad, st, nc);
+        if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+        count = nc;
+        std::swap(src, dst);
+    }
+    if (src != buf && !PB_CUDA_OK(cudaMemcpyAsync(buf, src, nn * sizeof(double2), cudaMemcpyDeviceToDevice, st)))
+        return PARAMENT_STATUS_CUBLAS_FAILED;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+struct F3Plan { int S; int cap; };
+
+// Chunk length S keeps the three S x npad^2 work arrays (Y, B_{k+1}, B_{k+2}) L2-resident (~57 MB) while a
+// launch still covers the machine; `cap` bounds the buffer of pending partial products.
+F3Plan plan_family3(const Context *c, const CallSpec &s) {
+    const size_t nn = (size_t)c->npad * c->npad;
+    F3Plan f;
+    f.S = (int)std::max<long long>(2, (19LL * 65536 + (long long)nn - 1) / (long long)nn);
+    if ((unsigned long long)f.S > s.nsteps) f.S = (int)std::max<unsigned long long>(s.nsteps, 1);
+    const size_t want = std::min<size_t>(2048, std::max<size_t>(64, ((size_t)2 << 30) / (nn * sizeof(double2))));
+    // no more than the run can produce
+    f.cap = (int)std::max<size_t>(2, std::min<size_t>(want, (size_t)std::min<unsigned long long>(s.nsteps, 1ull << 30)));
+    return f;
+}
+
+bool alloc_family3(Context *c, const F3Plan &f) {
+    const size_t nn = (size_t)c->npad * c->npad;
+    return ensure_dev(c->d_Y, (size_t)f.S * nn * sizeof(double2)) && ensure_dev(c->d_S0, (size_t)f.S * nn * sizeof(double2)) &&
+           ensure_dev(c->d_S1, (size_t)f.S * nn * sizeof(double2)) &&
+           ensure_dev(c->d_pending, (size_t)(f.cap + f.S) * nn * sizeof(double2)) &&
+           ensure_dev(c->d_tree, (size_t)((f.cap + f.S) / 2 + 1) * nn * sizeof(double2));
+}
+
+Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *carr_dev, const CallSpec &s, void *out_dev, cudaStream_t st) {
+    const int np = c->npad;
+    const size_t nn = (size_t)np * np;
+    const size_t io = c->fp64 ? sizeof(double2) : sizeof(float2);
+    const int tiles = k4_tiles(np);
+    const F3Plan f = plan_family3(c, s);
+    const int S = f.S, cap = f.cap;
+    double2 *Y = (double2 *)c->d_Y.ptr, *pend = (double2 *)c->d_pending.ptr, *tree = (double2 *)c->d_tree.ptr;
+    const int M = p.M;
+    for (unsigned int b = 0; b < s.batch; ++b) {
+        const char *cb = (const char *)carr_dev + (size_t)b * s.amps * s.stride * io;
+        int pending = 0;
+        for (unsigned long long step0 = 0; step0 < s.nsteps; step0 += S) {
+            const int Sc = (int)std::min<unsigned long long>(S, s.nsteps - step0);
+            double2 *S0 = (double2 *)c->d_S0.ptr, *S1 = (double2 *)c->d_S1.ptr;
+            PB_LAUNCH(k4_assemble(c->fp64, p, cb, (const double2 *)c->d_H.ptr, Y, S0, S1, step0, Sc, st));
+            double2 *E = S0;
+            if (M >= 2) {
+                GemmArgs g{};
+                g.strideA = g.strideB = g.strideC1 = g.strideD = (long long)nn;
+                g.C2 = nullptr; g.beta2 = 0.0; g.n = np; g.batch = Sc; g.B = Y;
+                for (int k = M - 2; k >= 1; --k) {   // B_k = B_{k+1} Y - B_{k+2} + a_k I   (parament.cpp:596-643)
+                    g.A = S0; g.C1 = S1; g.D = S1; g.beta1 = -1.0; g.gamma = p.a[k];
+                    PB_LAUNCH(k4_gemm(g, st));
+                    std::swap(S0, S1);
+                }
+                g.A = S0; g.C1 = S1; g.D = S1; g.beta1 = -2.0; g.gamma = p.a[0];   // E = B_1 Y - 2 B_2 + (J0-1) I
+                PB_LAUNCH(k4_gemm(g, st));
+                E = S1;
+            }
+            // ordered product inside the chunk while the launches still fill the machine
+            double2 *other = (E == S1) ? S0 : S1;
+            int count = Sc;
+            double2 *src = E;
+            while (count > 1 && (count / 2) * tiles >= 48) {
+                int nc = 0;
+                Parament_ErrorCode ec = tree_level(c, src, count, other, np, st, nc);
+                if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+                std::swap(src, other);
+                count = nc;
+            }
+            if (!PB_CUDA_OK(cudaMemcpyAsync(pend + (size_t)pending * nn, src, (size_t)count * nn * sizeof(double2), cudaMemcpyDeviceToDevice, st)))
+                return PARAMENT_STATUS_CUBLAS_FAILED;
+            pending += count;
+            if (pending >= cap) {
+                Parament_ErrorCode ec = tree_reduce_all(c, pend, pending, tree, np, st);
+                if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+                pending = 1;
+            }
+        }
+        Parament_ErrorCode ec = tree_reduce_all(c, pend, pending, tree, np, st);
+        if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+        PB_LAUNCH(k4_finish(c->fp64, pend, c->dim, np, (char *)out_dev + (size_t)b * c->dim * c->dim * io, true, st));
+    }
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+// Device-resident core shared by every equiprop entry point.
+Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const CallSpec &s, void *out_dev, cudaStream_t st) {
+    SeriesParams p;
+    Parament_ErrorCode ec = build_series(c, s, p);
+    if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+    c->stat_steps = s.nsteps;
+    c->stat_launches = 0;
+    // all allocations happen before the timed region (grow-only scratch, nothing is allocated in steady state)
+    K1Plan plan{};
+    if (c->family == 1) {
+        plan = plan_k1(c->npad, s.batch, s.nsteps, c->num_sms);
+        if (!ensure_dev(c->d_partials, plan.partial_elems * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+    } else if (!alloc_family3(c, plan_family3(c, s))) {
+        return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+    }
+    if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, st))) return PARAMENT_STATUS_CUBLAS_FAILED;
+    if (c->family == 1) {
+        if (launch_k1(c->npad, c->fp64, p, carr_dev, (const double2 *)c->d_H.ptr, (double2 *)c->d_partials.ptr, s.batch, plan,
+                      0, s.nsteps, out_dev, st) != cudaSuccess)
+            return PARAMENT_STATUS_CUBLAS_FAILED;
+        c->stat_launches = 2;
+    } else {
+        ec = run_family3(c, p, carr_dev, s, out_dev, st);
+        if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+    }
+    if (!PB_CUDA_OK(cudaEventRecord(c->ev_stop, st))) return PARAMENT_STATUS_CUBLAS_FAILED;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+template <typename T>
+void write_identity(T *out, int n, unsigned int batch) {
+    for (unsigned int b = 0; b < batch; ++b)
+        for (int r = 0; r < n; ++r)
+            for (int col = 0; col < n; ++col) {
+                out[((size_t)b * n + r) * n + col].re = (r == col) ? 1 : 0;
+                out[((size_t)b * n + r) * n + col].im = 0;
+            }
+}
+
+// Host-pointer entry: stage the needed part of the amplitude stream, run, copy the result back.
+// step range [lo, hi) of each pulse; carr holds batch * amps arrays of pts points.
+template <typename T>
+Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned int pts, unsigned int amps, unsigned int batch,
+                                 unsigned long long lo, unsigned long long hi, bool whole, T *out) {
+    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    cudaSetDevice(c->device);
+    if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);   // parament.cpp:795-798
+    if (!out || (!carr && amps > 0 && pts > 0) || (int)amps > c->amps || batch == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    const unsigned long long N = effective_steps(c, pts);
+    if (whole) { lo = 0; hi = N; }
+    if (hi > N || lo > hi) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    const int n = c->dim;
+    c->stat_ms = 0; c->stat_launches = 0; c->stat_h2d = 0; c->stat_d2h = 0; c->stat_steps = hi - lo;
+
+    CallSpec s{};
+    s.amps = amps; s.batch = batch; s.dt = dt; s.nsteps = hi - lo; s.total_steps = N;
+    {   // the degree / dt check happens before any transfer, as in the reference (parament.cpp:804-807)
+        SeriesParams probe;
+        CallSpec s0 = s; s0.stride = 1;
+        Parament_ErrorCode ec = build_series(c, s0, probe);
+        if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
+    }
+    if (s.nsteps == 0 || c->Hnorm == 0.0) {   // nothing to propagate: identity (reference returns stale memory, SURVEY A-7)
+        write_identity(out, n, batch);
+        c->lastError = PARAMENT_STATUS_SUCCESS;
+        return PARAMENT_STATUS_SUCCESS;
+    }
+    const int r = points_per_step(c);
+    const size_t p_lo = (size_t)r * lo;
+    const size_t seg = (size_t)r * s.nsteps + point_overlap(c);   // raw points needed per control array
+    s.stride = seg;
+    const size_t arrays = (size_t)batch * amps;
+    const size_t in_bytes = arrays * seg * sizeof(T);
+    const size_t out_bytes = (size_t)batch * n * n * sizeof(T);
+    if (!ensure_dev(c->d_carr, in_bytes) || !ensure_dev(c->d_out, out_bytes)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
+    if (seg == pts) {
+        if (in_bytes && !PB_CUDA_OK(cudaMemcpyAsync(c->d_carr.ptr, carr, in_bytes, cudaMemcpyHostToDevice, c->stream)))
+            return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+    } else {
+        for (size_t a = 0; a < arrays; ++a)
+            if (!PB_CUDA_OK(cudaMemcpyAsync((T *)c->d_carr.ptr + a * seg, carr + a * pts + p_lo, seg * sizeof(T),
+                                            cudaMemcpyHostToDevice, c->stream)))
+                return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+    }
+    c->stat_h2d = (double)in_bytes;
+    Parament_ErrorCode ec = propagate_device(c, c->d_carr.ptr, s, c->d_out.ptr, c->stream);
+    if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
+    if (!PB_CUDA_OK(cudaMemcpyAsync(out, c->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, c->stream)) ||
+        !PB_CUDA_OK(cudaStreamSynchronize(c->stream)))
+        return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+    c->stat_d2h = (double)out_bytes;
+    c->lastError = PARAMENT_STATUS_SUCCESS;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+template <typename T>
+Parament_ErrorCode equiprop_device(Context *c, const T *carr_dev, double dt, unsigned int pts, unsigned int amps,
+                                   unsigned int batch, T *out_dev, void *stream) {
+    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    cudaSetDevice(c->device);
+    if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);
+    if (!out_dev || !carr_dev || (int)amps > c->amps || batch == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    const unsigned long long N = effective_steps(c, pts);
+    CallSpec s{};
+    s.amps = amps; s.batch = batch; s.dt = dt; s.nsteps = N; s.total_steps = N; s.stride = pts;
+    c->stat_ms = 0; c->stat_h2d = 0; c->stat_d2h = 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (N == 0 || c->Hnorm == 0.0) {
+        std::vector<T> id((size_t)batch * c->dim * c->dim);
+        write_identity(id.data(), c->dim, batch);
+        if (!PB_CUDA_OK(cudaMemcpyAsync(out_dev, id.data(), id.size() * sizeof(T), cudaMemcpyHostToDevice, st)) ||
+            !PB_CUDA_OK(cudaStreamSynchronize(st)))
+            return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+        c->lastError = PARAMENT_STATUS_SUCCESS;
+        return PARAMENT_STATUS_SUCCESS;
+    }
+    Parament_ErrorCode ec = propagate_device(c, carr_dev, s, out_dev, st);
+    if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
+    if (!stream && !PB_CUDA_OK(cudaStreamSynchronize(st))) return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+    c->lastError = PARAMENT_STATUS_SUCCESS;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+// out = parts[count-1] ... parts[0] on the device (multi-GPU combine of time slices)
+template <typename T>
+Parament_ErrorCode combine_host(Context *c, const T *parts, unsigned int count, T *out) {
+    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    cudaSetDevice(c->device);
+    if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);
+    if (!parts || !out || count == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    const int n = c->dim;
+    const int gp = k4_pad(n);   // the combine always runs on the GEMM kernels
+    const size_t gnn = (size_t)gp * gp;
+    // E-form copies in double, zero padded: E = P - I
+    std::vector<double2> padded((size_t)count * gnn, make_double2(0, 0));
+    for (unsigned int i = 0; i < count; ++i)
+        for (int r = 0; r < n; ++r)
+            for (int col = 0; col < n; ++col) {
+                const T v = parts[((size_t)i * n + r) * n + col];
+                padded[(size_t)i * gnn + (size_t)r * gp + col] = make_double2((double)v.re - (r == col ? 1.0 : 0.0), (double)v.im);
+            }
+    const double2 *src_host = padded.data();
+    DeviceBuffer a, b;
+    const size_t out_bytes = (size_t)n * n * sizeof(T);
+    if (!ensure_dev(a, (size_t)count * gnn * sizeof(double2)) || !ensure_dev(b, (size_t)(count / 2 + 1) * gnn * sizeof(double2)) ||
+        !ensure_dev(c->d_out, out_bytes)) {
+        free_dev(a); free_dev(b);
+        return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
+    }
+    Parament_ErrorCode ec = PARAMENT_STATUS_SUCCESS;
+    c->stat_launches = 0;
+    if (!PB_CUDA_OK(cudaMemcpyAsync(a.ptr, src_host, (size_t)count * gnn * sizeof(double2), cudaMemcpyHostToDevice, c->stream)))
+        ec = PARAMENT_STATUS_CUBLAS_FAILED;
+    if (ec == PARAMENT_STATUS_SUCCESS) ec = tree_reduce_all(c, (double2 *)a.ptr, (int)count, (double2 *)b.ptr, gp, c->stream);
+    if (ec == PARAMENT_STATUS_SUCCESS && k4_finish(c->fp64, (const double2 *)a.ptr, n, gp, c->d_out.ptr, true, c->stream) != cudaSuccess)
+        ec = PARAMENT_STATUS_CUBLAS_FAILED;
+    if (ec == PARAMENT_STATUS_SUCCESS &&
+        (!PB_CUDA_OK(cudaMemcpyAsync(out, c->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, c->stream)) ||
+         !PB_CUDA_OK(cudaStreamSynchronize(c->stream))))
+        ec = PARAMENT_STATUS_CUBLAS_FAILED;
+    cudaStreamSynchronize(c->stream);
+    free_dev(a); free_dev(b);
+    if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
+    c->lastError = PARAMENT_STATUS_SUCCESS;
+    return ec;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// exported C symbols
+// =====================================================================================================
+extern "C" {
+
+Parament_ErrorCode Parament_create(struct Parament_Context_f32 **h) { return create_ctx(reinterpret_cast<Context **>(h), false); }
+Parament_ErrorCode Parament_create_fp64(struct Parament_Context_f64 **h) { return create_ctx(reinterpret_cast<Context **>(h), true); }
+Parament_ErrorCode Parament_destroy(struct Parament_Context_f32 *h) { return destroy_ctx(h ? as_ctx(h) : nullptr); }
+Parament_ErrorCode Parament_destroy_fp64(struct Parament_Context_f64 *h) { return destroy_ctx(h ? as_ctx(h) : nullptr); }
+
+Parament_ErrorCode Parament_setHamiltonian(struct Parament_Context_f32 *h, const Parament_c64 *H0, const Parament_c64 *H1,
+                                           unsigned int dim, unsigned int amps, bool use_magnus, enum Parament_QuadratureSpec q) {
+    return set_hamiltonian<Parament_c64>(as_ctx(h), H0, H1, dim, amps, use_magnus, (int)q);
+}
+Parament_ErrorCode Parament_setHamiltonian_fp64(struct Parament_Context_f64 *h, const Parament_c128 *H0, const Parament_c128 *H1,
+                                                unsigned int dim, unsigned int amps, bool use_magnus, Parament_QuadratureSpec q) {
+    return set_hamiltonian<Parament_c128>(as_ctx(h), H0, H1, dim, amps, use_magnus, (int)q);
+}
+
+Parament_ErrorCode Parament_equiprop(struct Parament_Context_f32 *h, const Parament_c64 *carr, double dt, unsigned int pts,
+                                     unsigned int amps, Parament_c64 *out) {
+    return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, 1, 0, 0, true, out);
+}
+Parament_ErrorCode Parament_equiprop_fp64(struct Parament_Context_f64 *h, const Parament_c128 *carr, double dt, unsigned int pts,
+                                          unsigned int amps, Parament_c128 *out) {
+    return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, 1, 0, 0, true, out);
+}
+
+Parament_ErrorCode Parament_equipropBatch(struct Parament_Context_f32 *h, const Parament_c64 *carr, double dt, unsigned int pts,
+                                          unsigned int amps, unsigned int batch, Parament_c64 *out) {
+    return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, batch, 0, 0, true, out);
+}
+Parament_ErrorCode Parament_equipropBatch_fp64(struct Parament_Context_f64 *h, const Parament_c128 *carr, double dt, unsigned int pts,
+                                               unsigned int amps, unsigned int batch, Parament_c128 *out) {
+    return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, batch, 0, 0, true, out);
+}
+
+Parament_ErrorCode Parament_equipropDevice(struct Parament_Context_f32 *h, const Parament_c64 *carr_dev, double dt, unsigned int pts,
+                                           unsigned int amps, unsigned int batch, Parament_c64 *out_dev, void *stream) {
+    return equiprop_device<Parament_c64>(as_ctx(h), carr_dev, dt, pts, amps, batch, out_dev, stream);
+}
+Parament_ErrorCode Parament_equipropDevice_fp64(struct Parament_Context_f64 *h, const Parament_c128 *carr_dev, double dt, unsigned int pts,
+                                                unsigned int amps, unsigned int batch, Parament_c128 *out_dev, void *stream) {
+    return equiprop_device<Parament_c128>(as_ctx(h), carr_dev, dt, pts, amps, batch, out_dev, stream);
+}
+
+Parament_ErrorCode Parament_equipropSlice(struct Parament_Context_f32 *h, const Parament_c64 *carr, double dt, unsigned int pts,
+                                          unsigned int amps, unsigned long long lo, unsigned long long hi, Parament_c64 *out) {
+    return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, 1, lo, hi, false, out);
+}
+Parament_ErrorCode Parament_equipropSlice_fp64(struct Parament_Context_f64 *h, const Parament_c128 *carr, double dt, unsigned int pts,
+                                               unsigned int amps, unsigned long long lo, unsigned long long hi, Parament_c128 *out) {
+    return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, 1, lo, hi, false, out);
+}
+
+Parament_ErrorCode Parament_combine(struct Parament_Context_f32 *h, const Parament_c64 *parts, unsigned int count, Parament_c64 *out) {
+    return combine_host<Parament_c64>(as_ctx(h), parts, count, out);
+}
+Parament_ErrorCode Parament_combine_fp64(struct Parament_Context_f64 *h, const Parament_c128 *parts, unsigned int count, Parament_c128 *out) {
+    return combine_host<Parament_c128>(as_ctx(h), parts, count, out);
+}
+
+int Parament_selectIterationCycles_fp32(double H_norm, double dt) { return select_cycles_fp32(H_norm, dt); }
+int Parament_selectIterationCycles_fp64(double H_norm, double dt) { return select_cycles_fp64(H_norm, dt); }
+
+static Parament_ErrorCode set_cycles(Context *c, unsigned int cycles) {   // parament.cpp:772-776
+    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    c->MMAX = (int)cycles;
+    c->MMAX_manual = true;
+    return PARAMENT_STATUS_SUCCESS;
+}
+static Parament_ErrorCode auto_cycles(Context *c) {   // parament.cpp:782-786
+    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    c->MMAX = 11;
+    c->MMAX_manual = false;
+    return PARAMENT_STATUS_SUCCESS;
+}
+Parament_ErrorCode Parament_setIterationCyclesManually(struct Parament_Context_f32 *h, unsigned int cycles) { return set_cycles(as_ctx(h), cycles); }
+Parament_ErrorCode Parament_setIterationCyclesManually_fp64(struct Parament_Context_f64 *h, unsigned int cycles) { return set_cycles(as_ctx(h), cycles); }
+Parament_ErrorCode Parament_automaticIterationCycles(struct Parament_Context_f32 *h) { return auto_cycles(as_ctx(h)); }
+Parament_ErrorCode Parament_automaticIterationCycles_fp64(struct Parament_Context_f64 *h) { return auto_cycles(as_ctx(h)); }
+
+Parament_ErrorCode Parament_peekAtLastError(struct Parament_Context_f32 *h) { Context *c = as_ctx(h); return c ? c->lastError : PARAMENT_STATUS_INVALID_VALUE; }
+Parament_ErrorCode Parament_peekAtLastError_fp64(struct Parament_Context_f64 *h) { Context *c = as_ctx(h); return c ? c->lastError : PARAMENT_STATUS_INVALID_VALUE; }
+Parament_ErrorCode Parament_getLastError(void *h) { Context *c = as_ctx(h); return c ? c->lastError : PARAMENT_STATUS_INVALID_VALUE; }
+
+const char *Parament_errorMessage(Parament_ErrorCode errorCode) {   // strings byte-identical to parament.cpp:859-882
+    switch (errorCode) {
+        case PARAMENT_STATUS_SUCCESS: return "Success";
+        case PARAMENT_STATUS_HOST_ALLOC_FAILED: return "Memory allocation on the host failed.";
+        case PARAMENT_STATUS_DEVICE_ALLOC_FAILED: return "Memory allocation on the device failed.";
+        case PARAMENT_STATUS_CUBLAS_INIT_FAILED: return "Failed to initialize the cuBLAS library.";
+        case PARAMENT_STATUS_INVALID_VALUE: return "Invalid value.";
+        case PARAMENT_STATUS_CUBLAS_FAILED: return "Failed to execute cuBLAS function.";
+        case PARAMENT_STATUS_SELECT_SMALLER_DT: return "Timestep too large";
+        case PARAMENT_STATUS_INVALID_QUADRATURE_SELECTION: return "Invalid quadrature selection.";
+        case PARAMENT_STATUS_NO_HAMILTONIAN: return "No hamiltonian set";
+        default: return "Unknown error code";
+    }
+}
+
+double OneNorm(const Parament_c64 *mat, unsigned int dim) { return one_norm_t<Parament_c64>(mat, dim); }
+double OneNorm_fp64(const Parament_c128 *mat, unsigned int dim) { return one_norm_t<Parament_c128>(mat, dim); }
+
+void device_info(void) {   // same table as deviceInfo.c:30-59
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        printf("Failed to query the number of CUDA devices. Error code: %d\n", (int)e);
+        cudaGetLastError();
+        return;
+    }
+    printf("PARAMENT_INFO:\nTotal number of CUDA devices: %d\n-----------------------------------\n", n);
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) != cudaSuccess) {
+            printf("Failed to query device properties.\n");
+            return;
+        }
+        printf("Device Number: %d\n  Device name: %s\n", i, prop.name);
+        printf("  Memory Clock Rate (KHz): %d\n  Memory Bus Width (bits): %d\n", prop.memoryClockRate, prop.memoryBusWidth);
+        printf("  Peak Memory Bandwidth (GB/s): %f\n", 2.0 * prop.memoryClockRate * (prop.memoryBusWidth / 8) / 1.0e6);
+        printf("  Total global memory: %zd MB\n\n", prop.totalGlobalMem / 1024 / 1024);
+    }
+    fflush(stdout);
+}
+
+double Parament_lastStat(void *h, int key) {
+    Context *c = as_ctx(h);
+    if (!c) return -1.0;
+    switch (key) {
+        case 0: {
+            float ms = 0;
+            cudaSetDevice(c->device);
+            if (cudaEventSynchronize(c->ev_stop) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) == cudaSuccess) return ms;
+            cudaGetLastError();
+            return -1.0;
+        }
+        case 1: return (double)c->stat_launches;
+        case 2: return c->stat_M_used;
+        case 3: return c->stat_M_ref;
+        case 4: return (double)c->stat_steps;
+        case 5: return c->family;
+        case 6: return c->stat_h2d;
+        case 7: return c->stat_d2h;
+        case 8: return c->Hnorm;
+        default: return -1.0;
+    }
+}
+
+Parament_ErrorCode Parament_setDevice(void *h, int device) {
+    Context *c = as_ctx(h);
+    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    if (device == c->device) return PARAMENT_STATUS_SUCCESS;
+    // move: drop everything that lives on the old device
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
+    free_dev(c->d_Y); free_dev(c->d_S0); free_dev(c->d_S1); free_dev(c->d_pending); free_dev(c->d_tree);
+    cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); cudaStreamDestroy(c->stream);
+    c->device = device;
+    c->have_hamiltonian = false;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess)
+        return fail(c, PARAMENT_STATUS_CUBLAS_INIT_FAILED);
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+const char *Parament_version(void) { return "parament-b200 0.1 (sm_100a, FP64 tensor pipe)"; }
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+// coef.cuh -- effective control coefficients of one time step, evaluated on the fly from the raw
+// amplitude stream (replaces the reference's separate quadrature kernels + c2 array,
+// control_expansion.cu:27-160 / parament.cpp:510-538).  Inputs are converted to double exactly; the
+// arithmetic is double for both context precisions.
+#pragma once
+#include "params.hpp"
+
+namespace pb {
+
+__device__ __forceinline__ cplx ld_amp(const float2 *p) { const float2 v = __ldg(p); return cplx{(double)v.x, (double)v.y}; }
+__device__ __forceinline__ cplx ld_amp(const double2 *p) { const double2 v = __ldg(p); return cplx{v.x, v.y}; }
+
+// `c` points at the first control array of the pulse; arrays are `pts` apart.  j is the effective step.
+template <typename IO>
+__device__ __forceinline__ cplx step_coefficient(const Term &t, const IO *__restrict__ c, unsigned int pts, int quad,
+                                                 double magfac, unsigned long long j) {
+    const IO *ca = c + (size_t)t.j * pts;
+    if (t.type == TERM_PLAIN) {
+        if (quad == QUAD_NONE) return ld_amp(ca + j);
+        if (quad == QUAD_MIDPOINT) {
+            const cplx u = ld_amp(ca + j), v = ld_amp(ca + j + 1);
+            return cplx{0.5 * (u.re + v.re), 0.5 * (u.im + v.im)};
+        }
+        const cplx u = ld_amp(ca + 2 * j), v = ld_amp(ca + 2 * j + 1), w = ld_amp(ca + 2 * j + 2);
+        // true division: a pre-rounded 1/6 would bias every step the same way
+        return cplx{((u.re + 4.0 * v.re) + w.re) / 6.0, ((u.im + 4.0 * v.im) + w.im) / 6.0};
+    }
+    if (t.type == TERM_MAG_DRIFT) {
+        const cplx u = ld_amp(ca + 2 * j), w = ld_amp(ca + 2 * j + 2);
+        const double dr = w.re - u.re, di = w.im - u.im;
+        return cplx{-di * magfac, dr * magfac};   // (w - u) * i * h/12
+    }
+    // TERM_MAG_PAIR
+    const IO *cb = c + (size_t)t.k * pts;
+    const cplx a0 = ld_amp(ca + 2 * j), a2 = ld_amp(ca + 2 * j + 2);
+    const cplx b0 = ld_amp(cb + 2 * j), b2 = ld_amp(cb + 2 * j + 2);
+    const double vr = (a0.re * b2.re - a0.im * b2.im) - (a2.re * b0.re - a2.im * b0.im);
+    const double vi = (a0.re * b2.im + a0.im * b2.re) - (a2.re * b0.im + a2.im * b0.re);
+    return cplx{-vi * magfac, vr * magfac};
+}
+
+}  // namespace pb

@@ -1,0 +1,60 @@
+// context.hpp -- the opaque Parament context of this library (reference: parament_context.hpp:26-78, which
+// holds a cuBLAS handle and three dim^2 x pts work arrays; none of that exists here).
+#pragma once
+#include <complex>
+#include <cstddef>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/parament.h"
+#include "params.hpp"
+
+namespace pb {
+
+typedef std::complex<double> zc;
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct Context {
+    unsigned int magic = 0x50423230;   // "PB20"
+    bool fp64 = false;                 // context precision of the I/O operands
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    Parament_ErrorCode lastError = PARAMENT_STATUS_SUCCESS;
+
+    // options (reference: parament_context.hpp:72-77)
+    int MMAX = 11;
+    bool MMAX_manual = false;
+    bool enable_magnus = false;
+    int quadrature = PARAMENT_QUADRATURE_NONE;
+
+    // Hamiltonian (host copies in double, exact conversions of the inputs)
+    bool have_hamiltonian = false;
+    int dim = 0;
+    int amps = 0;        // controls given to setHamiltonian
+    int nmats = 0;       // 1 + amps (+ amps + amps(amps-1)/2 commutators with Magnus)
+    double Hnorm = 0.0;
+    std::vector<zc> mats;   // nmats * dim * dim, row-major
+    int family = 0;      // 1 = register-resident warp kernels, 3 = batched GEMM pipeline
+    int npad = 0;
+    DeviceBuffer d_H;    // family 1: fragment-ordered table; family 3: padded row-major table
+
+    // per-call scratch (grow-only)
+    DeviceBuffer d_carr, d_out, d_partials;
+    DeviceBuffer d_Y, d_S0, d_S1, d_pending, d_tree;   // family 3
+    void *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for carr
+    void *h_out = nullptr;   size_t h_out_bytes = 0;    // pinned staging for results
+
+    // statistics of the last equiprop (Parament_lastStat)
+    double stat_ms = 0.0;
+    long long stat_launches = 0;
+    int stat_M_used = 0, stat_M_ref = 0;
+    unsigned long long stat_steps = 0;
+    double stat_h2d = 0.0, stat_d2h = 0.0;
+};
+
+}  // namespace pb

@@ -1,0 +1,184 @@
+// frag.cuh -- complex FP64 matrix fragments on the DMMA (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4) pipe.
+//
+// All arithmetic of this library is done in double precision on the FP64 tensor pipe, for complex64 and
+// complex128 contexts alike (DESIGN.md "Numerics": a float leaf cannot hold 1e-5 over 5e5 steps).
+// A warp owns whole (8*NT)x(8*NT) complex matrices in registers.  Two register layouts exist:
+//
+//   AccFrag  (accumulator / left-operand layout).  lane = 4*g + q, g = lane>>2, q = lane&3.
+//            element (mt, nt, i)  <->  row 8*mt + g, column 8*nt + 2*q + i.
+//            This is the C/D layout of m8n8k4.  Read column-slot-wise it is ALSO a legal A operand:
+//            the A fragment of k-tile kt = 2*nt + i is the register (mt, nt, i), i.e. the contraction
+//            index is enumerated in the permuted order  slot q of k-tile kt  <->  column 8*(kt>>1)+2*q+(kt&1).
+//   BFrag    (right-operand layout) built for that same permuted contraction order:
+//            element (kt, nt)  <->  row 8*(kt>>1) + 2*q + (kt&1), column 8*nt + g.
+//
+// Consequences used everywhere: (1) the result of  C = A*B  can be fed back as the left operand of
+// the next product with no data movement (Clenshaw recurrence  B_k = B_{k+1}*Y - B_{k+2} + a_k I);
+// (2) the transpose of an AccFrag matrix IS a BFrag of the same registers
+// (BFrag(E^T)(kt, nt) == AccFrag(E)(nt, kt>>1, kt&1)), so the running product Q <- Q * U^T needs no
+// shuffles either.  Q accumulates the transposed propagator.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pb {
+
+struct cplx { double re, im; };
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NT>
+struct AccFrag {
+    double re[NT][NT][2];
+    double im[NT][NT][2];
+};
+
+template <int NT>
+struct BFrag {
+    double re[2 * NT][NT];
+    double im[2 * NT][NT];
+    double nim[2 * NT][NT];   // -im: DMMA has no operand negation
+};
+
+// row / column of AccFrag element (mt, nt, i) for this lane
+__device__ __forceinline__ int acc_row(int lane, int mt) { return 8 * mt + (lane >> 2); }
+__device__ __forceinline__ int acc_col(int lane, int nt, int i) { return 8 * nt + 2 * (lane & 3) + i; }
+// row / column of BFrag element (kt, nt) for this lane
+__device__ __forceinline__ int bf_row(int lane, int kt) { return 8 * (kt >> 1) + 2 * (lane & 3) + (kt & 1); }
+__device__ __forceinline__ int bf_col(int lane, int nt) { return 8 * nt + (lane >> 2); }
+
+// C += A * B   (complex, 4 real DMMA products per tile triple)
+template <int NT>
+__device__ __forceinline__ void cmma(AccFrag<NT> &C, const AccFrag<NT> &A, const BFrag<NT> &B) {
+#pragma unroll
+    for (int kt = 0; kt < 2 * NT; ++kt) {
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) {
+            const double are = A.re[mt][kt >> 1][kt & 1];
+            const double aim = A.im[mt][kt >> 1][kt & 1];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                dmma884(C.re[mt][nt][0], C.re[mt][nt][1], are, B.re[kt][nt]);
+                dmma884(C.im[mt][nt][0], C.im[mt][nt][1], are, B.im[kt][nt]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                dmma884(C.re[mt][nt][0], C.re[mt][nt][1], aim, B.nim[kt][nt]);
+                dmma884(C.im[mt][nt][0], C.im[mt][nt][1], aim, B.re[kt][nt]);
+            }
+        }
+    }
+}
+
+// BFrag of E^T from the registers of AccFrag E (no data movement, see header comment)
+template <int NT>
+__device__ __forceinline__ void transpose_as_bfrag(BFrag<NT> &B, const AccFrag<NT> &E) {
+#pragma unroll
+    for (int kt = 0; kt < 2 * NT; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            B.re[kt][nt] = E.re[nt][kt >> 1][kt & 1];
+            B.im[kt][nt] = E.im[nt][kt >> 1][kt & 1];
+            B.nim[kt][nt] = -E.im[nt][kt >> 1][kt & 1];
+        }
+}
+
+template <int NT>
+__device__ __forceinline__ void set_identity(AccFrag<NT> &Q, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                Q.re[mt][nt][i] = (mt == nt && g == 2 * q + i) ? 1.0 : 0.0;
+                Q.im[mt][nt][i] = 0.0;
+            }
+}
+
+template <int NT>
+__device__ __forceinline__ void set_zero(AccFrag<NT> &Q) {
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { Q.re[mt][nt][i] = 0.0; Q.im[mt][nt][i] = 0.0; }
+}
+
+// S <- alpha * S + beta * I     (alpha real, beta complex)
+template <int NT>
+__device__ __forceinline__ void scale_add_diag(AccFrag<NT> &S, double alpha, cplx beta, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool diag = (mt == nt && g == 2 * q + i);
+                S.re[mt][nt][i] = alpha * S.re[mt][nt][i] + (diag ? beta.re : 0.0);
+                S.im[mt][nt][i] = alpha * S.im[mt][nt][i] + (diag ? beta.im : 0.0);
+            }
+}
+
+// S <- a * Y + b * I   (a, b complex)
+template <int NT>
+__device__ __forceinline__ void axpb_diag(AccFrag<NT> &S, cplx a, const AccFrag<NT> &Y, cplx b, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool diag = (mt == nt && g == 2 * q + i);
+                const double yr = Y.re[mt][nt][i], yi = Y.im[mt][nt][i];
+                S.re[mt][nt][i] = a.re * yr - a.im * yi + (diag ? b.re : 0.0);
+                S.im[mt][nt][i] = a.re * yi + a.im * yr + (diag ? b.im : 0.0);
+            }
+}
+
+// ---- memory <-> fragment, matrices stored row-major as interleaved complex doubles with pitch ld ----
+template <int NT>
+__device__ __forceinline__ void load_acc(AccFrag<NT> &Q, const double2 *m, int ld, int lane) {
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double2 v = m[acc_row(lane, mt) * ld + acc_col(lane, nt, i)];
+                Q.re[mt][nt][i] = v.x;
+                Q.im[mt][nt][i] = v.y;
+            }
+}
+
+template <int NT>
+__device__ __forceinline__ void store_acc(const AccFrag<NT> &Q, double2 *m, int ld, int lane) {
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                m[acc_row(lane, mt) * ld + acc_col(lane, nt, i)] = make_double2(Q.re[mt][nt][i], Q.im[mt][nt][i]);
+}
+
+template <int NT>
+__device__ __forceinline__ void load_bfrag(BFrag<NT> &B, const double2 *m, int ld, int lane) {
+#pragma unroll
+    for (int kt = 0; kt < 2 * NT; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const double2 v = m[bf_row(lane, kt) * ld + bf_col(lane, nt)];
+            B.re[kt][nt] = v.x;
+            B.im[kt][nt] = v.y;
+            B.nim[kt][nt] = -v.y;
+        }
+}
+
+}  // namespace pb

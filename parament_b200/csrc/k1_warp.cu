@@ -1,0 +1,241 @@
+// k1_warp.cu -- kernels (1)-(3) of the north_star for dim <= 16: everything register-resident.
+//
+//  k1_chain_kernel   one warp walks a contiguous chunk of effective time steps.  Per step it assembles
+//                    Y = sigma * (H0 + sum_t c_t H_t) from the raw amplitude stream (quadrature / Magnus
+//                    coefficients evaluated on the fly, coef.cuh), runs the Chebyshev/Bessel series by the
+//                    Clenshaw recurrence  B_k = B_{k+1} Y - B_{k+2} + a_k I  with every matrix product on
+//                    the FP64 tensor pipe (frag.cuh: no shared memory, no shuffles, nothing written to
+//                    HBM), and multiplies the step into the warp's running product.            [kernel 1]
+//                    The warps of a CTA then combine their chunk products in order through shared memory
+//                    and write ONE partial propagator per CTA.                                  [kernel 2]
+//  k3_reduce_kernel  ordered reduction of the per-CTA partials of each pulse, transposition to the
+//                    row-major physical propagator and conversion to the context precision.    [kernel 3]
+//
+// Replaces parament.cpp:486-718 (equipropExpand / equipropPropagate / equipropReduce) and
+// control_expansion.cu / diagonal_add.cu for these dimensions.  The running product is kept transposed,
+// Q = (U_{hi-1} ... U_lo)^T = U_lo^T ... U_{hi-1}^T, see frag.cuh.
+#include "coef.cuh"
+#include "k1_warp.hpp"
+
+namespace pb {
+
+constexpr int K1_WARPS = 4;   // warps per CTA of the chain kernel
+
+// Ordered in-CTA product: afterwards warp 0 holds Q_0 Q_1 ... Q_{nwarps-1}.  smem: (nwarps/2) matrices.
+template <int NT>
+__device__ __forceinline__ void cta_ordered_product(AccFrag<NT> &Q, double2 *smem, int warp, int nwarps, int lane) {
+    constexpr int NP = 8 * NT;
+    for (int stride = 1; stride < nwarps; stride <<= 1) {
+        const int mask = 2 * stride - 1;
+        const int slot = warp / (2 * stride);
+        if ((warp & mask) == stride) store_acc<NT>(Q, smem + slot * NP * NP, NP, lane);
+        __syncthreads();
+        if ((warp & mask) == 0 && warp + stride < nwarps) {
+            BFrag<NT> B;
+            load_bfrag<NT>(B, smem + slot * NP * NP, NP, lane);
+            AccFrag<NT> R;
+            set_zero<NT>(R);
+            cmma<NT>(R, Q, B);
+            Q = R;
+        }
+        __syncthreads();
+    }
+}
+
+// Hfrag layout: [matrix][layout 0 = AccFrag order, 1 = BFrag order][element e < 2*NT*NT][lane] as double2.
+template <int NT, typename IO>
+__global__ void __launch_bounds__(32 * K1_WARPS, (NT == 1) ? 6 : 3)
+k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ Hfrag,
+                double2 *__restrict__ partials, unsigned int batch, unsigned int chunks_per_pulse,
+                unsigned long long step_lo, unsigned long long step_hi, int reduce_in_cta) {
+    constexpr int NP = 8 * NT;
+    constexpr int NE = 2 * NT * NT;   // fragment elements per lane and layout
+    __shared__ double2 smem[(K1_WARPS / 2) * NP * NP];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * K1_WARPS + warp;
+    const unsigned int pulse = (unsigned int)(gw / chunks_per_pulse);
+    const unsigned int chunk = (unsigned int)(gw % chunks_per_pulse);
+    const bool active = pulse < batch;
+
+    AccFrag<NT> Q;
+    set_identity<NT>(Q, lane);
+
+    if (active) {
+        const unsigned long long nsteps = step_hi - step_lo;
+        const unsigned long long lo = step_lo + nsteps * chunk / chunks_per_pulse;
+        const unsigned long long hi = step_lo + nsteps * (chunk + 1) / chunks_per_pulse;
+        const IO *c = carr + (size_t)pulse * p.amps_in * p.pts;
+        const double2 *HA = Hfrag + lane;             // + (mat * 2 + 0) * NE * 32 + e * 32
+        const int M = p.M;
+
+        for (unsigned long long j = lo; j < hi; ++j) {
+            // ---- assemble X = H0 + sum_t c_t H_t in both register layouts, then Y = sigma X ----
+            AccFrag<NT> Ya;
+            BFrag<NT> Yb;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const double2 ha = __ldg(HA + e * 32);
+                const double2 hb = __ldg(HA + (NE + e) * 32);
+                (&Ya.re[0][0][0])[e] = ha.x; (&Ya.im[0][0][0])[e] = ha.y;
+                (&Yb.re[0][0])[e] = hb.x;    (&Yb.im[0][0])[e] = hb.y;
+            }
+            for (int t = 0; t < p.nterms; ++t) {
+                const cplx ct = step_coefficient<IO>(p.terms[t], c, p.pts, p.quad, p.magfac, j);
+                const double2 *Ht = HA + (size_t)p.terms[t].mat * 2 * NE * 32;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const double2 ha = __ldg(Ht + e * 32);
+                    const double2 hb = __ldg(Ht + (NE + e) * 32);
+                    (&Ya.re[0][0][0])[e] += ct.re * ha.x - ct.im * ha.y;
+                    (&Ya.im[0][0][0])[e] += ct.re * ha.y + ct.im * ha.x;
+                    (&Yb.re[0][0])[e] += ct.re * hb.x - ct.im * hb.y;
+                    (&Yb.im[0][0])[e] += ct.re * hb.y + ct.im * hb.x;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                (&Ya.re[0][0][0])[e] *= p.sigma; (&Ya.im[0][0][0])[e] *= p.sigma;
+                (&Yb.re[0][0])[e] *= p.sigma;    (&Yb.im[0][0])[e] *= p.sigma;
+                (&Yb.nim[0][0])[e] = -(&Yb.im[0][0])[e];
+            }
+
+            // ---- Clenshaw in E-form: E = U - I = a0' I + B_1 Y - 2 B_2 ----
+            AccFrag<NT> S0, S1;
+            if (M == 1) {
+                axpb_diag<NT>(S1, p.a[1], Ya, p.a[0], lane);
+            } else {
+                axpb_diag<NT>(S0, p.a[M], Ya, p.a[M - 1], lane);      // B_{M-1}
+                set_zero<NT>(S1);
+                scale_add_diag<NT>(S1, 0.0, p.a[M], lane);            // B_M
+                for (int k = M - 2; k >= 1; --k) {
+                    scale_add_diag<NT>(S1, -1.0, p.a[k], lane);       // a_k I - B_{k+2}
+                    cmma<NT>(S1, S0, Yb);                             // + B_{k+1} Y
+                    const AccFrag<NT> T = S0; S0 = S1; S1 = T;
+                }
+                scale_add_diag<NT>(S1, -2.0, p.a[0], lane);           // a0' I - 2 B_2
+                cmma<NT>(S1, S0, Yb);                                 // + B_1 Y   -> E
+            }
+
+            // ---- running product  Q <- Q (I + E)^T = Q + Q E^T ----
+            BFrag<NT> Et;
+            transpose_as_bfrag<NT>(Et, S1);
+            AccFrag<NT> Qn = Q;
+            cmma<NT>(Qn, Q, Et);
+            Q = Qn;
+        }
+    }
+
+    if (reduce_in_cta) {
+        cta_ordered_product<NT>(Q, smem, warp, K1_WARPS, lane);
+        if (warp == 0 && active) {
+            const unsigned int nb = chunks_per_pulse / K1_WARPS;
+            store_acc<NT>(Q, partials + ((size_t)pulse * nb + chunk / K1_WARPS) * NP * NP, NP, lane);
+        }
+    } else if (active) {
+        store_acc<NT>(Q, partials + ((size_t)pulse * chunks_per_pulse + chunk) * NP * NP, NP, lane);
+    }
+}
+
+// One CTA per pulse: ordered product of its nb partials, then out[r][c] = Q[c][r] in the IO precision.
+template <int NT, typename IO>
+__global__ void __launch_bounds__(256)
+k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, int n, IO *__restrict__ out) {
+    constexpr int NP = 8 * NT;
+    __shared__ double2 smem[4 * NP * NP];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const unsigned int pulse = blockIdx.x;
+    const double2 *P = partials + (size_t)pulse * nb * NP * NP;
+
+    const unsigned int b0 = (unsigned int)((unsigned long long)nb * warp / nwarps);
+    const unsigned int b1 = (unsigned int)((unsigned long long)nb * (warp + 1) / nwarps);
+    AccFrag<NT> Q;
+    if (b0 < b1) {
+        load_acc<NT>(Q, P + (size_t)b0 * NP * NP, NP, lane);
+        for (unsigned int b = b0 + 1; b < b1; ++b) {
+            BFrag<NT> B;
+            load_bfrag<NT>(B, P + (size_t)b * NP * NP, NP, lane);
+            AccFrag<NT> R;
+            set_zero<NT>(R);
+            cmma<NT>(R, Q, B);
+            Q = R;
+        }
+    } else {
+        set_identity<NT>(Q, lane);
+    }
+    cta_ordered_product<NT>(Q, smem, warp, nwarps, lane);
+    if (warp == 0) {
+        IO *o = out + (size_t)pulse * n * n;
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r = acc_row(lane, mt), cidx = acc_col(lane, nt, i);
+                    if (r < n && cidx < n) {
+                        IO v;
+                        v.x = Q.re[mt][nt][i];
+                        v.y = Q.im[mt][nt][i];
+                        o[(size_t)cidx * n + r] = v;   // transpose back: P = Q^T
+                    }
+                }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+template <int NT, typename IO>
+static cudaError_t launch_k1_t(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
+                               unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
+                               unsigned long long step_hi, IO *out, cudaStream_t stream) {
+    k1_chain_kernel<NT, IO><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
+                                                                      plan.chunks_per_pulse, step_lo, step_hi,
+                                                                      plan.reduce_in_cta);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k3_reduce_kernel<NT, IO><<<batch, 32 * plan.k3_warps, 0, stream>>>(partials, plan.partials_per_pulse, p.n, out);
+    return cudaGetLastError();
+}
+
+K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms) {
+    K1Plan plan{};
+    const int ctas_per_sm = (npad == 8) ? 6 : 3;
+    const unsigned long long warps_total = (unsigned long long)num_sms * ctas_per_sm * K1_WARPS;
+    if (batch >= warps_total / 2 || nsteps < 2ull * K1_WARPS) {
+        plan.chunks_per_pulse = 1;                 // a warp owns a whole pulse
+        plan.reduce_in_cta = 0;
+        plan.partials_per_pulse = 1;
+    } else {
+        unsigned long long ctas_per_pulse = (warps_total / K1_WARPS + batch - 1) / batch;
+        // keep at least ~8 steps per warp so the identity-start product stays a small fraction
+        const unsigned long long max_ctas = (nsteps / 8 + K1_WARPS - 1) / K1_WARPS;
+        if (ctas_per_pulse > max_ctas) ctas_per_pulse = max_ctas;
+        if (ctas_per_pulse < 1) ctas_per_pulse = 1;
+        plan.chunks_per_pulse = (unsigned int)(ctas_per_pulse * K1_WARPS);
+        plan.reduce_in_cta = 1;
+        plan.partials_per_pulse = (unsigned int)ctas_per_pulse;
+    }
+    const unsigned long long total_warps = (unsigned long long)batch * plan.chunks_per_pulse;
+    plan.grid = (unsigned int)((total_warps + K1_WARPS - 1) / K1_WARPS);
+    plan.k3_warps = plan.partials_per_pulse >= 64 ? 8 : (plan.partials_per_pulse >= 8 ? 4 : 1);
+    plan.partial_elems = (size_t)batch * plan.partials_per_pulse * npad * npad;
+    return plan;
+}
+
+cudaError_t launch_k1(int npad, bool fp64_io, const SeriesParams &p, const void *carr, const double2 *Hfrag,
+                      double2 *partials, unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
+                      unsigned long long step_hi, void *out, cudaStream_t stream) {
+    if (npad == 8) {
+        return fp64_io ? launch_k1_t<1, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, (double2 *)out, stream)
+                       : launch_k1_t<1, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, (float2 *)out, stream);
+    }
+    return fp64_io ? launch_k1_t<2, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, (double2 *)out, stream)
+                   : launch_k1_t<2, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, (float2 *)out, stream);
+}
+
+}  // namespace pb

@@ -1,0 +1,255 @@
+// k4_gemm.cu -- kernel (4) of the north_star: dense complex FP64 contraction for dim > 16.
+//
+// A time chunk of S steps is processed as a batch that stays L2-resident:
+//   k4_assemble_kernel   Y_s = sigma (H0 + sum_t c_t(s) H_t),  S0_s = a_M Y_s + a_{M-1} I,  S1_s = a_M I
+//                        (fuses the reference's outer-product broadcast, quadrature kernels and rank-A' GEMM,
+//                        parament.cpp:491-554, with the first, algorithmically free, Clenshaw step)
+//   k4_zgemm_kernel      D_s = A_s B_s + beta1 C1_s + beta2 C2_s + gamma I   on the FP64 tensor pipe
+//                        (mma.sync.m8n8k4.f64), cp.async multi-stage shared-memory pipeline, Clenshaw
+//                        epilogue (-B_{k+2}, +a_k I; reference: a separate diagonal_add launch per
+//                        iteration, diagonal_add.cu:21-51) and the E-form pair product
+//                        E_b + E_a + E_b E_a of the ordered reduction (parament.cpp:657-718) fused in.
+// Replaces cublasZgemmStridedBatched at parament.cpp:596-605,627-636,681-690.
+#include "coef.cuh"
+#include "k4_gemm.hpp"
+
+namespace pb {
+
+constexpr int K4_BK = 16;       // contraction depth per pipeline stage
+constexpr int K4_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int BM, int BN>
+struct K4Smem {
+    static constexpr int PA = K4_BK + 4;   // pitch of the A tile in double2: 8 lanes of an LDS.128 phase hit 8 bank groups
+    static constexpr int PB = BN + 2;      // pitch of the B tile
+    static constexpr int A_ELEMS = BM * PA;
+    static constexpr int B_ELEMS = K4_BK * PB;
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr size_t BYTES = (size_t)K4_STAGES * STAGE_ELEMS * sizeof(double2);
+};
+
+template <int BM, int BN, int WM, int WN>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+k4_zgemm_kernel(const GemmArgs g) {
+    using SM = K4Smem<BM, BN>;
+    constexpr int NTHREADS = (BM / WM) * (BN / WN) * 32;
+    constexpr int MT = WM / 8, NTL = WN / 8;
+    extern __shared__ __align__(16) unsigned char k4_smem_raw[];
+    double2 *smem = reinterpret_cast<double2 *>(k4_smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, q = lane & 3;
+    const int tiles_n = g.n / BN;
+    const int tile_m = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
+    const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
+    const long long b = blockIdx.y;
+
+    const double2 *A = g.A + b * g.strideA + (size_t)tile_m * BM * g.n;   // rows tile_m*BM.., all k
+    const double2 *B = g.B + b * g.strideB + (size_t)tile_n * BN;         // all k, cols tile_n*BN..
+
+    auto load_stage = [&](int stage, int k0) {
+        double2 *sA = smem + stage * SM::STAGE_ELEMS;
+        double2 *sB = sA + SM::A_ELEMS;
+        for (int e = tid; e < BM * K4_BK; e += NTHREADS) {
+            const int r = e / K4_BK, c = e % K4_BK;
+            cp_async16(sA + r * SM::PA + c, A + (size_t)r * g.n + k0 + c);
+        }
+        for (int e = tid; e < K4_BK * BN; e += NTHREADS) {
+            const int r = e / BN, c = e % BN;
+            cp_async16(sB + r * SM::PB + c, B + (size_t)(k0 + r) * g.n + c);
+        }
+    };
+
+    double cre[MT][NTL][2], cim[MT][NTL][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt) { cre[mt][nt][0] = cre[mt][nt][1] = 0.0; cim[mt][nt][0] = cim[mt][nt][1] = 0.0; }
+
+    const int nk = g.n / K4_BK;
+#pragma unroll
+    for (int s = 0; s < K4_STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s * K4_BK);
+        cp_async_commit();
+    }
+    for (int ks = 0; ks < nk; ++ks) {
+        cp_async_wait<K4_STAGES - 2>();
+        __syncthreads();
+        {   // prefetch stage ks + STAGES - 1 into the buffer consumed in iteration ks - 1
+            const int nxt = ks + K4_STAGES - 1;
+            if (nxt < nk) load_stage(nxt % K4_STAGES, nxt * K4_BK);
+            cp_async_commit();
+        }
+        const double2 *sA = smem + (ks % K4_STAGES) * SM::STAGE_ELEMS;
+        const double2 *sB = sA + SM::A_ELEMS;
+#pragma unroll
+        for (int kt = 0; kt < K4_BK / 4; ++kt) {
+            double2 af[MT], bf[NTL];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) af[mt] = sA[(wm0 + 8 * mt + gq) * SM::PA + 4 * kt + q];
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) bf[nt] = sB[(4 * kt + q) * SM::PB + wn0 + 8 * nt + gq];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].x, bf[nt].x);
+                    dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].x, bf[nt].y);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].y, -bf[nt].y);
+                    dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].y, bf[nt].x);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: D = acc + beta1 C1 + beta2 C2 + gamma I ----
+    const size_t row0 = (size_t)tile_m * BM + wm0, col0 = (size_t)tile_n * BN + wn0;
+    double2 *D = g.D + b * g.strideD;
+    const double2 *C1 = g.C1 ? g.C1 + b * g.strideC1 : nullptr;
+    const double2 *C2 = g.C2 ? g.C2 + b * g.strideC2 : nullptr;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt) {
+            const size_t r = row0 + 8 * mt + gq, c = col0 + 8 * nt + 2 * q;
+            const size_t off = r * g.n + c;
+            double v0r = cre[mt][nt][0], v0i = cim[mt][nt][0], v1r = cre[mt][nt][1], v1i = cim[mt][nt][1];
+            if (C1) {
+                const double2 x0 = C1[off], x1 = C1[off + 1];
+                v0r += g.beta1 * x0.x; v0i += g.beta1 * x0.y; v1r += g.beta1 * x1.x; v1i += g.beta1 * x1.y;
+            }
+            if (C2) {
+                const double2 x0 = C2[off], x1 = C2[off + 1];
+                v0r += g.beta2 * x0.x; v0i += g.beta2 * x0.y; v1r += g.beta2 * x1.x; v1i += g.beta2 * x1.y;
+            }
+            if (r == c) { v0r += g.gamma.re; v0i += g.gamma.im; }
+            if (r == c + 1) { v1r += g.gamma.re; v1i += g.gamma.im; }
+            D[off] = make_double2(v0r, v0i);
+            D[off + 1] = make_double2(v1r, v1i);
+        }
+}
+
+// Assembly of a chunk.  grid = (npad*npad/256, ceil(S/8)); H: [mat][npad*npad] row-major, zero padded.
+template <typename IO>
+__global__ void __launch_bounds__(256)
+k4_assemble_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ H,
+                   double2 *__restrict__ Y, double2 *__restrict__ S0, double2 *__restrict__ S1,
+                   unsigned long long step0, int S) {
+    __shared__ cplx coef[kMaxTerms][8];
+    const int sg0 = blockIdx.y * 8;
+    const int ns = min(8, S - sg0);
+    for (int i = threadIdx.x; i < p.nterms * 8; i += blockDim.x) {
+        const int t = i / 8, s = i % 8;
+        if (s < ns) coef[t][s] = step_coefficient<IO>(p.terms[t], carr, p.pts, p.quad, p.magfac, step0 + sg0 + s);
+    }
+    __syncthreads();
+    const size_t nn = (size_t)p.npad * p.npad;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nn) return;
+    const int r = (int)(e / p.npad), c = (int)(e % p.npad);
+    const double2 h0 = H[e];
+    double xr[8], xi[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { xr[s] = h0.x; xi[s] = h0.y; }
+    for (int t = 0; t < p.nterms; ++t) {
+        const double2 h = H[(size_t)p.terms[t].mat * nn + e];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const cplx ct = coef[t][s];
+            xr[s] += ct.re * h.x - ct.im * h.y;
+            xi[s] += ct.re * h.y + ct.im * h.x;
+        }
+    }
+    const bool diag = (r == c);
+    const int M = p.M;
+    const cplx aM = p.a[M], aM1 = p.a[M - 1];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        if (s < ns) {
+            const size_t o = (size_t)(sg0 + s) * nn + e;
+            const double yr = xr[s] * p.sigma, yi = xi[s] * p.sigma;
+            Y[o] = make_double2(yr, yi);
+            // M == 1: S0 holds E = a_1 Y + a0' I directly (a[M-1] == a[0]); S1 unused
+            S0[o] = make_double2(aM.re * yr - aM.im * yi + (diag ? aM1.re : 0.0),
+                                 aM.re * yi + aM.im * yr + (diag ? aM1.im : 0.0));
+            S1[o] = make_double2(diag ? aM.re : 0.0, diag ? aM.im : 0.0);
+        }
+    }
+}
+
+// out[r][c] (n x n, IO precision) = I + E[r][c]  (E padded to npad)
+template <typename IO>
+__global__ void k4_finish_kernel(const double2 *__restrict__ E, int n, int npad, IO *__restrict__ out, int add_identity) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * n) return;
+    const int r = e / n, c = e % n;
+    const double2 v = E[(size_t)r * npad + c];
+    IO o;
+    o.x = v.x + ((add_identity && r == c) ? 1.0 : 0.0);
+    o.y = v.y;
+    out[e] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BN, int WM, int WN>
+static cudaError_t launch_gemm_t(const GemmArgs &g, cudaStream_t stream) {
+    using SM = K4Smem<BM, BN>;
+    static bool configured[64] = {};   // the opt-in shared-memory size is a per-device function attribute
+    auto kern = k4_zgemm_kernel<BM, BN, WM, WN>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    dim3 grid((g.n / BM) * (g.n / BN), g.batch);
+    kern<<<grid, (BM / WM) * (BN / WN) * 32, SM::BYTES, stream>>>(g);
+    return cudaGetLastError();
+}
+
+cudaError_t k4_gemm(const GemmArgs &g, cudaStream_t stream) {
+    if (g.batch <= 0) return cudaSuccess;
+    if (g.n % 64 == 0) return launch_gemm_t<64, 64, 32, 16>(g, stream);
+    return launch_gemm_t<32, 32, 16, 16>(g, stream);
+}
+
+int k4_pad(int n) { return n <= 32 ? 32 : ((n + 63) / 64) * 64; }
+
+int k4_tiles(int npad) { return npad % 64 == 0 ? (npad / 64) * (npad / 64) : 1; }
+
+cudaError_t k4_assemble(bool fp64_io, const SeriesParams &p, const void *carr, const double2 *H, double2 *Y,
+                        double2 *S0, double2 *S1, unsigned long long step0, int S, cudaStream_t stream) {
+    const size_t nn = (size_t)p.npad * p.npad;
+    dim3 grid((unsigned)((nn + 255) / 256), (unsigned)((S + 7) / 8));
+    if (fp64_io)
+        k4_assemble_kernel<double2><<<grid, 256, 0, stream>>>(p, (const double2 *)carr, H, Y, S0, S1, step0, S);
+    else
+        k4_assemble_kernel<float2><<<grid, 256, 0, stream>>>(p, (const float2 *)carr, H, Y, S0, S1, step0, S);
+    return cudaGetLastError();
+}
+
+cudaError_t k4_finish(bool fp64_io, const double2 *E, int n, int npad, void *out, bool add_identity, cudaStream_t stream) {
+    const int blocks = (n * n + 255) / 256;
+    if (fp64_io)
+        k4_finish_kernel<double2><<<blocks, 256, 0, stream>>>(E, n, npad, (double2 *)out, add_identity ? 1 : 0);
+    else
+        k4_finish_kernel<float2><<<blocks, 256, 0, stream>>>(E, n, npad, (float2 *)out, add_identity ? 1 : 0);
+    return cudaGetLastError();
+}
+
+}  // namespace pb

@@ -1,0 +1,38 @@
+// params.hpp -- plain-data kernel parameter blocks shared by host and device code.
+#pragma once
+#include "frag.cuh"
+
+namespace pb {
+
+constexpr int kMaxTerms = 64;    // effective control terms A' per step (controls + Magnus commutators)
+constexpr int kMaxDegree = 63;   // Chebyshev degree MMAX
+
+enum TermType : int {
+    TERM_PLAIN = 0,      // quadrature-averaged amplitude of control j          (control_expansion.cu:105-160)
+    TERM_MAG_DRIFT = 1,  // (c_j(t2) - c_j(t0)) * i h/12   on [H0, H_j]          (control_expansion.cu:43-46)
+    TERM_MAG_PAIR = 2    // (c_j(t0) c_k(t2) - c_j(t2) c_k(t0)) * i h/12 on [H_j, H_k], j < k (control_expansion.cu:49-59)
+};
+
+enum QuadKind : int { QUAD_NONE = 0, QUAD_MIDPOINT = 1, QUAD_SIMPSON = 2 };
+
+struct Term {
+    int type;   // TermType
+    int mat;    // index into the device matrix table (0 = H0)
+    int j, k;   // control indices
+};
+
+struct SeriesParams {
+    int n;                       // Hamiltonian dimension
+    int npad;                    // padded dimension used by the kernel family
+    int quad;                    // QuadKind (Magnus implies SIMPSON)
+    int nterms;                  // A'
+    int M;                       // Chebyshev degree actually evaluated
+    unsigned int pts;            // raw points per control array
+    unsigned int amps_in;        // control arrays per pulse in `carr`
+    double sigma;                // 2 / Hnorm as rounded to double; x is derived from THIS value on the host
+    double magfac;               // h / 12
+    cplx a[kMaxDegree + 1];      // a[0] = J_0(x) - 1,  a[k] = (-i)^k J_k(x)
+    Term terms[kMaxTerms];
+};
+
+}  // namespace pb
