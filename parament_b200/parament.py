@@ -43,6 +43,7 @@ class Parament:
         self._check_error(self._fn("Parament_create")(ctypes.byref(self._handle)))
         self.dim = -1
         self.amps = -1
+        self._quadrature, self._magnus = "none", False
         if device is not None:
             self._check_error(lib.Parament_setDevice(self._handle, int(device)))
 
@@ -87,6 +88,7 @@ class Parament:
         amps = H1.shape[0] if H1.ndim > 2 else 1
         dim = H0.shape[0]
         self.dim, self.amps = dim, amps
+        self._quadrature, self._magnus = quadrature_mode, bool(use_magnus)
         self._check_error(self._fn("Parament_setHamiltonian")(
             self._handle,
             np.ascontiguousarray(np.ravel(H0, order="C").astype(self._ctype)),
@@ -139,6 +141,12 @@ class Parament:
         self._check_error(self._fn("Parament_equipropSlice")(self._handle, flat, float(dt), pts, amps,
                                                              int(step_lo), int(step_hi), out))
         return out.reshape(self.dim, self.dim)
+
+    def steps_of(self, pts):
+        """Effective steps of a pulse with `pts` points under the quadrature set last (parament.cpp:820-831)."""
+        if self._quadrature == "simpson" or self._magnus:
+            return max((pts - 1) // 2, 0)
+        return max(pts - 1, 0) if self._quadrature == "midpoint" else pts
 
     def combine(self, parts):
         """parts[count-1] @ ... @ parts[0] on the device; parts: (count, dim, dim), earliest slice first."""
