@@ -88,6 +88,7 @@ Parament_ErrorCode create_ctx(Context **out, bool fp64) {
         delete c;
         return PARAMENT_STATUS_CUBLAS_INIT_FAILED;
     }
+    if (const char *e = getenv("PARAMENT_SERIES")) c->series_mode = (strcmp(e, "clenshaw") == 0) ? 1 : 0;
     c->lastError = PARAMENT_STATUS_SUCCESS;
     *out = c;
     return PARAMENT_STATUS_SUCCESS;
@@ -294,6 +295,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     if (ec != PARAMENT_STATUS_SUCCESS) return ec;
     c->stat_M_ref = M_ref;
     c->stat_M_used = M_used;
+    c->stat_horner = 0;
     memset(&p, 0, sizeof(p));
     p.n = c->dim;
     p.npad = c->npad;
@@ -311,15 +313,48 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     std::vector<long double> J; long double j0m1;
     bessel_j_table(x, M_used, J, j0m1);
     p.a[0] = cplx{(double)j0m1, 0.0};
+    p.a_lo[0] = cplx{(double)(j0m1 - (long double)p.a[0].re), 0.0};
     for (int k = 1; k <= M_used; ++k) {
         const double v = (double)J[k];
+        const double l = (double)(J[k] - (long double)v);   // remainder below the double rounding of J_k
         switch (k & 3) {   // (-i)^k, mathhelper.cpp:35-46
-            case 0: p.a[k] = cplx{v, 0.0}; break;
-            case 1: p.a[k] = cplx{0.0, -v}; break;
-            case 2: p.a[k] = cplx{-v, 0.0}; break;
-            default: p.a[k] = cplx{0.0, v}; break;
+            case 0: p.a[k] = cplx{v, 0.0};  p.a_lo[k] = cplx{l, 0.0}; break;
+            case 1: p.a[k] = cplx{0.0, -v}; p.a_lo[k] = cplx{0.0, -l}; break;
+            case 2: p.a[k] = cplx{-v, 0.0}; p.a_lo[k] = cplx{-l, 0.0}; break;
+            default: p.a[k] = cplx{0.0, v}; p.a_lo[k] = cplx{0.0, l}; break;
         }
     }
+    // Horner-in-Y^2 evaluation of the same polynomial (register-resident family only): monomial coefficients
+    // c_m = 2^-m sum_k alpha_k t_{k,m}, alpha_0 = J0 - 1, alpha_k = 2 (-i)^k J_k, t_{k,m} the integer coefficients of T_k,
+    // converted in long double.  Restricted to x <= 1, where every term of the monomial sum is <= 1 (no cancellation).
+    p.horner = 0;
+    if (c->family == 1 && c->series_mode != 1 && M_used >= 3 && M_used <= 24 && (double)x <= 1.0) {
+        p.horner = 1;
+        const int d = M_used;
+        std::vector<std::vector<long double>> t(d + 1, std::vector<long double>(d + 1, 0.0L));
+        t[0][0] = 1.0L;
+        if (d >= 1) t[1][1] = 1.0L;
+        for (int k = 2; k <= d; ++k)
+            for (int m = 0; m <= k; ++m) t[k][m] = (m > 0 ? 2.0L * t[k - 1][m - 1] : 0.0L) - t[k - 2][m];
+        long double pow2 = 1.0L;
+        for (int m = 0; m <= d + 1; ++m, pow2 *= 2.0L) {
+            long double cr = 0.0L, ci = 0.0L;
+            for (int k = d; k >= m && m <= d; --k) {          // small terms first
+                if (((k - m) & 1) || t[k][m] == 0.0L) continue;
+                const long double mag = (k == 0) ? j0m1 : 2.0L * J[k];
+                switch (k & 3) {
+                    case 0: cr += mag * t[k][m]; break;
+                    case 1: ci -= mag * t[k][m]; break;
+                    case 2: cr -= mag * t[k][m]; break;
+                    default: ci += mag * t[k][m]; break;
+                }
+            }
+            cr /= pow2; ci /= pow2;
+            p.a[m] = cplx{(double)cr, (double)ci};
+            p.a_lo[m] = cplx{(double)(cr - (long double)p.a[m].re), (double)(ci - (long double)p.a[m].im)};
+        }
+    }
+    c->stat_horner = p.horner;
     const int A = c->amps, Ain = (int)s.amps;
     int nt = 0;
     const int need = Ain + (c->enable_magnus ? Ain + Ain * (Ain - 1) / 2 : 0);
@@ -351,6 +386,7 @@ Parament_ErrorCode tree_level(Context *c, const double2 *src, int count, double2
     g.C2 = src + nn; g.strideC2 = 2 * nn; g.beta2 = 1.0;
     g.D = dst; g.strideD = nn;
     g.gamma = cplx{0.0, 0.0};
+    g.gamma_lo = cplx{0.0, 0.0};
     g.n = npad; g.batch = pairs;
     if (pairs > 0) PB_LAUNCH(k4_gemm(g, st));
     if (count & 1) {
@@ -423,11 +459,11 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
                 g.strideA = g.strideB = g.strideC1 = g.strideD = (long long)nn;
                 g.C2 = nullptr; g.beta2 = 0.0; g.n = np; g.batch = Sc; g.B = Y;
                 for (int k = M - 2; k >= 1; --k) {   // B_k = B_{k+1} Y - B_{k+2} + a_k I   (parament.cpp:596-643)
-                    g.A = S0; g.C1 = S1; g.D = S1; g.beta1 = -1.0; g.gamma = p.a[k];
+                    g.A = S0; g.C1 = S1; g.D = S1; g.beta1 = -1.0; g.gamma = p.a[k]; g.gamma_lo = p.a_lo[k];
                     PB_LAUNCH(k4_gemm(g, st));
                     std::swap(S0, S1);
                 }
-                g.A = S0; g.C1 = S1; g.D = S1; g.beta1 = -2.0; g.gamma = p.a[0];   // E = B_1 Y - 2 B_2 + (J0-1) I
+                g.A = S0; g.C1 = S1; g.D = S1; g.beta1 = -2.0; g.gamma = p.a[0]; g.gamma_lo = p.a_lo[0];   // E = B_1 Y - 2 B_2 + (J0-1) I
                 PB_LAUNCH(k4_gemm(g, st));
                 E = S1;
             }
@@ -468,7 +504,7 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
     // all allocations happen before the timed region (grow-only scratch, nothing is allocated in steady state)
     K1Plan plan{};
     if (c->family == 1) {
-        plan = plan_k1(c->npad, s.batch, s.nsteps, c->num_sms);
+        plan = plan_k1(c->npad, s.batch, s.nsteps, c->num_sms, p.horner != 0);
         if (!ensure_dev(c->d_partials, plan.partial_elems * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
     } else if (!alloc_family3(c, plan_family3(c, s))) {
         return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
@@ -773,6 +809,7 @@ double Parament_lastStat(void *h, int key) {
         case 6: return c->stat_h2d;
         case 7: return c->stat_d2h;
         case 8: return c->Hnorm;
+        case 9: return c->stat_horner;
         default: return -1.0;
     }
 }

@@ -52,7 +52,8 @@ struct Context {
     // statistics of the last equiprop (Parament_lastStat)
     double stat_ms = 0.0;
     long long stat_launches = 0;
-    int stat_M_used = 0, stat_M_ref = 0;
+    int stat_M_used = 0, stat_M_ref = 0, stat_horner = 0;
+    int series_mode = 0;   // 0 automatic, 1 force the Clenshaw recurrence ($PARAMENT_SERIES=clenshaw)
     unsigned long long stat_steps = 0;
     double stat_h2d = 0.0, stat_d2h = 0.0;
 };

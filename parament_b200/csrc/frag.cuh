@@ -109,9 +109,9 @@ __device__ __forceinline__ void set_zero(AccFrag<NT> &Q) {
             for (int i = 0; i < 2; ++i) { Q.re[mt][nt][i] = 0.0; Q.im[mt][nt][i] = 0.0; }
 }
 
-// S <- alpha * S + beta * I     (alpha real, beta complex)
+// S <- alpha * S + (beta + beta_lo) * I     (alpha real; beta_lo, the sub-ulp remainder of beta, is added first)
 template <int NT>
-__device__ __forceinline__ void scale_add_diag(AccFrag<NT> &S, double alpha, cplx beta, int lane) {
+__device__ __forceinline__ void scale_add_diag(AccFrag<NT> &S, double alpha, cplx beta, cplx beta_lo, int lane) {
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int mt = 0; mt < NT; ++mt)
@@ -120,14 +120,14 @@ __device__ __forceinline__ void scale_add_diag(AccFrag<NT> &S, double alpha, cpl
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const bool diag = (mt == nt && g == 2 * q + i);
-                S.re[mt][nt][i] = alpha * S.re[mt][nt][i] + (diag ? beta.re : 0.0);
-                S.im[mt][nt][i] = alpha * S.im[mt][nt][i] + (diag ? beta.im : 0.0);
+                S.re[mt][nt][i] = (alpha * S.re[mt][nt][i] + (diag ? beta_lo.re : 0.0)) + (diag ? beta.re : 0.0);
+                S.im[mt][nt][i] = (alpha * S.im[mt][nt][i] + (diag ? beta_lo.im : 0.0)) + (diag ? beta.im : 0.0);
             }
 }
 
-// S <- a * Y + b * I   (a, b complex)
+// S <- a * Y + (b + b_lo) * I   (a, b complex)
 template <int NT>
-__device__ __forceinline__ void axpb_diag(AccFrag<NT> &S, cplx a, const AccFrag<NT> &Y, cplx b, int lane) {
+__device__ __forceinline__ void axpb_diag(AccFrag<NT> &S, cplx a, const AccFrag<NT> &Y, cplx b, cplx b_lo, int lane) {
     const int g = lane >> 2, q = lane & 3;
 #pragma unroll
     for (int mt = 0; mt < NT; ++mt)
@@ -137,8 +137,34 @@ __device__ __forceinline__ void axpb_diag(AccFrag<NT> &S, cplx a, const AccFrag<
             for (int i = 0; i < 2; ++i) {
                 const bool diag = (mt == nt && g == 2 * q + i);
                 const double yr = Y.re[mt][nt][i], yi = Y.im[mt][nt][i];
-                S.re[mt][nt][i] = a.re * yr - a.im * yi + (diag ? b.re : 0.0);
-                S.im[mt][nt][i] = a.re * yi + a.im * yr + (diag ? b.im : 0.0);
+                S.re[mt][nt][i] = ((a.re * yr - a.im * yi) + (diag ? b_lo.re : 0.0)) + (diag ? b.re : 0.0);
+                S.im[mt][nt][i] = ((a.re * yi + a.im * yr) + (diag ? b_lo.im : 0.0)) + (diag ? b.im : 0.0);
+            }
+}
+
+// Horner addend  S <- i (ci + ci_lo) Y + (cr + cr_lo) I   for REAL scalars ci, cr (the monomial coefficients of the
+// series are purely imaginary for odd and purely real for even powers).  The sub-ulp remainders go in first so the
+// dominant term is rounded once, by the final FMA (unbiased rounding of the constants, DESIGN.md "Numerics").
+template <int NT, bool LO>
+__device__ __forceinline__ void horner_addend(AccFrag<NT> &S, double ci, double ci_lo, const AccFrag<NT> &Y, double cr,
+                                              double cr_lo, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool diag = (mt == nt && g == 2 * q + i);
+                const double yr = Y.re[mt][nt][i], yi = Y.im[mt][nt][i];
+                if (LO) {
+                    double tr = fma(-ci_lo, yi, diag ? cr_lo : 0.0) + (diag ? cr : 0.0);
+                    S.re[mt][nt][i] = fma(-ci, yi, tr);
+                    S.im[mt][nt][i] = fma(ci, yr, ci_lo * yr);
+                } else {
+                    S.re[mt][nt][i] = fma(-ci, yi, diag ? cr : 0.0);
+                    S.im[mt][nt][i] = ci * yr;
+                }
             }
 }
 

@@ -43,8 +43,8 @@ __device__ __forceinline__ void cta_ordered_product(AccFrag<NT> &Q, double2 *sme
 }
 
 // Hfrag layout: [matrix][layout 0 = AccFrag order, 1 = BFrag order][element e < 2*NT*NT][lane] as double2.
-template <int NT, typename IO>
-__global__ void __launch_bounds__(32 * K1_WARPS, (NT == 1) ? 6 : 3)
+template <int NT, typename IO, int HORNER>
+__global__ void __launch_bounds__(32 * K1_WARPS, (NT == 1) ? 6 : (HORNER ? 2 : 3))
 k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ Hfrag,
                 double2 *__restrict__ partials, unsigned int batch, unsigned int chunks_per_pulse,
                 unsigned long long step_lo, unsigned long long step_hi, int reduce_in_cta) {
@@ -84,14 +84,26 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
             for (int t = 0; t < p.nterms; ++t) {
                 const cplx ct = step_coefficient<IO>(p.terms[t], c, p.pts, p.quad, p.magfac, j);
                 const double2 *Ht = HA + (size_t)p.terms[t].mat * 2 * NE * 32;
+                if (ct.im == 0.0) {   // real amplitude (warp-uniform): half the FP64-pipe work of the assembly
 #pragma unroll
-                for (int e = 0; e < NE; ++e) {
-                    const double2 ha = __ldg(Ht + e * 32);
-                    const double2 hb = __ldg(Ht + (NE + e) * 32);
-                    (&Ya.re[0][0][0])[e] += ct.re * ha.x - ct.im * ha.y;
-                    (&Ya.im[0][0][0])[e] += ct.re * ha.y + ct.im * ha.x;
-                    (&Yb.re[0][0])[e] += ct.re * hb.x - ct.im * hb.y;
-                    (&Yb.im[0][0])[e] += ct.re * hb.y + ct.im * hb.x;
+                    for (int e = 0; e < NE; ++e) {
+                        const double2 ha = __ldg(Ht + e * 32);
+                        const double2 hb = __ldg(Ht + (NE + e) * 32);
+                        (&Ya.re[0][0][0])[e] = fma(ct.re, ha.x, (&Ya.re[0][0][0])[e]);
+                        (&Ya.im[0][0][0])[e] = fma(ct.re, ha.y, (&Ya.im[0][0][0])[e]);
+                        (&Yb.re[0][0])[e] = fma(ct.re, hb.x, (&Yb.re[0][0])[e]);
+                        (&Yb.im[0][0])[e] = fma(ct.re, hb.y, (&Yb.im[0][0])[e]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        const double2 ha = __ldg(Ht + e * 32);
+                        const double2 hb = __ldg(Ht + (NE + e) * 32);
+                        (&Ya.re[0][0][0])[e] += ct.re * ha.x - ct.im * ha.y;
+                        (&Ya.im[0][0][0])[e] += ct.re * ha.y + ct.im * ha.x;
+                        (&Yb.re[0][0])[e] += ct.re * hb.x - ct.im * hb.y;
+                        (&Yb.im[0][0])[e] += ct.re * hb.y + ct.im * hb.x;
+                    }
                 }
             }
 #pragma unroll
@@ -101,20 +113,52 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                 (&Yb.nim[0][0])[e] = -(&Yb.im[0][0])[e];
             }
 
-            // ---- Clenshaw in E-form: E = U - I = a0' I + B_1 Y - 2 B_2 ----
             AccFrag<NT> S0, S1;
+            if (HORNER) {
+                // ---- Horner in W = Y^2:  E = sum_i (c_2i I + c_2i+1 Y) W^i, 1 + floor(M/2) products instead of M - 1.
+                // W is needed as a RIGHT operand.  (Y^T)^2 = (Y^2)^T is formed in accumulator layout from register
+                // relabelings only -- AccFrag(Y^T) is Yb, BFrag(Y^T) is Ya (frag.cuh) -- and its transpose read as BFrag.
+                AccFrag<NT> Zt;
+                BFrag<NT> Bt;
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            Zt.re[mt][nt][i] = Yb.re[2 * nt + i][mt];
+                            Zt.im[mt][nt][i] = Yb.im[2 * nt + i][mt];
+                        }
+                transpose_as_bfrag<NT>(Bt, Ya);
+                AccFrag<NT> Wt;
+                set_zero<NT>(Wt);
+                cmma<NT>(Wt, Zt, Bt);                       // (Y^T)(Y^T)
+                BFrag<NT> Wb;
+                transpose_as_bfrag<NT>(Wb, Wt);             // BFrag(Y^2)
+                const int L = M >> 1;
+                horner_addend<NT, false>(S0, p.a[2 * L + 1].im, 0.0, Ya, p.a[2 * L].re, 0.0, lane);   // B_L (c_{M+1} = 0 for even M)
+#pragma unroll 1
+                for (int i = L - 1; i >= 0; --i) {
+                    if (i <= 1) horner_addend<NT, true>(S1, p.a[2 * i + 1].im, p.a_lo[2 * i + 1].im, Ya, p.a[2 * i].re, p.a_lo[2 * i].re, lane);
+                    else        horner_addend<NT, false>(S1, p.a[2 * i + 1].im, 0.0, Ya, p.a[2 * i].re, 0.0, lane);
+                    cmma<NT>(S1, S0, Wb);                   // R <- R W + B_i
+                    const AccFrag<NT> T = S0; S0 = S1; S1 = T;
+                }
+                S1 = S0;                                    // E
+            } else
+            // ---- Clenshaw in E-form: E = U - I = a0' I + B_1 Y - 2 B_2 ----
             if (M == 1) {
-                axpb_diag<NT>(S1, p.a[1], Ya, p.a[0], lane);
+                axpb_diag<NT>(S1, p.a[1], Ya, p.a[0], p.a_lo[0], lane);
             } else {
-                axpb_diag<NT>(S0, p.a[M], Ya, p.a[M - 1], lane);      // B_{M-1}
+                axpb_diag<NT>(S0, p.a[M], Ya, p.a[M - 1], p.a_lo[M - 1], lane);      // B_{M-1}
                 set_zero<NT>(S1);
-                scale_add_diag<NT>(S1, 0.0, p.a[M], lane);            // B_M
+                scale_add_diag<NT>(S1, 0.0, p.a[M], p.a_lo[M], lane);            // B_M
                 for (int k = M - 2; k >= 1; --k) {
-                    scale_add_diag<NT>(S1, -1.0, p.a[k], lane);       // a_k I - B_{k+2}
+                    scale_add_diag<NT>(S1, -1.0, p.a[k], p.a_lo[k], lane);       // a_k I - B_{k+2}
                     cmma<NT>(S1, S0, Yb);                             // + B_{k+1} Y
                     const AccFrag<NT> T = S0; S0 = S1; S1 = T;
                 }
-                scale_add_diag<NT>(S1, -2.0, p.a[0], lane);           // a0' I - 2 B_2
+                scale_add_diag<NT>(S1, -2.0, p.a[0], p.a_lo[0], lane);           // a0' I - 2 B_2
                 cmma<NT>(S1, S0, Yb);                                 // + B_1 Y   -> E
             }
 
@@ -189,11 +233,11 @@ k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, int n, I
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
-template <int NT, typename IO>
-static cudaError_t launch_k1_t(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
+template <int NT, typename IO, int HORNER>
+static cudaError_t launch_k1_tt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
                                unsigned long long step_hi, IO *out, cudaStream_t stream) {
-    k1_chain_kernel<NT, IO><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
+    k1_chain_kernel<NT, IO, HORNER><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
                                                                       plan.chunks_per_pulse, step_lo, step_hi,
                                                                       plan.reduce_in_cta);
     cudaError_t e = cudaGetLastError();
@@ -202,9 +246,17 @@ static cudaError_t launch_k1_t(const SeriesParams &p, const IO *carr, const doub
     return cudaGetLastError();
 }
 
-K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms) {
+template <int NT, typename IO>
+static cudaError_t launch_k1_t(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
+                               unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
+                               unsigned long long step_hi, IO *out, cudaStream_t stream) {
+    return p.horner ? launch_k1_tt<NT, IO, 1>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, out, stream)
+                    : launch_k1_tt<NT, IO, 0>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, out, stream);
+}
+
+K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms, bool horner) {
     K1Plan plan{};
-    const int ctas_per_sm = (npad == 8) ? 6 : 3;
+    const int ctas_per_sm = (npad == 8) ? 6 : (horner ? 2 : 3);
     const unsigned long long warps_total = (unsigned long long)num_sms * ctas_per_sm * K1_WARPS;
     if (batch >= warps_total / 2 || nsteps < 2ull * K1_WARPS) {
         plan.chunks_per_pulse = 1;                 // a warp owns a whole pulse

@@ -15,7 +15,7 @@ struct K1Plan {
     size_t partial_elems;              // double2 elements of the partial buffer
 };
 
-K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms);
+K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms, bool horner);
 
 // carr / out are device pointers in the context precision; Hfrag is the fragment-ordered matrix table.
 cudaError_t launch_k1(int npad, bool fp64_io, const SeriesParams &p, const void *carr, const double2 *Hfrag,

@@ -134,8 +134,8 @@ k4_zgemm_kernel(const GemmArgs g) {
                 const double2 x0 = C2[off], x1 = C2[off + 1];
                 v0r += g.beta2 * x0.x; v0i += g.beta2 * x0.y; v1r += g.beta2 * x1.x; v1i += g.beta2 * x1.y;
             }
-            if (r == c) { v0r += g.gamma.re; v0i += g.gamma.im; }
-            if (r == c + 1) { v1r += g.gamma.re; v1i += g.gamma.im; }
+            if (r == c) { v0r = (v0r + g.gamma_lo.re) + g.gamma.re; v0i = (v0i + g.gamma_lo.im) + g.gamma.im; }
+            if (r == c + 1) { v1r = (v1r + g.gamma_lo.re) + g.gamma.re; v1i = (v1i + g.gamma_lo.im) + g.gamma.im; }
             D[off] = make_double2(v0r, v0i);
             D[off + 1] = make_double2(v1r, v1i);
         }
@@ -174,7 +174,7 @@ k4_assemble_kernel(const SeriesParams p, const IO *__restrict__ carr, const doub
     }
     const bool diag = (r == c);
     const int M = p.M;
-    const cplx aM = p.a[M], aM1 = p.a[M - 1];
+    const cplx aM = p.a[M], aM1 = p.a[M - 1], aM1lo = p.a_lo[M - 1];
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         if (s < ns) {
@@ -182,8 +182,8 @@ k4_assemble_kernel(const SeriesParams p, const IO *__restrict__ carr, const doub
             const double yr = xr[s] * p.sigma, yi = xi[s] * p.sigma;
             Y[o] = make_double2(yr, yi);
             // M == 1: S0 holds E = a_1 Y + a0' I directly (a[M-1] == a[0]); S1 unused
-            S0[o] = make_double2(aM.re * yr - aM.im * yi + (diag ? aM1.re : 0.0),
-                                 aM.re * yi + aM.im * yr + (diag ? aM1.im : 0.0));
+            S0[o] = make_double2(((aM.re * yr - aM.im * yi) + (diag ? aM1lo.re : 0.0)) + (diag ? aM1.re : 0.0),
+                                 ((aM.re * yi + aM.im * yr) + (diag ? aM1lo.im : 0.0)) + (diag ? aM1.im : 0.0));
             S1[o] = make_double2(diag ? aM.re : 0.0, diag ? aM.im : 0.0);
         }
     }

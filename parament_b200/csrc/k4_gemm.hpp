@@ -5,7 +5,7 @@
 
 namespace pb {
 
-// D_b = A_b * B_b + beta1 * C1_b + beta2 * C2_b + gamma * I   for b < batch; all matrices n x n row-major
+// D_b = A_b * B_b + beta1 * C1_b + beta2 * C2_b + (gamma + gamma_lo) * I   for b < batch; all matrices n x n row-major
 // interleaved complex double, n a multiple of 32 (n <= 32) or 64.  C1 / C2 may be null and may alias D.
 struct GemmArgs {
     const double2 *A; long long strideA;
@@ -14,6 +14,7 @@ struct GemmArgs {
     const double2 *C2; long long strideC2; double beta2;
     double2 *D; long long strideD;
     cplx gamma;
+    cplx gamma_lo;   // sub-ulp remainder of gamma, added before gamma
     int n;
     int batch;
 };

@@ -27,11 +27,16 @@ struct SeriesParams {
     int quad;                    // QuadKind (Magnus implies SIMPSON)
     int nterms;                  // A'
     int M;                       // Chebyshev degree actually evaluated
+    int horner;                  // 0: Clenshaw on the Chebyshev coefficients; 1: Horner in W = Y^2 on the monomial
+                                 // coefficients of the SAME polynomial (a[m] = c_m, p(Y) - I = sum_m c_m Y^m)
     unsigned int pts;            // raw points per control array
     unsigned int amps_in;        // control arrays per pulse in `carr`
     double sigma;                // 2 / Hnorm as rounded to double; x is derived from THIS value on the host
     double magfac;               // h / 12
-    cplx a[kMaxDegree + 1];      // a[0] = J_0(x) - 1,  a[k] = (-i)^k J_k(x)
+    cplx a[kMaxDegree + 1];      // a[0] = J_0(x) - 1,  a[k] = (-i)^k J_k(x)          (rounded to double)
+    cplx a_lo[kMaxDegree + 1];   // long-double remainder of a[k]: added to the diagonal BEFORE a[k], while the
+                                 // accumulator is still small, so that the rounding of the series constants does
+                                 // not bias every step the same way (DESIGN.md "Numerics")
     Term terms[kMaxTerms];
 };
 
