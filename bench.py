@@ -204,6 +204,7 @@ def run_ours(args):
     # small ordered reduction, so the average per-step device time is the launch duration
     kernel_ms = dev_ms / args.steps if world == 1 else ctx.stat(K.STAT_DEVICE_MS)
     M_used, M_ref = int(ctx.stat(K.STAT_DEGREE_USED)), int(ctx.stat(K.STAT_DEGREE_REFERENCE))
+    products, horner, family = ctx.stat(K.STAT_PRODUCTS), int(ctx.stat(K.STAT_HORNER)), int(ctx.stat(K.STAT_FAMILY))
     gpu_launches = launches[0]
 
     # ---- timed region 2: end to end through the host-pointer C-ABI, pinned host buffers ----
@@ -246,7 +247,7 @@ def run_ours(args):
     if rank == 0:
         peaks, how = load_measured_peaks()
         F_alg = algorithmic_flops_per_step(w, M_ref)
-        F_exe = algorithmic_flops_per_step(w, M_used)
+        F_exe = algorithmic_flops_per_step(w, products)     # complex products actually executed per step
         per_gpu_rate = steps_rank / (kernel_ms * 1e-3)         # last equiprop on rank 0, kernels only
         achieved = F_alg * per_gpu_rate * 1e-12
         traffic = None
@@ -264,6 +265,8 @@ def run_ours(args):
                        "pulses_per_gpu": w.batch, "effective_steps_per_gpu": steps_rank, "quadrature": w.quadrature,
                        "magnus": w.use_magnus, "io_precision": "complex64" if not fp64 else "complex128",
                        "x_Hnorm_h": w.meta["x"], "degree_reference": M_ref, "degree_used": M_used,
+                       "series_evaluation": "Horner in Y^2 (same polynomial)" if horner else "Clenshaw recurrence",
+                       "matrix_products_per_step": products, "kernel_family": family,
                        "l2": f"inputs rotate over {nbuf} device copies ({nbuf * in_bytes / 1e6:.0f} MB > 126 MB L2)" if flush is None
                              else "L2 flushed by a 256 MiB write between iterations",
                        "parallelism": f"time axis sliced over {world} GPU(s), ordered NCCL all-gather + combine" if w.batch == 1
@@ -276,7 +279,7 @@ def run_ours(args):
             "roofline": {"bound": "fp64_tensor", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s",
                          "frac": achieved / peak_dmma if peak_dmma > 0 else None, "traffic": traffic,
                          "peak_source": "Parament_measurePeak(DMMA mma.sync.m8n8k4.f64) in this process; MEASURED_PEAKS.json has no FP64 figure",
-                         "kernel": "k1_chain_kernel" if n <= 16 else "k4_zgemm_kernel",
+                         "kernel": {1: "k1_chain_kernel", 2: "k4_chain_kernel", 3: "k4_zgemm_kernel"}[family],
                          "kernel_ms_per_launch": kernel_ms,
                          "flops_per_step_algorithmic": F_alg, "flops_per_step_executed": F_exe,
                          "executed_tflops": F_exe * per_gpu_rate * 1e-12,

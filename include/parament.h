@@ -183,9 +183,11 @@ PARAMENT_API Parament_ErrorCode Parament_combine_fp64(struct Parament_Context_f6
  *   0 device milliseconds between first and last kernel (CUDA events on the context stream)
  *   1 number of kernels launched          2 Chebyshev degree used (MMAX actually evaluated)
  *   3 degree the reference table selects  4 effective steps per pulse N
- *   5 kernel family used (1 = register-resident DMMA warp kernel, 2 = shared-memory CTA kernel,
- *                         3 = batched global-memory GEMM pipeline)
- *   6 H2D bytes copied                    7 D2H bytes copied */
+ *   5 kernel family used (1 = register-resident DMMA warp kernel, 2 = persistent CTA chain kernel,
+ *                         3 = batched GEMM pipeline over L2-resident time chunks)
+ *   6 H2D bytes copied                    7 D2H bytes copied
+ *   8 Hnorm of the loaded Hamiltonian     9 series evaluation (0 Clenshaw recurrence, 1 Horner in Y^2)
+ *  10 complex matrix products executed per effective step (series + ordered product) */
 PARAMENT_API double Parament_lastStat(void *handle, int key);
 
 /* Select the CUDA device a context lives on.  Must be called before setHamiltonian; default is device 0

@@ -99,7 +99,7 @@ Parament_ErrorCode destroy_ctx(Context *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
-    free_dev(c->d_Y); free_dev(c->d_S0); free_dev(c->d_S1); free_dev(c->d_pending); free_dev(c->d_tree);
+    free_dev(c->d_Y); free_dev(c->d_W); free_dev(c->d_S0); free_dev(c->d_S1); free_dev(c->d_pending); free_dev(c->d_tree);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_out) cudaFreeHost(c->h_out);
     cudaEventDestroy(c->ev_start);
@@ -232,7 +232,8 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     }
 
     if (dim <= 16) { c->family = 1; c->npad = dim <= 8 ? 8 : 16; }
-    else           { c->family = 3; c->npad = k4_pad((int)dim); }
+    else if (dim <= 64) { c->family = 2; c->npad = k4_pad((int)dim); c->k4_slots = k4_chain_slots(c->npad, c->num_sms); }
+    else                { c->family = 3; c->npad = k4_pad((int)dim); c->k4_slots = k4_wave_slots(c->npad, c->num_sms); }
     if (!upload_matrices(c)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
     c->have_hamiltonian = true;
     c->lastError = PARAMENT_STATUS_SUCCESS;
@@ -328,7 +329,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     // c_m = 2^-m sum_k alpha_k t_{k,m}, alpha_0 = J0 - 1, alpha_k = 2 (-i)^k J_k, t_{k,m} the integer coefficients of T_k,
     // converted in long double.  Restricted to x <= 1, where every term of the monomial sum is <= 1 (no cancellation).
     p.horner = 0;
-    if (c->family == 1 && c->series_mode != 1 && M_used >= 3 && M_used <= 24 && (double)x <= 1.0) {
+    if (c->series_mode != 1 && M_used >= 3 && M_used <= 24 && (double)x <= 1.0) {
         p.horner = 1;
         const int d = M_used;
         std::vector<std::vector<long double>> t(d + 1, std::vector<long double>(d + 1, 0.0L));
@@ -382,7 +383,7 @@ Parament_ErrorCode tree_level(Context *c, const double2 *src, int count, double2
     GemmArgs g{};
     g.A = src + nn; g.strideA = 2 * nn;
     g.B = src; g.strideB = 2 * nn;
-    g.C1 = src; g.strideC1 = 2 * nn; g.beta1 = 1.0;
+    g.C1 = src; g.strideC1 = 2 * nn; g.beta1 = cplx{1.0, 0.0}; g.beta1_lo = cplx{0.0, 0.0};
     g.C2 = src + nn; g.strideC2 = 2 * nn; g.beta2 = 1.0;
     g.D = dst; g.strideD = nn;
     g.gamma = cplx{0.0, 0.0};
@@ -416,27 +417,62 @@ Parament_ErrorCode tree_reduce_all(Context *c, double2 *buf, int count, double2 
 
 struct F3Plan { int S; int cap; };
 
-// Chunk length S keeps the three S x npad^2 work arrays (Y, B_{k+1}, B_{k+2}) L2-resident (~57 MB) while a
-// launch still covers the machine; `cap` bounds the buffer of pending partial products.
+// Chunk length S: a whole number of GEMM waves (S * tiles == k * co-resident CTAs: a launch that spills a few CTAs
+// into an extra wave costs a full wave) with the four S x npad^2 work arrays (Y, W, two recurrence registers)
+// L2-resident (<= ~80 MB).  `cap` bounds the buffer of pending partial products.
 F3Plan plan_family3(const Context *c, const CallSpec &s) {
     const size_t nn = (size_t)c->npad * c->npad;
+    const int tiles = k4_tiles(c->npad);
+    const int slots = c->k4_slots > 0 ? c->k4_slots : 2 * c->num_sms;
     F3Plan f;
-    f.S = (int)std::max<long long>(2, (19LL * 65536 + (long long)nn - 1) / (long long)nn);
+    const long long per_wave = std::max<long long>(1, slots / tiles);
+    const long long budget = std::max<long long>(1, (long long)(80e6 / (4.0 * nn * sizeof(double2))));
+    long long waves = std::max<long long>(1, budget / per_wave);
+    if (waves > 4) waves = 4;
+    f.S = (int)std::max<long long>(2, std::min<long long>(per_wave * waves, std::max<long long>(budget, per_wave)));
     if ((unsigned long long)f.S > s.nsteps) f.S = (int)std::max<unsigned long long>(s.nsteps, 1);
     const size_t want = std::min<size_t>(2048, std::max<size_t>(64, ((size_t)2 << 30) / (nn * sizeof(double2))));
-    // no more than the run can produce
     f.cap = (int)std::max<size_t>(2, std::min<size_t>(want, (size_t)std::min<unsigned long long>(s.nsteps, 1ull << 30)));
     return f;
 }
 
+int chain_grid(const Context *c, const CallSpec &s) {
+    return (int)std::max<unsigned long long>(1, std::min<unsigned long long>((unsigned long long)c->k4_slots, s.nsteps));
+}
+
 bool alloc_family3(Context *c, const F3Plan &f) {
     const size_t nn = (size_t)c->npad * c->npad;
-    return ensure_dev(c->d_Y, (size_t)f.S * nn * sizeof(double2)) && ensure_dev(c->d_S0, (size_t)f.S * nn * sizeof(double2)) &&
-           ensure_dev(c->d_S1, (size_t)f.S * nn * sizeof(double2)) &&
+    return ensure_dev(c->d_Y, (size_t)f.S * nn * sizeof(double2)) && ensure_dev(c->d_W, (size_t)f.S * nn * sizeof(double2)) &&
+           ensure_dev(c->d_S0, (size_t)f.S * nn * sizeof(double2)) && ensure_dev(c->d_S1, (size_t)f.S * nn * sizeof(double2)) &&
            ensure_dev(c->d_pending, (size_t)(f.cap + f.S) * nn * sizeof(double2)) &&
            ensure_dev(c->d_tree, (size_t)((f.cap + f.S) / 2 + 1) * nn * sizeof(double2));
 }
 
+bool alloc_family2(Context *c, int grid) {
+    const size_t nn = (size_t)c->npad * c->npad;
+    return ensure_dev(c->d_Y, (size_t)grid * 6 * nn * sizeof(double2)) &&          // per-CTA scratch: 6 matrices
+           ensure_dev(c->d_pending, (size_t)grid * nn * sizeof(double2)) &&
+           ensure_dev(c->d_tree, (size_t)(grid / 2 + 1) * nn * sizeof(double2));
+}
+
+// dim 17..64: one persistent launch per pulse + the ordered reduction of the per-CTA partials.
+Parament_ErrorCode run_family2(Context *c, const SeriesParams &p, const void *carr_dev, const CallSpec &s, void *out_dev, cudaStream_t st) {
+    const int np = c->npad;
+    const size_t io = c->fp64 ? sizeof(double2) : sizeof(float2);
+    const SeriesProgram prog = build_program(p);
+    const int grid = chain_grid(c, s);
+    double2 *pend = (double2 *)c->d_pending.ptr, *tree = (double2 *)c->d_tree.ptr;
+    for (unsigned int b = 0; b < s.batch; ++b) {
+        const char *cb = (const char *)carr_dev + (size_t)b * s.amps * s.stride * io;
+        PB_LAUNCH(k4_chain(c->fp64, p, prog, cb, (const double2 *)c->d_H.ptr, (double2 *)c->d_Y.ptr, pend, s.nsteps, grid, st));
+        Parament_ErrorCode ec = tree_reduce_all(c, pend, grid, tree, np, st);
+        if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+        PB_LAUNCH(k4_finish(c->fp64, pend, c->dim, np, (char *)out_dev + (size_t)b * c->dim * c->dim * io, true, st));
+    }
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+// dim > 64: L2-resident time chunks, every series op one batched launch.
 Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *carr_dev, const CallSpec &s, void *out_dev, cudaStream_t st) {
     const int np = c->npad;
     const size_t nn = (size_t)np * np;
@@ -444,33 +480,28 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
     const int tiles = k4_tiles(np);
     const F3Plan f = plan_family3(c, s);
     const int S = f.S, cap = f.cap;
-    double2 *Y = (double2 *)c->d_Y.ptr, *pend = (double2 *)c->d_pending.ptr, *tree = (double2 *)c->d_tree.ptr;
-    const int M = p.M;
+    const SeriesProgram prog = build_program(p);
+    double2 *slots[4] = {(double2 *)c->d_Y.ptr, (double2 *)c->d_W.ptr, (double2 *)c->d_S0.ptr, (double2 *)c->d_S1.ptr};
+    double2 *pend = (double2 *)c->d_pending.ptr, *tree = (double2 *)c->d_tree.ptr;
     for (unsigned int b = 0; b < s.batch; ++b) {
         const char *cb = (const char *)carr_dev + (size_t)b * s.amps * s.stride * io;
         int pending = 0;
         for (unsigned long long step0 = 0; step0 < s.nsteps; step0 += S) {
             const int Sc = (int)std::min<unsigned long long>(S, s.nsteps - step0);
-            double2 *S0 = (double2 *)c->d_S0.ptr, *S1 = (double2 *)c->d_S1.ptr;
-            PB_LAUNCH(k4_assemble(c->fp64, p, cb, (const double2 *)c->d_H.ptr, Y, S0, S1, step0, Sc, st));
-            double2 *E = S0;
-            if (M >= 2) {
+            PB_LAUNCH(k4_assemble(c->fp64, p, prog, cb, (const double2 *)c->d_H.ptr, slots[0], slots[2], slots[3], step0, Sc, st));
+            for (int o = 0; o < prog.nops; ++o) {
+                const SeriesOp &op = prog.ops[o];
                 GemmArgs g{};
+                g.A = slots[op.A]; g.B = slots[op.B]; g.C1 = op.C1 >= 0 ? slots[op.C1] : nullptr; g.D = slots[op.D];
                 g.strideA = g.strideB = g.strideC1 = g.strideD = (long long)nn;
-                g.C2 = nullptr; g.beta2 = 0.0; g.n = np; g.batch = Sc; g.B = Y;
-                for (int k = M - 2; k >= 1; --k) {   // B_k = B_{k+1} Y - B_{k+2} + a_k I   (parament.cpp:596-643)
-                    g.A = S0; g.C1 = S1; g.D = S1; g.beta1 = -1.0; g.gamma = p.a[k]; g.gamma_lo = p.a_lo[k];
-                    PB_LAUNCH(k4_gemm(g, st));
-                    std::swap(S0, S1);
-                }
-                g.A = S0; g.C1 = S1; g.D = S1; g.beta1 = -2.0; g.gamma = p.a[0]; g.gamma_lo = p.a_lo[0];   // E = B_1 Y - 2 B_2 + (J0-1) I
+                g.beta1 = op.beta1; g.beta1_lo = op.beta1_lo; g.gamma = op.gamma; g.gamma_lo = op.gamma_lo;
+                g.C2 = nullptr; g.beta2 = 0.0; g.n = np; g.batch = Sc;
                 PB_LAUNCH(k4_gemm(g, st));
-                E = S1;
             }
             // ordered product inside the chunk while the launches still fill the machine
-            double2 *other = (E == S1) ? S0 : S1;
+            double2 *src = slots[prog.e_slot];
+            double2 *other = slots[prog.e_slot == 2 ? 3 : 2];
             int count = Sc;
-            double2 *src = E;
             while (count > 1 && (count / 2) * tiles >= 48) {
                 int nc = 0;
                 Parament_ErrorCode ec = tree_level(c, src, count, other, np, st, nc);
@@ -506,6 +537,8 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
     if (c->family == 1) {
         plan = plan_k1(c->npad, s.batch, s.nsteps, c->num_sms, p.horner != 0);
         if (!ensure_dev(c->d_partials, plan.partial_elems * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+    } else if (c->family == 2) {
+        if (!alloc_family2(c, chain_grid(c, s))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
     } else if (!alloc_family3(c, plan_family3(c, s))) {
         return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
     }
@@ -516,7 +549,7 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
             return PARAMENT_STATUS_CUBLAS_FAILED;
         c->stat_launches = 2;
     } else {
-        ec = run_family3(c, p, carr_dev, s, out_dev, st);
+        ec = c->family == 2 ? run_family2(c, p, carr_dev, s, out_dev, st) : run_family3(c, p, carr_dev, s, out_dev, st);
         if (ec != PARAMENT_STATUS_SUCCESS) return ec;
     }
     if (!PB_CUDA_OK(cudaEventRecord(c->ev_stop, st))) return PARAMENT_STATUS_CUBLAS_FAILED;
@@ -810,6 +843,11 @@ double Parament_lastStat(void *h, int key) {
         case 7: return c->stat_d2h;
         case 8: return c->Hnorm;
         case 9: return c->stat_horner;
+        case 10: {   // complex matrix products executed per effective step (series + ordered product)
+            const int M = c->stat_M_used;
+            if (M <= 0) return 0.0;
+            return c->stat_horner ? 2.0 + (M >> 1) : (double)std::max(M, 1);
+        }
         default: return -1.0;
     }
 }
@@ -824,7 +862,7 @@ Parament_ErrorCode Parament_setDevice(void *h, int device) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
-    free_dev(c->d_Y); free_dev(c->d_S0); free_dev(c->d_S1); free_dev(c->d_pending); free_dev(c->d_tree);
+    free_dev(c->d_Y); free_dev(c->d_W); free_dev(c->d_S0); free_dev(c->d_S1); free_dev(c->d_pending); free_dev(c->d_tree);
     cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); cudaStreamDestroy(c->stream);
     c->device = device;
     c->have_hamiltonian = false;

@@ -39,13 +39,14 @@ struct Context {
     int nmats = 0;       // 1 + amps (+ amps + amps(amps-1)/2 commutators with Magnus)
     double Hnorm = 0.0;
     std::vector<zc> mats;   // nmats * dim * dim, row-major
-    int family = 0;      // 1 = register-resident warp kernels, 3 = batched GEMM pipeline
+    int family = 0;      // 1 = register-resident warp kernels, 2 = persistent CTA chain kernel, 3 = batched GEMM pipeline
     int npad = 0;
+    int k4_slots = 0;    // co-resident CTAs of the GEMM kernel (family 3)
     DeviceBuffer d_H;    // family 1: fragment-ordered table; family 3: padded row-major table
 
     // per-call scratch (grow-only)
     DeviceBuffer d_carr, d_out, d_partials;
-    DeviceBuffer d_Y, d_S0, d_S1, d_pending, d_tree;   // family 3
+    DeviceBuffer d_Y, d_W, d_S0, d_S1, d_pending, d_tree;   // families 2 / 3
     void *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for carr
     void *h_out = nullptr;   size_t h_out_bytes = 0;    // pinned staging for results
 

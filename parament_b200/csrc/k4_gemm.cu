@@ -1,15 +1,17 @@
 // k4_gemm.cu -- kernel (4) of the north_star: dense complex FP64 contraction for dim > 16.
 //
-// A time chunk of S steps is processed as a batch that stays L2-resident:
-//   k4_assemble_kernel   Y_s = sigma (H0 + sum_t c_t(s) H_t),  S0_s = a_M Y_s + a_{M-1} I,  S1_s = a_M I
-//                        (fuses the reference's outer-product broadcast, quadrature kernels and rank-A' GEMM,
-//                        parament.cpp:491-554, with the first, algorithmically free, Clenshaw step)
-//   k4_zgemm_kernel      D_s = A_s B_s + beta1 C1_s + beta2 C2_s + gamma I   on the FP64 tensor pipe
-//                        (mma.sync.m8n8k4.f64), cp.async multi-stage shared-memory pipeline, Clenshaw
-//                        epilogue (-B_{k+2}, +a_k I; reference: a separate diagonal_add launch per
-//                        iteration, diagonal_add.cu:21-51) and the E-form pair product
-//                        E_b + E_a + E_b E_a of the ordered reduction (parament.cpp:657-718) fused in.
-// Replaces cublasZgemmStridedBatched at parament.cpp:596-605,627-636,681-690.
+// tile_gemm             one BM x BN complex output tile  D = A B + beta1 C1 + beta2 C2 + gamma I  on the FP64 tensor
+//                       pipe (mma.sync.m8n8k4.f64 -> DMMA.8x8x4): 3-stage cp.async shared-memory pipeline,
+//                       bank-conflict-free pitches for the LDS.128 fragment loads, fused epilogue (the Clenshaw
+//                       "-B_{k+2} + a_k I", the Horner "+c_{2i+1} Y + c_{2i} I" and the E-form pair product
+//                       "E_b + E_a + E_b E_a" of the ordered reduction).  Reference: cublasZgemmStridedBatched plus a
+//                       separate diagonal_add launch per iteration (parament.cpp:596-643,681-690, diagonal_add.cu:21-51).
+// k4_chain_kernel       dim 17..64: PERSISTENT kernel, one CTA per contiguous range of time steps.  Per step the CTA
+//                       assembles Y into its private, L2-resident scratch, runs the whole series program and multiplies
+//                       the step into its running product -- one launch for the whole pulse, no grid-wide dependency.
+// k4_zgemm_kernel       dim > 64: the same tile code as a batched launch over the S steps of an L2-resident time chunk.
+// k4_assemble_kernel    batched assembly Y_s = sigma (H0 + sum_t c_t(s) H_t) + series start values (fuses the reference's
+//                       outer-product broadcast, quadrature kernels and rank-A' GEMM, parament.cpp:491-554).
 #include "coef.cuh"
 #include "k4_gemm.hpp"
 
@@ -36,24 +38,26 @@ struct K4Smem {
     static constexpr size_t BYTES = (size_t)K4_STAGES * STAGE_ELEMS * sizeof(double2);
 };
 
+struct TileArgs {
+    const double2 *A, *B, *C1, *C2;   // matrix bases (n x n row-major)
+    double2 *D;
+    cplx beta1, beta1_lo;
+    double beta2;
+    cplx gamma, gamma_lo;
+    int n;
+};
+
+// All threads of the CTA call this; returns with every thread's part of D written (no trailing barrier).
 template <int BM, int BN, int WM, int WN>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
-k4_zgemm_kernel(const GemmArgs g) {
+__device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int tile_m, int tile_n) {
     using SM = K4Smem<BM, BN>;
     constexpr int NTHREADS = (BM / WM) * (BN / WN) * 32;
     constexpr int MT = WM / 8, NTL = WN / 8;
-    extern __shared__ __align__(16) unsigned char k4_smem_raw[];
-    double2 *smem = reinterpret_cast<double2 *>(k4_smem_raw);
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, q = lane & 3;
-    const int tiles_n = g.n / BN;
-    const int tile_m = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
     const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
-    const long long b = blockIdx.y;
-
-    const double2 *A = g.A + b * g.strideA + (size_t)tile_m * BM * g.n;   // rows tile_m*BM.., all k
-    const double2 *B = g.B + b * g.strideB + (size_t)tile_n * BN;         // all k, cols tile_n*BN..
+    const double2 *A = g.A + (size_t)tile_m * BM * g.n;   // rows tile_m*BM.., all k
+    const double2 *B = g.B + (size_t)tile_n * BN;         // all k, cols tile_n*BN..
 
     auto load_stage = [&](int stage, int k0) {
         double2 *sA = smem + stage * SM::STAGE_ELEMS;
@@ -113,39 +117,143 @@ k4_zgemm_kernel(const GemmArgs g) {
         }
     }
     cp_async_wait<0>();
+    __syncthreads();   // every warp is done with the stage buffers: the next tile_gemm may refill them
 
-    // ---- epilogue: D = acc + beta1 C1 + beta2 C2 + gamma I ----
+    // ---- epilogue: D = acc + beta2 C2 + beta1_lo C1 + gamma_lo I  + gamma I  + beta1 C1   (small terms first) ----
     const size_t row0 = (size_t)tile_m * BM + wm0, col0 = (size_t)tile_n * BN + wn0;
-    double2 *D = g.D + b * g.strideD;
-    const double2 *C1 = g.C1 ? g.C1 + b * g.strideC1 : nullptr;
-    const double2 *C2 = g.C2 ? g.C2 + b * g.strideC2 : nullptr;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NTL; ++nt) {
             const size_t r = row0 + 8 * mt + gq, c = col0 + 8 * nt + 2 * q;
             const size_t off = r * g.n + c;
-            double v0r = cre[mt][nt][0], v0i = cim[mt][nt][0], v1r = cre[mt][nt][1], v1i = cim[mt][nt][1];
-            if (C1) {
-                const double2 x0 = C1[off], x1 = C1[off + 1];
-                v0r += g.beta1 * x0.x; v0i += g.beta1 * x0.y; v1r += g.beta1 * x1.x; v1i += g.beta1 * x1.y;
+            double vr[2] = {cre[mt][nt][0], cre[mt][nt][1]}, vi[2] = {cim[mt][nt][0], cim[mt][nt][1]};
+            if (g.C2) {
+                const double2 x0 = g.C2[off], x1 = g.C2[off + 1];
+                vr[0] += g.beta2 * x0.x; vi[0] += g.beta2 * x0.y; vr[1] += g.beta2 * x1.x; vi[1] += g.beta2 * x1.y;
             }
-            if (C2) {
-                const double2 x0 = C2[off], x1 = C2[off + 1];
-                v0r += g.beta2 * x0.x; v0i += g.beta2 * x0.y; v1r += g.beta2 * x1.x; v1i += g.beta2 * x1.y;
+            double2 y[2] = {make_double2(0, 0), make_double2(0, 0)};
+            if (g.C1) {
+                y[0] = g.C1[off]; y[1] = g.C1[off + 1];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    vr[i] += g.beta1_lo.re * y[i].x - g.beta1_lo.im * y[i].y;
+                    vi[i] += g.beta1_lo.re * y[i].y + g.beta1_lo.im * y[i].x;
+                }
             }
-            if (r == c) { v0r = (v0r + g.gamma_lo.re) + g.gamma.re; v0i = (v0i + g.gamma_lo.im) + g.gamma.im; }
-            if (r == c + 1) { v1r = (v1r + g.gamma_lo.re) + g.gamma.re; v1i = (v1i + g.gamma_lo.im) + g.gamma.im; }
-            D[off] = make_double2(v0r, v0i);
-            D[off + 1] = make_double2(v1r, v1i);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (r == c + i) { vr[i] = (vr[i] + g.gamma_lo.re) + g.gamma.re; vi[i] = (vi[i] + g.gamma_lo.im) + g.gamma.im; }
+            if (g.C1) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    vr[i] = fma(g.beta1.re, y[i].x, fma(-g.beta1.im, y[i].y, vr[i]));
+                    vi[i] = fma(g.beta1.re, y[i].y, fma(g.beta1.im, y[i].x, vi[i]));
+                }
+            }
+            g.D[off] = make_double2(vr[0], vi[0]);
+            g.D[off + 1] = make_double2(vr[1], vi[1]);
         }
 }
 
-// Assembly of a chunk.  grid = (npad*npad/256, ceil(S/8)); H: [mat][npad*npad] row-major, zero padded.
+template <int BM, int BN, int WM, int WN>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+k4_zgemm_kernel(const GemmArgs g) {
+    extern __shared__ __align__(16) unsigned char k4_smem_raw[];
+    double2 *smem = reinterpret_cast<double2 *>(k4_smem_raw);
+    const long long b = blockIdx.y;
+    const int tiles_n = g.n / BN;
+    TileArgs t;
+    t.A = g.A + b * g.strideA;
+    t.B = g.B + b * g.strideB;
+    t.C1 = g.C1 ? g.C1 + b * g.strideC1 : nullptr;
+    t.C2 = g.C2 ? g.C2 + b * g.strideC2 : nullptr;
+    t.D = g.D + b * g.strideD;
+    t.beta1 = g.beta1; t.beta1_lo = g.beta1_lo; t.beta2 = g.beta2; t.gamma = g.gamma; t.gamma_lo = g.gamma_lo;
+    t.n = g.n;
+    tile_gemm<BM, BN, WM, WN>(smem, t, blockIdx.x / tiles_n, blockIdx.x % tiles_n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent chain kernel (npad == BM): scratch slots per CTA: 0 Y, 1 W, 2, 3 recurrence, 4, 5 running product
+// ------------------------------------------------------------------------------------------------
+template <int BM, int WM, int WN, typename IO>
+__global__ void __launch_bounds__((BM / WM) * (BM / WN) * 32)
+k4_chain_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__restrict__ carr, const double2 *__restrict__ H,
+                double2 *__restrict__ scratch, double2 *__restrict__ partials, unsigned long long nsteps) {
+    constexpr int NTHREADS = (BM / WM) * (BM / WN) * 32;
+    constexpr int NN = BM * BM;
+    extern __shared__ __align__(16) unsigned char k4_smem_raw[];
+    double2 *smem = reinterpret_cast<double2 *>(k4_smem_raw);
+    __shared__ cplx coef[kMaxTerms];
+
+    const int tid = threadIdx.x;
+    double2 *slot = scratch + (size_t)blockIdx.x * 6 * NN;
+    const unsigned long long lo = nsteps * blockIdx.x / gridDim.x, hi = nsteps * (blockIdx.x + 1) / gridDim.x;
+    int f_cur = 4;
+    bool have_f = false;
+
+    for (unsigned long long j = lo; j < hi; ++j) {
+        for (int t = tid; t < p.nterms; t += NTHREADS)
+            coef[t] = step_coefficient<IO>(p.terms[t], carr, p.pts, p.quad, p.magfac, j);
+        __syncthreads();
+        // ---- assemble Y (slot 0) and the series start values (slots 2, 3) ----
+        for (int e = tid; e < NN; e += NTHREADS) {
+            double2 x = __ldg(H + e);
+            for (int t = 0; t < p.nterms; ++t) {
+                const double2 h = __ldg(H + (size_t)p.terms[t].mat * NN + e);
+                const cplx ct = coef[t];
+                x.x += ct.re * h.x - ct.im * h.y;
+                x.y += ct.re * h.y + ct.im * h.x;
+            }
+            const double yr = x.x * p.sigma, yi = x.y * p.sigma;
+            const bool diag = (e / BM == e % BM);
+            slot[e] = make_double2(yr, yi);
+            slot[2 * NN + e] = make_double2(((prog.u.re * yr - prog.u.im * yi) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
+                                            ((prog.u.re * yi + prog.u.im * yr) + (diag ? prog.v_lo.im : 0.0)) + (diag ? prog.v.im : 0.0));
+            if (prog.init3) slot[3 * NN + e] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
+        }
+        __syncthreads();
+        // ---- series program ----
+        for (int o = 0; o < prog.nops; ++o) {
+            const SeriesOp &op = prog.ops[o];
+            TileArgs t;
+            t.A = slot + (size_t)op.A * NN;
+            t.B = slot + (size_t)op.B * NN;
+            t.C1 = op.C1 >= 0 ? slot + (size_t)op.C1 * NN : nullptr;
+            t.C2 = nullptr;
+            t.D = slot + (size_t)op.D * NN;
+            t.beta1 = op.beta1; t.beta1_lo = op.beta1_lo; t.beta2 = 0.0; t.gamma = op.gamma; t.gamma_lo = op.gamma_lo;
+            t.n = BM;
+            tile_gemm<BM, BM, WM, WN>(smem, t, 0, 0);
+            __syncthreads();
+        }
+        // ---- running product in E-form:  F <- E + F + E F  (later step on the left) ----
+        const double2 *E = slot + (size_t)prog.e_slot * NN;
+        if (!have_f) {
+            for (int e = tid; e < NN; e += NTHREADS) slot[(size_t)f_cur * NN + e] = E[e];
+            have_f = true;
+        } else {
+            TileArgs t;
+            t.A = E; t.B = slot + (size_t)f_cur * NN; t.C1 = E; t.C2 = slot + (size_t)f_cur * NN;
+            t.D = slot + (size_t)(f_cur ^ 1) * NN;
+            t.beta1 = cplx{1.0, 0.0}; t.beta1_lo = cplx{0.0, 0.0}; t.beta2 = 1.0;
+            t.gamma = cplx{0.0, 0.0}; t.gamma_lo = cplx{0.0, 0.0};
+            t.n = BM;
+            tile_gemm<BM, BM, WM, WN>(smem, t, 0, 0);
+            f_cur ^= 1;
+        }
+        __syncthreads();
+    }
+    double2 *out = partials + (size_t)blockIdx.x * NN;
+    for (int e = tid; e < NN; e += NTHREADS) out[e] = have_f ? slot[(size_t)f_cur * NN + e] : make_double2(0.0, 0.0);
+}
+
+// Batched assembly.  grid = (npad*npad/256, ceil(S/8)); H: [mat][npad*npad] row-major, zero padded.
 template <typename IO>
 __global__ void __launch_bounds__(256)
-k4_assemble_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ H,
-                   double2 *__restrict__ Y, double2 *__restrict__ S0, double2 *__restrict__ S1,
+k4_assemble_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__restrict__ carr, const double2 *__restrict__ H,
+                   double2 *__restrict__ Y, double2 *__restrict__ S2, double2 *__restrict__ S3,
                    unsigned long long step0, int S) {
     __shared__ cplx coef[kMaxTerms][8];
     const int sg0 = blockIdx.y * 8;
@@ -173,18 +281,15 @@ k4_assemble_kernel(const SeriesParams p, const IO *__restrict__ carr, const doub
         }
     }
     const bool diag = (r == c);
-    const int M = p.M;
-    const cplx aM = p.a[M], aM1 = p.a[M - 1], aM1lo = p.a_lo[M - 1];
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         if (s < ns) {
             const size_t o = (size_t)(sg0 + s) * nn + e;
             const double yr = xr[s] * p.sigma, yi = xi[s] * p.sigma;
             Y[o] = make_double2(yr, yi);
-            // M == 1: S0 holds E = a_1 Y + a0' I directly (a[M-1] == a[0]); S1 unused
-            S0[o] = make_double2(((aM.re * yr - aM.im * yi) + (diag ? aM1lo.re : 0.0)) + (diag ? aM1.re : 0.0),
-                                 ((aM.re * yi + aM.im * yr) + (diag ? aM1lo.im : 0.0)) + (diag ? aM1.im : 0.0));
-            S1[o] = make_double2(diag ? aM.re : 0.0, diag ? aM.im : 0.0);
+            S2[o] = make_double2(((prog.u.re * yr - prog.u.im * yi) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
+                                 ((prog.u.re * yi + prog.u.im * yr) + (diag ? prog.v_lo.im : 0.0)) + (diag ? prog.v.im : 0.0));
+            if (prog.init3) S3[o] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
         }
     }
 }
@@ -205,18 +310,54 @@ __global__ void k4_finish_kernel(const double2 *__restrict__ E, int n, int npad,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// The series as a program over slots (k4_gemm.hpp).  Clenshaw: B_k = B_{k+1} Y - B_{k+2} + a_k I, E = B_1 Y - 2 B_2 + a0' I
+// (parament.cpp:569-652 restated in E-form).  Horner: W = Y^2, R <- R W + c_{2i+1} Y + c_{2i} I on the monomial
+// coefficients of the same polynomial (p.horner, coefficients in p.a).
+SeriesProgram build_program(const SeriesParams &p) {
+    SeriesProgram g{};
+    const int M = p.M;
+    const cplx zero{0.0, 0.0};
+    auto push = [&](int A, int B, int C1, int D, cplx b1, cplx b1lo, cplx ga, cplx galo) {
+        SeriesOp &o = g.ops[g.nops++];
+        o.A = A; o.B = B; o.C1 = C1; o.D = D; o.beta1 = b1; o.beta1_lo = b1lo; o.gamma = ga; o.gamma_lo = galo;
+    };
+    if (p.horner) {
+        const int L = M >> 1;
+        g.u = p.a[2 * L + 1]; g.v = p.a[2 * L]; g.v_lo = p.a_lo[2 * L]; g.init3 = 0; g.w = zero;
+        push(0, 0, -1, 1, zero, zero, zero, zero);                       // W = Y Y
+        int cur = 2;
+        for (int i = L - 1; i >= 0; --i) {
+            push(cur, 1, 0, cur ^ 1, p.a[2 * i + 1], p.a_lo[2 * i + 1], p.a[2 * i], p.a_lo[2 * i]);
+            cur ^= 1;
+        }
+        g.e_slot = cur;
+    } else if (M == 1) {
+        g.u = p.a[1]; g.v = p.a[0]; g.v_lo = p.a_lo[0]; g.init3 = 0; g.w = zero;
+        g.e_slot = 2;
+    } else {
+        g.u = p.a[M]; g.v = p.a[M - 1]; g.v_lo = p.a_lo[M - 1]; g.init3 = 1; g.w = p.a[M];
+        int cur = 2;                                                       // slot 2 = B_{M-1}, slot 3 = B_M
+        for (int k = M - 2; k >= 1; --k) {
+            push(cur, 0, cur ^ 1, cur ^ 1, cplx{-1.0, 0.0}, zero, p.a[k], p.a_lo[k]);
+            cur ^= 1;
+        }
+        push(cur, 0, cur ^ 1, cur ^ 1, cplx{-2.0, 0.0}, zero, p.a[0], p.a_lo[0]);
+        g.e_slot = cur ^ 1;
+    }
+    return g;
+}
+
+template <typename K>
+static cudaError_t opt_in_smem(K kern, size_t bytes) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 template <int BM, int BN, int WM, int WN>
 static cudaError_t launch_gemm_t(const GemmArgs &g, cudaStream_t stream) {
     using SM = K4Smem<BM, BN>;
-    static bool configured[64] = {};   // the opt-in shared-memory size is a per-device function attribute
     auto kern = k4_zgemm_kernel<BM, BN, WM, WN>;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
+    cudaError_t e = opt_in_smem(kern, SM::BYTES);   // per-device function attribute; cheap, so set on every launch
+    if (e != cudaSuccess) return e;
     dim3 grid((g.n / BM) * (g.n / BN), g.batch);
     kern<<<grid, (BM / WM) * (BN / WN) * 32, SM::BYTES, stream>>>(g);
     return cudaGetLastError();
@@ -229,17 +370,62 @@ cudaError_t k4_gemm(const GemmArgs &g, cudaStream_t stream) {
 }
 
 int k4_pad(int n) { return n <= 32 ? 32 : ((n + 63) / 64) * 64; }
-
 int k4_tiles(int npad) { return npad % 64 == 0 ? (npad / 64) * (npad / 64) : 1; }
 
-cudaError_t k4_assemble(bool fp64_io, const SeriesParams &p, const void *carr, const double2 *H, double2 *Y,
-                        double2 *S0, double2 *S1, unsigned long long step0, int S, cudaStream_t stream) {
+int k4_wave_slots(int npad, int num_sms) {
+    int per_sm = 0;
+    if (npad % 64 == 0) {
+        opt_in_smem(k4_zgemm_kernel<64, 64, 32, 16>, K4Smem<64, 64>::BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_zgemm_kernel<64, 64, 32, 16>, 256, K4Smem<64, 64>::BYTES);
+    } else {
+        opt_in_smem(k4_zgemm_kernel<32, 32, 16, 16>, K4Smem<32, 32>::BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_zgemm_kernel<32, 32, 16, 16>, 128, K4Smem<32, 32>::BYTES);
+    }
+    if (per_sm < 1) per_sm = 1;
+    return per_sm * num_sms;
+}
+
+int k4_chain_slots(int npad, int num_sms) {
+    int per_sm = 0;
+    if (npad == 64) {
+        opt_in_smem(k4_chain_kernel<64, 32, 16, double2>, K4Smem<64, 64>::BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_chain_kernel<64, 32, 16, double2>, 256, K4Smem<64, 64>::BYTES);
+    } else {
+        opt_in_smem(k4_chain_kernel<32, 16, 16, double2>, K4Smem<32, 32>::BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_chain_kernel<32, 16, 16, double2>, 128, K4Smem<32, 32>::BYTES);
+    }
+    if (per_sm < 1) per_sm = 1;
+    return per_sm * num_sms;
+}
+
+template <int BM, int WM, int WN, typename IO>
+static cudaError_t launch_chain_t(const SeriesParams &p, const SeriesProgram &prog, const IO *carr, const double2 *H,
+                                  double2 *scratch, double2 *partials, unsigned long long nsteps, int grid, cudaStream_t stream) {
+    using SM = K4Smem<BM, BM>;
+    auto kern = k4_chain_kernel<BM, WM, WN, IO>;
+    cudaError_t e = opt_in_smem(kern, SM::BYTES);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, (BM / WM) * (BM / WN) * 32, SM::BYTES, stream>>>(p, prog, carr, H, scratch, partials, nsteps);
+    return cudaGetLastError();
+}
+
+cudaError_t k4_chain(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,
+                     double2 *scratch, double2 *partials, unsigned long long nsteps, int grid, cudaStream_t stream) {
+    if (p.npad == 64)
+        return fp64_io ? launch_chain_t<64, 32, 16, double2>(p, prog, (const double2 *)carr, H, scratch, partials, nsteps, grid, stream)
+                       : launch_chain_t<64, 32, 16, float2>(p, prog, (const float2 *)carr, H, scratch, partials, nsteps, grid, stream);
+    return fp64_io ? launch_chain_t<32, 16, 16, double2>(p, prog, (const double2 *)carr, H, scratch, partials, nsteps, grid, stream)
+                   : launch_chain_t<32, 16, 16, float2>(p, prog, (const float2 *)carr, H, scratch, partials, nsteps, grid, stream);
+}
+
+cudaError_t k4_assemble(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,
+                        double2 *slot0, double2 *slot2, double2 *slot3, unsigned long long step0, int S, cudaStream_t stream) {
     const size_t nn = (size_t)p.npad * p.npad;
     dim3 grid((unsigned)((nn + 255) / 256), (unsigned)((S + 7) / 8));
     if (fp64_io)
-        k4_assemble_kernel<double2><<<grid, 256, 0, stream>>>(p, (const double2 *)carr, H, Y, S0, S1, step0, S);
+        k4_assemble_kernel<double2><<<grid, 256, 0, stream>>>(p, prog, (const double2 *)carr, H, slot0, slot2, slot3, step0, S);
     else
-        k4_assemble_kernel<float2><<<grid, 256, 0, stream>>>(p, (const float2 *)carr, H, Y, S0, S1, step0, S);
+        k4_assemble_kernel<float2><<<grid, 256, 0, stream>>>(p, prog, (const float2 *)carr, H, slot0, slot2, slot3, step0, S);
     return cudaGetLastError();
 }
 

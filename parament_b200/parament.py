@@ -176,7 +176,8 @@ class Parament:
         return lib.Parament_lastStat(self._handle, int(key))
 
     def stats(self):
-        names = ["device_ms", "launches", "degree_used", "degree_reference", "steps", "family", "h2d_bytes", "d2h_bytes", "hnorm"]
+        names = ["device_ms", "launches", "degree_used", "degree_reference", "steps", "family", "h2d_bytes", "d2h_bytes", "hnorm",
+                 "horner", "products_per_step"]
         return {n: self.stat(i) for i, n in enumerate(names)}
 
     # ---- errors ----------------------------------------------------------------------------------

@@ -79,7 +79,7 @@ def test_debug_expm(pb):
 def test_extended_cases_vs_oracle(pb, case):
     U, fam = run_case(pb, case)
     n = case["H0"].shape[0]
-    assert fam == (1 if n <= 16 else 3)
+    assert fam == (1 if n <= 16 else (2 if n <= 64 else 3))
     if case.get("mmax"):
         # a forced degree truncates the series: compare with the oracle only when the degree is sufficient
         from oracle.reference_emulation import select_iteration_cycles
@@ -90,6 +90,26 @@ def test_extended_cases_vs_oracle(pb, case):
             pytest.skip("forced degree below the table value")
     Uo = equiprop_oracle(case["H0"], case["H1"], case["carr"], case["dt"], case["quadrature"], case["use_magnus"], case["precision"])
     assert rel_frobenius(U, Uo) < TOL[case["precision"]]
+
+
+@pytest.mark.parametrize("case", [c for c in extended_cases() if c["name"].startswith("fp64")], ids=lambda c: c["name"])
+def test_extended_cases_clenshaw_path(pb, case, monkeypatch):
+    """The same cases with the Horner-in-Y^2 evaluation disabled: the plain Clenshaw recurrence of the reference
+    (parament.cpp:569-652) must give the same propagators (it is also what runs for Hnorm*h > 1)."""
+    monkeypatch.setenv("PARAMENT_SERIES", "clenshaw")
+    with pb.Parament(case["precision"]) as ctx:
+        ctx.set_hamiltonian(case["H0"], *case["H1"], use_magnus=case["use_magnus"], quadrature_mode=case["quadrature"])
+        if case.get("mmax"):
+            ctx.set_iteration_cycles(case["mmax"])
+        U = ctx.equiprop(case["dt"], *case["carr"])
+        assert ctx.stat(9) == 0
+    monkeypatch.delenv("PARAMENT_SERIES")
+    with pb.Parament(case["precision"]) as ctx:
+        ctx.set_hamiltonian(case["H0"], *case["H1"], use_magnus=case["use_magnus"], quadrature_mode=case["quadrature"])
+        if case.get("mmax"):
+            ctx.set_iteration_cycles(case["mmax"])
+        V = ctx.equiprop(case["dt"], *case["carr"])
+    assert rel_frobenius(U, V) < 1e-13
 
 
 @pytest.mark.parametrize("case", [c for c in extended_cases() + reference_test_cases()], ids=lambda c: c["name"])
