@@ -329,6 +329,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     // c_m = 2^-m sum_k alpha_k t_{k,m}, alpha_0 = J0 - 1, alpha_k = 2 (-i)^k J_k, t_{k,m} the integer coefficients of T_k,
     // converted in long double.  Restricted to x <= 1, where every term of the monomial sum is <= 1 (no cancellation).
     p.horner = 0;
+    const double sigma0 = p.sigma;
     if (c->series_mode != 1 && M_used >= 3 && M_used <= 24 && (double)x <= 1.0) {
         p.horner = 1;
         const int d = M_used;
@@ -351,9 +352,12 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
                 }
             }
             cr /= pow2; ci /= pow2;
+            // fold sigma^m in: the kernels then work on the unscaled X = H0 + sum c_t H_t (p.sigma = 1)
+            for (int q = 0; q < m; ++q) { cr *= (long double)sigma0; ci *= (long double)sigma0; }
             p.a[m] = cplx{(double)cr, (double)ci};
             p.a_lo[m] = cplx{(double)(cr - (long double)p.a[m].re), (double)(ci - (long double)p.a[m].im)};
         }
+        p.sigma = 1.0;
     }
     c->stat_horner = p.horner;
     const int A = c->amps, Ain = (int)s.amps;

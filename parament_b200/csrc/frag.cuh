@@ -29,6 +29,11 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
         : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// -x on the integer pipe: the FP64 pipe is shared with DMMA, a DADD/DMUL spent on a sign flip is taken from it.
+__device__ __forceinline__ double neg(double x) {
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
 template <int NT>
 struct AccFrag {
     double re[NT][NT][2];
@@ -81,7 +86,7 @@ __device__ __forceinline__ void transpose_as_bfrag(BFrag<NT> &B, const AccFrag<N
         for (int nt = 0; nt < NT; ++nt) {
             B.re[kt][nt] = E.re[nt][kt >> 1][kt & 1];
             B.im[kt][nt] = E.im[nt][kt >> 1][kt & 1];
-            B.nim[kt][nt] = -E.im[nt][kt >> 1][kt & 1];
+            B.nim[kt][nt] = neg(E.im[nt][kt >> 1][kt & 1]);
         }
 }
 
@@ -203,7 +208,7 @@ __device__ __forceinline__ void load_bfrag(BFrag<NT> &B, const double2 *m, int l
             const double2 v = m[bf_row(lane, kt) * ld + bf_col(lane, nt)];
             B.re[kt][nt] = v.x;
             B.im[kt][nt] = v.y;
-            B.nim[kt][nt] = -v.y;
+            B.nim[kt][nt] = neg(v.y);
         }
 }
 

@@ -106,11 +106,13 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                     }
                 }
             }
+            if (!HORNER) {   // Horner form: sigma is folded into the monomial coefficients on the host, Y == X
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                (&Ya.re[0][0][0])[e] *= p.sigma; (&Ya.im[0][0][0])[e] *= p.sigma;
-                (&Yb.re[0][0])[e] *= p.sigma;    (&Yb.im[0][0])[e] *= p.sigma;
-                (&Yb.nim[0][0])[e] = -(&Yb.im[0][0])[e];
+                for (int e = 0; e < NE; ++e) {
+                    (&Ya.re[0][0][0])[e] *= p.sigma; (&Ya.im[0][0][0])[e] *= p.sigma;
+                    (&Yb.re[0][0])[e] *= p.sigma;    (&Yb.im[0][0])[e] *= p.sigma;
+                    (&Yb.nim[0][0])[e] = neg((&Yb.im[0][0])[e]);
+                }
             }
 
             AccFrag<NT> S0, S1;
@@ -139,7 +141,8 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                 horner_addend<NT, false>(S0, p.a[2 * L + 1].im, 0.0, Ya, p.a[2 * L].re, 0.0, lane);   // B_L (c_{M+1} = 0 for even M)
 #pragma unroll 1
                 for (int i = L - 1; i >= 0; --i) {
-                    if (i <= 1) horner_addend<NT, true>(S1, p.a[2 * i + 1].im, p.a_lo[2 * i + 1].im, Ya, p.a[2 * i].re, p.a_lo[2 * i].re, lane);
+                    if (i <= 1 && sizeof(IO) == sizeof(double2))   // sub-ulp remainders only matter for complex128 contexts
+                        horner_addend<NT, true>(S1, p.a[2 * i + 1].im, p.a_lo[2 * i + 1].im, Ya, p.a[2 * i].re, p.a_lo[2 * i].re, lane);
                     else        horner_addend<NT, false>(S1, p.a[2 * i + 1].im, 0.0, Ya, p.a[2 * i].re, 0.0, lane);
                     cmma<NT>(S1, S0, Wb);                   // R <- R W + B_i
                     const AccFrag<NT> T = S0; S0 = S1; S1 = T;
