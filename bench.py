@@ -276,8 +276,12 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": in_bytes * world,
                     "d2h_bytes_per_step": out_host.nbytes * world, "ms_per_step": e2e_ms / e2e_steps, "timed_steps": e2e_steps,
                     "api": "Parament_equipropBatch (host pointers, pinned)"},
+            # `achieved` = algorithmic flops of the reference's recurrence / time.  When the Horner-in-Y^2
+            # evaluation executes fewer products than that recurrence, `frac` is computed from the EXECUTED flops so that
+            # it stays a pipe utilisation (<= 1); the algorithmic figure is kept in `algorithmic_frac`.
             "roofline": {"bound": "fp64_tensor", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s",
-                         "frac": achieved / peak_dmma if peak_dmma > 0 else None, "traffic": traffic,
+                         "frac": min(achieved, F_exe * per_gpu_rate * 1e-12) / peak_dmma if peak_dmma > 0 else None,
+                         "algorithmic_frac": achieved / peak_dmma if peak_dmma > 0 else None, "traffic": traffic,
                          "peak_source": "Parament_measurePeak(DMMA mma.sync.m8n8k4.f64) in this process; MEASURED_PEAKS.json has no FP64 figure",
                          "kernel": {1: "k1_chain_kernel", 2: "k4_chain_kernel", 3: "k4_zgemm_kernel"}[family],
                          "kernel_ms_per_launch": kernel_ms,
@@ -301,11 +305,33 @@ def run_ours(args):
 # ----------------------------------------------------------------------------------------------------------
 # CPU oracle baseline and the reference arm  (the only places that execute oracle/)
 # ----------------------------------------------------------------------------------------------------------
+def _oracle_pulse(args):
+    from oracle.equiprop_oracle import equiprop_oracle, _single_thread_blas
+    H0, H1, carr, dt, quad, mag, prec = args
+    with _single_thread_blas():
+        return equiprop_oracle(H0, H1, carr, dt, quad, mag, prec)
+
+
 def cpu_baseline(w, budget_s=12.0):
     from oracle.equiprop_oracle import equiprop_oracle
     cores = os.cpu_count() or 1
     workers = min(cores, 32)
-    carr = w.carr[0] if w.batch > 1 else w.carr
+    if w.batch > 1:
+        # ensemble: whole pulses, one per worker process at a time
+        from concurrent.futures import ProcessPoolExecutor
+        t = time.time()
+        _oracle_pulse((w.H0, w.H1, w.carr[0], w.dt, w.quadrature, w.use_magnus, w.precision))
+        per_pulse = time.time() - t
+        npulses = int(max(workers, min(w.batch, budget_s / per_pulse * workers * 0.7)))
+        jobs = [(w.H0, w.H1, w.carr[b], w.dt, w.quadrature, w.use_magnus, w.precision) for b in range(npulses)]
+        t = time.time()
+        with ProcessPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(_oracle_pulse, jobs, chunksize=max(1, npulses // (4 * workers))))
+        dt = time.time() - t
+        return {"value": npulses * w.steps / dt, "unit": "steps/s", "cores": workers, "kind": "port",
+                "sample": f"first {npulses} pulses of the ensemble ({npulses * w.steps} effective steps), float64 scipy.linalg.expm + "
+                          f"ordered product, {workers} processes x 1 BLAS thread, {dt:.1f} s"}
+    carr = w.carr
     per_step_pts = 2 if (w.use_magnus or w.quadrature == "simpson") else 1
     # probe, then size the sample for ~budget_s of CPU work
     probe_steps = max(8, min(w.steps, {2: 4000, 8: 4000, 16: 2000, 64: 200, 256: 16}.get(w.dim, 100)))

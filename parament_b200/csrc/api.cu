@@ -61,6 +61,16 @@ bool ensure_pinned(void *&p, size_t &have, size_t bytes) {
     return true;
 }
 
+bool create_copy_events(Context *c) {
+    for (int i = 0; i < 8; ++i)
+        if (!PB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming))) return false;
+    return true;
+}
+void destroy_copy_events(Context *c) {
+    for (int i = 0; i < 8; ++i)
+        if (c->ev_copy[i]) { cudaEventDestroy(c->ev_copy[i]); c->ev_copy[i] = nullptr; }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // create / destroy                                                   (reference parament.cpp:51-205)
 // ---------------------------------------------------------------------------------------------------
@@ -83,6 +93,7 @@ Parament_ErrorCode create_ctx(Context **out, bool fp64) {
     if (!PB_CUDA_OK(cudaSetDevice(dev)) ||
         !PB_CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, dev)) ||
         !PB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
+        !PB_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) || !create_copy_events(c) ||
         !PB_CUDA_OK(cudaEventCreate(&c->ev_start)) || !PB_CUDA_OK(cudaEventCreate(&c->ev_stop))) {
         cudaGetLastError();
         delete c;
@@ -104,6 +115,8 @@ Parament_ErrorCode destroy_ctx(Context *c) {
     if (c->h_out) cudaFreeHost(c->h_out);
     cudaEventDestroy(c->ev_start);
     cudaEventDestroy(c->ev_stop);
+    destroy_copy_events(c);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     c->magic = 0;
     delete c;
@@ -548,15 +561,85 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
     }
     if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, st))) return PARAMENT_STATUS_CUBLAS_FAILED;
     if (c->family == 1) {
-        if (launch_k1(c->npad, c->fp64, p, carr_dev, (const double2 *)c->d_H.ptr, (double2 *)c->d_partials.ptr, s.batch, plan,
-                      0, s.nsteps, out_dev, st) != cudaSuccess)
-            return PARAMENT_STATUS_CUBLAS_FAILED;
-        c->stat_launches = 2;
+        PB_LAUNCH(launch_k1_chain(c->npad, c->fp64, p, carr_dev, (const double2 *)c->d_H.ptr, (double2 *)c->d_partials.ptr,
+                                  s.batch, plan, 0, s.nsteps, st));
+        PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, plan.partials_per_pulse, c->dim,
+                                   out_dev, s.batch, plan.k3_warps, st));
     } else {
         ec = c->family == 2 ? run_family2(c, p, carr_dev, s, out_dev, st) : run_family3(c, p, carr_dev, s, out_dev, st);
         if (ec != PARAMENT_STATUS_SUCCESS) return ec;
     }
     if (!PB_CUDA_OK(cudaEventRecord(c->ev_stop, st))) return PARAMENT_STATUS_CUBLAS_FAILED;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+// Host-pointer path of the register-resident family with the H2D copy of the amplitude stream overlapped with the
+// kernels: the work is cut into G groups (pulse ranges of an ensemble, time ranges of a single pulse); group g+1 is
+// copied on the copy stream while group g is propagated.  Replaces the reference's one blocking cudaMemcpy of the
+// whole array before any work starts (parament.cpp:477).
+template <typename T>
+Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts, size_t p_lo, size_t seg, const CallSpec &s,
+                                     int G, void *out_dev) {
+    SeriesParams p;
+    Parament_ErrorCode ec = build_series(c, s, p);
+    if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+    c->stat_steps = s.nsteps;
+    c->stat_launches = 0;
+    const int n = c->dim, NP2 = c->npad * c->npad;
+    T *dcarr = (T *)c->d_carr.ptr;
+    const bool horner = p.horner != 0;
+    if (G > 8) G = 8;
+    auto copy_arrays = [&](size_t a0, size_t a1, size_t pt0, size_t npts) -> bool {
+        // arrays [a0, a1) of the device buffer (stride seg) <- host arrays (stride pts), points [pt0, pt0 + npts) of the slice
+        if (seg == pts && npts == seg)
+            return PB_CUDA_OK(cudaMemcpyAsync(dcarr + a0 * seg, carr + a0 * pts, (a1 - a0) * seg * sizeof(T), cudaMemcpyHostToDevice, c->copy_stream));
+        // strided: one 2-D copy (rows = control arrays) instead of one call per array
+        return PB_CUDA_OK(cudaMemcpy2DAsync(dcarr + a0 * seg + pt0, seg * sizeof(T), carr + a0 * pts + p_lo + pt0, (size_t)pts * sizeof(T),
+                                            npts * sizeof(T), a1 - a0, cudaMemcpyHostToDevice, c->copy_stream));
+    };
+    if (s.batch > 1) {
+        const unsigned int bg = (s.batch + G - 1) / G;
+        const K1Plan big = plan_k1(c->npad, bg, s.nsteps, c->num_sms, horner);
+        if (!ensure_dev(c->d_partials, big.partial_elems * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+        if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, c->stream))) return PARAMENT_STATUS_CUBLAS_FAILED;
+        int g = 0;
+        for (unsigned int b0 = 0; b0 < s.batch; b0 += bg, ++g) {
+            const unsigned int b1 = std::min(s.batch, b0 + bg);
+            if (!copy_arrays((size_t)b0 * s.amps, (size_t)b1 * s.amps, 0, seg) ||
+                !PB_CUDA_OK(cudaEventRecord(c->ev_copy[g], c->copy_stream)) || !PB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0)))
+                return PARAMENT_STATUS_CUBLAS_FAILED;
+            const K1Plan plan = plan_k1(c->npad, b1 - b0, s.nsteps, c->num_sms, horner);
+            PB_LAUNCH(launch_k1_chain(c->npad, c->fp64, p, dcarr + (size_t)b0 * s.amps * seg, (const double2 *)c->d_H.ptr,
+                                      (double2 *)c->d_partials.ptr, b1 - b0, plan, 0, s.nsteps, c->stream));
+            PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, plan.partials_per_pulse, n,
+                                       (T *)out_dev + (size_t)b0 * n * n, b1 - b0, plan.k3_warps, c->stream));
+        }
+    } else {
+        const int r = points_per_step(c), ov = point_overlap(c);
+        unsigned long long bound[9];
+        K1Plan plans[8];
+        size_t off[9];
+        off[0] = 0;
+        for (int g = 0; g <= G; ++g) bound[g] = s.nsteps * g / G;
+        for (int g = 0; g < G; ++g) {
+            plans[g] = plan_k1(c->npad, 1, bound[g + 1] - bound[g], c->num_sms, horner);
+            off[g + 1] = off[g] + plans[g].partials_per_pulse;
+        }
+        if (!ensure_dev(c->d_partials, off[G] * NP2 * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+        if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, c->stream))) return PARAMENT_STATUS_CUBLAS_FAILED;
+        for (int g = 0; g < G; ++g) {
+            const size_t pt0 = (size_t)r * bound[g] + (g == 0 ? 0 : ov);            // the overlap point came with the previous group
+            const size_t pt1 = (size_t)r * bound[g + 1] + ov;
+            if (!copy_arrays(0, s.amps, pt0, pt1 - pt0) ||
+                !PB_CUDA_OK(cudaEventRecord(c->ev_copy[g], c->copy_stream)) || !PB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0)))
+                return PARAMENT_STATUS_CUBLAS_FAILED;
+            PB_LAUNCH(launch_k1_chain(c->npad, c->fp64, p, dcarr, (const double2 *)c->d_H.ptr, (double2 *)c->d_partials.ptr + off[g] * NP2,
+                                      1, plans[g], bound[g], bound[g + 1], c->stream));
+        }
+        PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, (unsigned int)off[G], n, out_dev, 1,
+                                   k3_warps_for((unsigned int)off[G]), c->stream));
+    }
+    if (!PB_CUDA_OK(cudaEventRecord(c->ev_stop, c->stream))) return PARAMENT_STATUS_CUBLAS_FAILED;
     return PARAMENT_STATUS_SUCCESS;
 }
 
@@ -606,17 +689,25 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
     const size_t in_bytes = arrays * seg * sizeof(T);
     const size_t out_bytes = (size_t)batch * n * n * sizeof(T);
     if (!ensure_dev(c->d_carr, in_bytes) || !ensure_dev(c->d_out, out_bytes)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
-    if (seg == pts) {
-        if (in_bytes && !PB_CUDA_OK(cudaMemcpyAsync(c->d_carr.ptr, carr, in_bytes, cudaMemcpyHostToDevice, c->stream)))
-            return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
-    } else {
-        for (size_t a = 0; a < arrays; ++a)
-            if (!PB_CUDA_OK(cudaMemcpyAsync((T *)c->d_carr.ptr + a * seg, carr + a * pts + p_lo, seg * sizeof(T),
-                                            cudaMemcpyHostToDevice, c->stream)))
-                return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
-    }
+    // groups of >= 4 MB (and >= 16k steps along the time axis) for the copy / compute overlap of the register-resident family
+    int G = (int)std::min<size_t>(8, in_bytes / ((size_t)4 << 20));
+    if (batch == 1) G = (int)std::min<unsigned long long>(G, s.nsteps / 16384);
+    else G = (int)std::min<unsigned int>(G, batch);
+    Parament_ErrorCode ec;
     c->stat_h2d = (double)in_bytes;
-    Parament_ErrorCode ec = propagate_device(c, c->d_carr.ptr, s, c->d_out.ptr, c->stream);
+    if (c->family == 1 && G >= 2) {
+        ec = pipelined_family1<T>(c, carr, pts, p_lo, seg, s, G, c->d_out.ptr);
+    } else {
+        if (seg == pts) {
+            if (in_bytes && !PB_CUDA_OK(cudaMemcpyAsync(c->d_carr.ptr, carr, in_bytes, cudaMemcpyHostToDevice, c->stream)))
+                return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+        } else {
+            if (!PB_CUDA_OK(cudaMemcpy2DAsync(c->d_carr.ptr, seg * sizeof(T), carr + p_lo, (size_t)pts * sizeof(T), seg * sizeof(T), arrays,
+                                              cudaMemcpyHostToDevice, c->stream)))
+                return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+        }
+        ec = propagate_device(c, c->d_carr.ptr, s, c->d_out.ptr, c->stream);
+    }
     if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
     if (!PB_CUDA_OK(cudaMemcpyAsync(out, c->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, c->stream)) ||
         !PB_CUDA_OK(cudaStreamSynchronize(c->stream)))
@@ -867,12 +958,14 @@ Parament_ErrorCode Parament_setDevice(void *h, int device) {
     cudaStreamSynchronize(c->stream);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
     free_dev(c->d_Y); free_dev(c->d_W); free_dev(c->d_S0); free_dev(c->d_S1); free_dev(c->d_pending); free_dev(c->d_tree);
-    cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); cudaStreamDestroy(c->stream);
+    cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); destroy_copy_events(c);
+    cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->stream);
     c->device = device;
     c->have_hamiltonian = false;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess || !create_copy_events(c) ||
         cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess)
         return fail(c, PARAMENT_STATUS_CUBLAS_INIT_FAILED);
     return PARAMENT_STATUS_SUCCESS;

@@ -23,6 +23,8 @@ struct Context {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;        // H2D of the amplitude stream, overlapped with the kernels
+    cudaEvent_t ev_copy[8] = {};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     Parament_ErrorCode lastError = PARAMENT_STATUS_SUCCESS;
 

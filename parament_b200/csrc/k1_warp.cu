@@ -237,25 +237,24 @@ k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, int n, I
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
 template <int NT, typename IO, int HORNER>
-static cudaError_t launch_k1_tt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
-                               unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
-                               unsigned long long step_hi, IO *out, cudaStream_t stream) {
+static cudaError_t launch_chain_tt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
+                                   unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
+                                   unsigned long long step_hi, cudaStream_t stream) {
     k1_chain_kernel<NT, IO, HORNER><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
-                                                                      plan.chunks_per_pulse, step_lo, step_hi,
-                                                                      plan.reduce_in_cta);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    k3_reduce_kernel<NT, IO><<<batch, 32 * plan.k3_warps, 0, stream>>>(partials, plan.partials_per_pulse, p.n, out);
+                                                                              plan.chunks_per_pulse, step_lo, step_hi,
+                                                                              plan.reduce_in_cta);
     return cudaGetLastError();
 }
 
 template <int NT, typename IO>
-static cudaError_t launch_k1_t(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
-                               unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
-                               unsigned long long step_hi, IO *out, cudaStream_t stream) {
-    return p.horner ? launch_k1_tt<NT, IO, 1>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, out, stream)
-                    : launch_k1_tt<NT, IO, 0>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, out, stream);
+static cudaError_t launch_chain_t(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
+                                  unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
+                                  unsigned long long step_hi, cudaStream_t stream) {
+    return p.horner ? launch_chain_tt<NT, IO, 1>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream)
+                    : launch_chain_tt<NT, IO, 0>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
 }
+
+int k3_warps_for(unsigned int partials_per_pulse);
 
 K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms, bool horner) {
     K1Plan plan{};
@@ -277,20 +276,34 @@ K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_
     }
     const unsigned long long total_warps = (unsigned long long)batch * plan.chunks_per_pulse;
     plan.grid = (unsigned int)((total_warps + K1_WARPS - 1) / K1_WARPS);
-    plan.k3_warps = plan.partials_per_pulse >= 64 ? 8 : (plan.partials_per_pulse >= 8 ? 4 : 1);
+    plan.k3_warps = k3_warps_for(plan.partials_per_pulse);
     plan.partial_elems = (size_t)batch * plan.partials_per_pulse * npad * npad;
     return plan;
 }
 
-cudaError_t launch_k1(int npad, bool fp64_io, const SeriesParams &p, const void *carr, const double2 *Hfrag,
-                      double2 *partials, unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
-                      unsigned long long step_hi, void *out, cudaStream_t stream) {
+cudaError_t launch_k1_chain(int npad, bool fp64_io, const SeriesParams &p, const void *carr, const double2 *Hfrag,
+                            double2 *partials, unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
+                            unsigned long long step_hi, cudaStream_t stream) {
     if (npad == 8) {
-        return fp64_io ? launch_k1_t<1, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, (double2 *)out, stream)
-                       : launch_k1_t<1, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, (float2 *)out, stream);
+        return fp64_io ? launch_chain_t<1, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream)
+                       : launch_chain_t<1, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
     }
-    return fp64_io ? launch_k1_t<2, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, (double2 *)out, stream)
-                   : launch_k1_t<2, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, (float2 *)out, stream);
+    return fp64_io ? launch_chain_t<2, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream)
+                   : launch_chain_t<2, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
 }
+
+cudaError_t launch_k3_reduce(int npad, bool fp64_io, const double2 *partials, unsigned int partials_per_pulse, int n,
+                             void *out, unsigned int batch, int k3_warps, cudaStream_t stream) {
+    if (npad == 8) {
+        if (fp64_io) k3_reduce_kernel<1, double2><<<batch, 32 * k3_warps, 0, stream>>>(partials, partials_per_pulse, n, (double2 *)out);
+        else         k3_reduce_kernel<1, float2><<<batch, 32 * k3_warps, 0, stream>>>(partials, partials_per_pulse, n, (float2 *)out);
+    } else {
+        if (fp64_io) k3_reduce_kernel<2, double2><<<batch, 32 * k3_warps, 0, stream>>>(partials, partials_per_pulse, n, (double2 *)out);
+        else         k3_reduce_kernel<2, float2><<<batch, 32 * k3_warps, 0, stream>>>(partials, partials_per_pulse, n, (float2 *)out);
+    }
+    return cudaGetLastError();
+}
+
+int k3_warps_for(unsigned int partials_per_pulse) { return partials_per_pulse >= 64 ? 8 : (partials_per_pulse >= 8 ? 4 : 1); }
 
 }  // namespace pb

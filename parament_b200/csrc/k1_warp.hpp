@@ -18,8 +18,13 @@ struct K1Plan {
 K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms, bool horner);
 
 // carr / out are device pointers in the context precision; Hfrag is the fragment-ordered matrix table.
-cudaError_t launch_k1(int npad, bool fp64_io, const SeriesParams &p, const void *carr, const double2 *Hfrag,
-                      double2 *partials, unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
-                      unsigned long long step_hi, void *out, cudaStream_t stream);
+// The chain kernel (kernels 1+2) leaves plan.partials_per_pulse partial products per pulse at `partials`; the reduce
+// kernel (kernel 3) combines `partials_per_pulse` consecutive partials of each pulse in order and writes the propagator.
+cudaError_t launch_k1_chain(int npad, bool fp64_io, const SeriesParams &p, const void *carr, const double2 *Hfrag,
+                            double2 *partials, unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
+                            unsigned long long step_hi, cudaStream_t stream);
+cudaError_t launch_k3_reduce(int npad, bool fp64_io, const double2 *partials, unsigned int partials_per_pulse, int n,
+                             void *out, unsigned int batch, int k3_warps, cudaStream_t stream);
+int k3_warps_for(unsigned int partials_per_pulse);
 
 }  // namespace pb

@@ -25,3 +25,26 @@ if __name__ == "__main__":
     sweep("C1", [10000])
     sweep("C3", [2000, 20000], reps=2)
     sweep("C4", [200, 1000], reps=2)
+
+def e2e(name, reps=5, pinned=False, **kw):
+    import torch
+    w = make_workload(name, **kw)
+    carr = np.ascontiguousarray(w.carr if w.batch > 1 else w.carr[None])
+    if pinned:
+        t = torch.from_numpy(carr).pin_memory(); carr = t.numpy()
+    with pb.Parament(w.precision) as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=w.use_magnus, quadrature_mode=w.quadrature)
+        fn = getattr(pb._lib.lib, "Parament_equipropBatch" + ("_fp64" if w.precision == "fp64" else ""))
+        out = np.zeros((w.batch, w.dim, w.dim), dtype=w.ctype)
+        best = 1e9
+        for r in range(reps):
+            t0 = time.time()
+            ec = fn(ctx._handle, carr.reshape(-1), float(w.dt), w.pts, w.amps, w.batch, out.reshape(-1))
+            best = min(best, time.time() - t0)
+        print(f"e2e {name} pinned={pinned} best wall_ms={best*1e3:.3f} steps/s={w.total_steps/best:.3e} kernel-region ms={ctx.stat(0):.3f} launches={int(ctx.stat(1))}", flush=True)
+
+if __name__ == "__main__":
+    for pin in (False, True):
+        e2e("C2", pinned=pin)
+        e2e("C5", pinned=pin)
+        e2e("C2", pinned=pin, pts=1000000 - 1)   # even point count: strided 2-D copy path
