@@ -245,7 +245,12 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     }
 
     if (dim <= 16) { c->family = 1; c->npad = dim <= 8 ? 8 : 16; }
-    else if (dim <= 64) { c->family = 2; c->npad = k4_pad((int)dim); c->k4_slots = k4_chain_slots(c->npad, c->num_sms); }
+    else if (dim <= 64) {
+        c->family = 2; c->npad = k4_pad((int)dim);
+        const int oc = (c->npad == 64 && !getenv("PARAMENT_NO_ONCHIP")) ? k4_onchip_slots(c->num_sms) : 0;
+        c->onchip = oc > 0;
+        c->k4_slots = c->onchip ? oc : k4_chain_slots(c->npad, c->num_sms);
+    }
     else                { c->family = 3; c->npad = k4_pad((int)dim); c->k4_slots = k4_wave_slots(c->npad, c->num_sms); }
     if (!upload_matrices(c)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
     c->have_hamiltonian = true;
@@ -481,7 +486,10 @@ Parament_ErrorCode run_family2(Context *c, const SeriesParams &p, const void *ca
     double2 *pend = (double2 *)c->d_pending.ptr, *tree = (double2 *)c->d_tree.ptr;
     for (unsigned int b = 0; b < s.batch; ++b) {
         const char *cb = (const char *)carr_dev + (size_t)b * s.amps * s.stride * io;
-        PB_LAUNCH(k4_chain(c->fp64, p, prog, cb, (const double2 *)c->d_H.ptr, (double2 *)c->d_Y.ptr, pend, s.nsteps, grid, st));
+        if (c->onchip)
+            PB_LAUNCH(k4_onchip(c->fp64, p, prog, cb, (const double2 *)c->d_H.ptr, (double2 *)c->d_Y.ptr, pend, s.nsteps, grid, st));
+        else
+            PB_LAUNCH(k4_chain(c->fp64, p, prog, cb, (const double2 *)c->d_H.ptr, (double2 *)c->d_Y.ptr, pend, s.nsteps, grid, st));
         Parament_ErrorCode ec = tree_reduce_all(c, pend, grid, tree, np, st);
         if (ec != PARAMENT_STATUS_SUCCESS) return ec;
         PB_LAUNCH(k4_finish(c->fp64, pend, c->dim, np, (char *)out_dev + (size_t)b * c->dim * c->dim * io, true, st));

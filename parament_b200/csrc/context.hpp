@@ -43,6 +43,7 @@ struct Context {
     std::vector<zc> mats;   // nmats * dim * dim, row-major
     int family = 0;      // 1 = register-resident warp kernels, 2 = persistent CTA chain kernel, 3 = batched GEMM pipeline
     int npad = 0;
+    bool onchip = false; // family 2: operands resident in shared memory (npad == 64)
     int k4_slots = 0;    // co-resident CTAs of the GEMM kernel (family 3)
     DeviceBuffer d_H;    // family 1: fragment-ordered table; family 3: padded row-major table
 
