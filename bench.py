@@ -279,7 +279,7 @@ def run_ours(args):
             # `achieved` = algorithmic flops of the reference's recurrence / time.  When the Horner-in-Y^2
             # evaluation executes fewer products than that recurrence, `frac` is computed from the EXECUTED flops so that
             # it stays a pipe utilisation (<= 1); the algorithmic figure is kept in `algorithmic_frac`.
-            "roofline": {"bound": "fp64_tensor", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "pipe": "FP64 tensor pipe (DMMA.8x8x4)", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s",
                          "frac": min(achieved, F_exe * per_gpu_rate * 1e-12) / peak_dmma if peak_dmma > 0 else None,
                          "algorithmic_frac": achieved / peak_dmma if peak_dmma > 0 else None, "traffic": traffic,
                          "peak_source": "Parament_measurePeak(DMMA mma.sync.m8n8k4.f64) in this process; MEASURED_PEAKS.json has no FP64 figure",

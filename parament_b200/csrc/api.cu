@@ -561,7 +561,8 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
     K1Plan plan{};
     if (c->family == 1) {
         plan = plan_k1(c->npad, s.batch, s.nsteps, c->num_sms, p.horner != 0);
-        if (!ensure_dev(c->d_partials, plan.partial_elems * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+        if (!ensure_dev(c->d_partials, (plan.partial_elems + k3_mid_elems(c->npad, s.batch, plan.partials_per_pulse)) * sizeof(double2)))
+            return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
     } else if (c->family == 2) {
         if (!alloc_family2(c, chain_grid(c, s))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
     } else if (!alloc_family3(c, plan_family3(c, s))) {
@@ -572,7 +573,8 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
         PB_LAUNCH(launch_k1_chain(c->npad, c->fp64, p, carr_dev, (const double2 *)c->d_H.ptr, (double2 *)c->d_partials.ptr,
                                   s.batch, plan, 0, s.nsteps, st));
         PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, plan.partials_per_pulse, c->dim,
-                                   out_dev, s.batch, plan.k3_warps, st));
+                                   out_dev, s.batch, (double2 *)c->d_partials.ptr + plan.partial_elems, st));
+        c->stat_launches += k3_launches(plan.partials_per_pulse) - 1;
     } else {
         ec = c->family == 2 ? run_family2(c, p, carr_dev, s, out_dev, st) : run_family3(c, p, carr_dev, s, out_dev, st);
         if (ec != PARAMENT_STATUS_SUCCESS) return ec;
@@ -608,7 +610,8 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
     if (s.batch > 1) {
         const unsigned int bg = (s.batch + G - 1) / G;
         const K1Plan big = plan_k1(c->npad, bg, s.nsteps, c->num_sms, horner);
-        if (!ensure_dev(c->d_partials, big.partial_elems * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+        if (!ensure_dev(c->d_partials, (big.partial_elems + k3_mid_elems(c->npad, bg, big.partials_per_pulse)) * sizeof(double2)))
+            return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
         if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, c->stream))) return PARAMENT_STATUS_CUBLAS_FAILED;
         int g = 0;
         for (unsigned int b0 = 0; b0 < s.batch; b0 += bg, ++g) {
@@ -620,7 +623,8 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
             PB_LAUNCH(launch_k1_chain(c->npad, c->fp64, p, dcarr + (size_t)b0 * s.amps * seg, (const double2 *)c->d_H.ptr,
                                       (double2 *)c->d_partials.ptr, b1 - b0, plan, 0, s.nsteps, c->stream));
             PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, plan.partials_per_pulse, n,
-                                       (T *)out_dev + (size_t)b0 * n * n, b1 - b0, plan.k3_warps, c->stream));
+                                       (T *)out_dev + (size_t)b0 * n * n, b1 - b0, (double2 *)c->d_partials.ptr + big.partial_elems, c->stream));
+            c->stat_launches += k3_launches(plan.partials_per_pulse) - 1;
         }
     } else {
         const int r = points_per_step(c), ov = point_overlap(c);
@@ -633,7 +637,8 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
             plans[g] = plan_k1(c->npad, 1, bound[g + 1] - bound[g], c->num_sms, horner);
             off[g + 1] = off[g] + plans[g].partials_per_pulse;
         }
-        if (!ensure_dev(c->d_partials, off[G] * NP2 * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+        if (!ensure_dev(c->d_partials, (off[G] * NP2 + k3_mid_elems(c->npad, 1, (unsigned int)off[G])) * sizeof(double2)))
+            return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
         if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, c->stream))) return PARAMENT_STATUS_CUBLAS_FAILED;
         for (int g = 0; g < G; ++g) {
             const size_t pt0 = (size_t)r * bound[g] + (g == 0 ? 0 : ov);            // the overlap point came with the previous group
@@ -645,7 +650,8 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
                                       1, plans[g], bound[g], bound[g + 1], c->stream));
         }
         PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, (unsigned int)off[G], n, out_dev, 1,
-                                   k3_warps_for((unsigned int)off[G]), c->stream));
+                                   (double2 *)c->d_partials.ptr + off[G] * NP2, c->stream));
+        c->stat_launches += k3_launches((unsigned int)off[G]) - 1;
     }
     if (!PB_CUDA_OK(cudaEventRecord(c->ev_stop, c->stream))) return PARAMENT_STATUS_CUBLAS_FAILED;
     return PARAMENT_STATUS_SUCCESS;

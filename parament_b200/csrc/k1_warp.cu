@@ -185,51 +185,65 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
     }
 }
 
-// One CTA per pulse: ordered product of its nb partials, then out[r][c] = Q[c][r] in the IO precision.
+// Ordered reduction of the partial products of each pulse.  grid = (pulses, groups): CTA (pulse, g) multiplies the
+// contiguous group g of that pulse's nb partials (each warp a contiguous sub-range, the next partial prefetched while the
+// current product runs, then the in-CTA tree).  With mid != nullptr the group product is written back as a partial
+// (first level of a two-level reduction), otherwise it is transposed to the row-major physical propagator, converted to
+// the IO precision and written to out[pulse].
 template <int NT, typename IO>
 __global__ void __launch_bounds__(256)
-k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, int n, IO *__restrict__ out) {
+k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, unsigned int group, int n, double2 *__restrict__ mid,
+                 IO *__restrict__ out) {
     constexpr int NP = 8 * NT;
     __shared__ double2 smem[4 * NP * NP];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const unsigned int pulse = blockIdx.x;
-    const double2 *P = partials + (size_t)pulse * nb * NP * NP;
+    const unsigned int pulse = blockIdx.x, g = blockIdx.y;
+    const unsigned int g0 = g * group, g1 = min(nb, g0 + group);
+    const double2 *P = partials + ((size_t)pulse * nb + g0) * NP * NP;
+    const unsigned int cnt = g1 - g0;
 
-    const unsigned int b0 = (unsigned int)((unsigned long long)nb * warp / nwarps);
-    const unsigned int b1 = (unsigned int)((unsigned long long)nb * (warp + 1) / nwarps);
+    const unsigned int b0 = (unsigned int)((unsigned long long)cnt * warp / nwarps);
+    const unsigned int b1 = (unsigned int)((unsigned long long)cnt * (warp + 1) / nwarps);
     AccFrag<NT> Q;
     if (b0 < b1) {
         load_acc<NT>(Q, P + (size_t)b0 * NP * NP, NP, lane);
+        BFrag<NT> B;
+        if (b0 + 1 < b1) load_bfrag<NT>(B, P + (size_t)(b0 + 1) * NP * NP, NP, lane);
         for (unsigned int b = b0 + 1; b < b1; ++b) {
-            BFrag<NT> B;
-            load_bfrag<NT>(B, P + (size_t)b * NP * NP, NP, lane);
+            BFrag<NT> Bn;
+            if (b + 1 < b1) load_bfrag<NT>(Bn, P + (size_t)(b + 1) * NP * NP, NP, lane);   // prefetch
             AccFrag<NT> R;
             set_zero<NT>(R);
             cmma<NT>(R, Q, B);
             Q = R;
+            if (b + 1 < b1) B = Bn;
         }
     } else {
         set_identity<NT>(Q, lane);
     }
     cta_ordered_product<NT>(Q, smem, warp, nwarps, lane);
     if (warp == 0) {
-        IO *o = out + (size_t)pulse * n * n;
+        if (mid) {
+            store_acc<NT>(Q, mid + ((size_t)pulse * gridDim.y + g) * NP * NP, NP, lane);
+        } else {
+            IO *o = out + (size_t)pulse * n * n;
 #pragma unroll
-        for (int mt = 0; mt < NT; ++mt)
+            for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
+                for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = acc_row(lane, mt), cidx = acc_col(lane, nt, i);
-                    if (r < n && cidx < n) {
-                        IO v;
-                        v.x = Q.re[mt][nt][i];
-                        v.y = Q.im[mt][nt][i];
-                        o[(size_t)cidx * n + r] = v;   // transpose back: P = Q^T
+                    for (int i = 0; i < 2; ++i) {
+                        const int r = acc_row(lane, mt), cidx = acc_col(lane, nt, i);
+                        if (r < n && cidx < n) {
+                            IO v;
+                            v.x = Q.re[mt][nt][i];
+                            v.y = Q.im[mt][nt][i];
+                            o[(size_t)cidx * n + r] = v;   // transpose back: P = Q^T
+                        }
                     }
-                }
+        }
     }
 }
 
@@ -292,18 +306,38 @@ cudaError_t launch_k1_chain(int npad, bool fp64_io, const SeriesParams &p, const
                    : launch_chain_t<2, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
 }
 
-cudaError_t launch_k3_reduce(int npad, bool fp64_io, const double2 *partials, unsigned int partials_per_pulse, int n,
-                             void *out, unsigned int batch, int k3_warps, cudaStream_t stream) {
-    if (npad == 8) {
-        if (fp64_io) k3_reduce_kernel<1, double2><<<batch, 32 * k3_warps, 0, stream>>>(partials, partials_per_pulse, n, (double2 *)out);
-        else         k3_reduce_kernel<1, float2><<<batch, 32 * k3_warps, 0, stream>>>(partials, partials_per_pulse, n, (float2 *)out);
-    } else {
-        if (fp64_io) k3_reduce_kernel<2, double2><<<batch, 32 * k3_warps, 0, stream>>>(partials, partials_per_pulse, n, (double2 *)out);
-        else         k3_reduce_kernel<2, float2><<<batch, 32 * k3_warps, 0, stream>>>(partials, partials_per_pulse, n, (float2 *)out);
+template <int NT, typename IO>
+static cudaError_t launch_k3_t(const double2 *partials, unsigned int nb, int n, double2 *mid, IO *out, unsigned int batch,
+                               cudaStream_t stream) {
+    constexpr unsigned int GROUP = 16;
+    if (nb > 32 && mid) {   // two levels: groups of 16 in parallel CTAs, then the group products
+        const unsigned int ng = (nb + GROUP - 1) / GROUP;
+        k3_reduce_kernel<NT, IO><<<dim3(batch, ng), 256, 0, stream>>>(partials, nb, GROUP, n, mid, out);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        k3_reduce_kernel<NT, IO><<<dim3(batch, 1), 32 * k3_warps_for(ng), 0, stream>>>(mid, ng, ng, n, nullptr, out);
+        return cudaGetLastError();
     }
+    k3_reduce_kernel<NT, IO><<<dim3(batch, 1), 32 * k3_warps_for(nb), 0, stream>>>(partials, nb, nb, n, nullptr, out);
     return cudaGetLastError();
 }
 
-int k3_warps_for(unsigned int partials_per_pulse) { return partials_per_pulse >= 64 ? 8 : (partials_per_pulse >= 8 ? 4 : 1); }
+// `mid`: scratch for k3_mid_elems(...) double2 (first-level group products); may be null for nb <= 32.
+cudaError_t launch_k3_reduce(int npad, bool fp64_io, const double2 *partials, unsigned int partials_per_pulse, int n,
+                             void *out, unsigned int batch, double2 *mid, cudaStream_t stream) {
+    if (npad == 8)
+        return fp64_io ? launch_k3_t<1, double2>(partials, partials_per_pulse, n, mid, (double2 *)out, batch, stream)
+                       : launch_k3_t<1, float2>(partials, partials_per_pulse, n, mid, (float2 *)out, batch, stream);
+    return fp64_io ? launch_k3_t<2, double2>(partials, partials_per_pulse, n, mid, (double2 *)out, batch, stream)
+                   : launch_k3_t<2, float2>(partials, partials_per_pulse, n, mid, (float2 *)out, batch, stream);
+}
+
+size_t k3_mid_elems(int npad, unsigned int batch, unsigned int partials_per_pulse) {
+    return partials_per_pulse > 32 ? (size_t)batch * ((partials_per_pulse + 15) / 16) * npad * npad : 0;
+}
+
+int k3_launches(unsigned int partials_per_pulse) { return partials_per_pulse > 32 ? 2 : 1; }
+
+int k3_warps_for(unsigned int partials_per_pulse) { return partials_per_pulse >= 16 ? 8 : (partials_per_pulse >= 4 ? 4 : 1); }
 
 }  // namespace pb

@@ -24,7 +24,9 @@ cudaError_t launch_k1_chain(int npad, bool fp64_io, const SeriesParams &p, const
                             double2 *partials, unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
                             unsigned long long step_hi, cudaStream_t stream);
 cudaError_t launch_k3_reduce(int npad, bool fp64_io, const double2 *partials, unsigned int partials_per_pulse, int n,
-                             void *out, unsigned int batch, int k3_warps, cudaStream_t stream);
+                             void *out, unsigned int batch, double2 *mid, cudaStream_t stream);
+size_t k3_mid_elems(int npad, unsigned int batch, unsigned int partials_per_pulse);   // scratch of the two-level reduction
+int k3_launches(unsigned int partials_per_pulse);
 int k3_warps_for(unsigned int partials_per_pulse);
 
 }  // namespace pb

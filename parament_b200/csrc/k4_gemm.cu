@@ -358,6 +358,7 @@ static cudaError_t launch_gemm_t(const GemmArgs &g, cudaStream_t stream) {
     auto kern = k4_zgemm_kernel<BM, BN, WM, WN>;
     cudaError_t e = opt_in_smem(kern, SM::BYTES);   // per-device function attribute; cheap, so set on every launch
     if (e != cudaSuccess) return e;
+    // (programmatic dependent launch was measured here: 2.78e4 -> 2.50e4 steps/s at dim 256, so plain stream order is kept)
     dim3 grid((g.n / BM) * (g.n / BN), g.batch);
     kern<<<grid, (BM / WM) * (BN / WN) * 32, SM::BYTES, stream>>>(g);
     return cudaGetLastError();
