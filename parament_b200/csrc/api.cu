@@ -110,7 +110,7 @@ Parament_ErrorCode destroy_ctx(Context *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
-    free_dev(c->d_Y); free_dev(c->d_W); free_dev(c->d_S0); free_dev(c->d_S1); free_dev(c->d_pending); free_dev(c->d_tree);
+    free_dev(c->d_Y); free_dev(c->d_pending); free_dev(c->d_tree);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_out) cudaFreeHost(c->h_out);
     cudaEventDestroy(c->ev_start);
@@ -376,6 +376,9 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
             p.a_lo[m] = cplx{(double)(cr - (long double)p.a[m].re), (double)(ci - (long double)p.a[m].im)};
         }
         p.sigma = 1.0;
+        // Paterson-Stockmeyer blocks of four (3 + floor(M/4) products instead of 1 + floor(M/2)) where the kernels keep their
+        // operands in global memory; the register- and shared-memory-resident kernels evaluate the Y^2 form.
+        if (M_used >= 10 && (c->family == 3 || (c->family == 2 && !c->onchip))) p.horner = 2;
     }
     c->stat_horner = p.horner;
     const int A = c->amps, Ain = (int)s.amps;
@@ -405,11 +408,9 @@ Parament_ErrorCode tree_level(Context *c, const double2 *src, int count, double2
     GemmArgs g{};
     g.A = src + nn; g.strideA = 2 * nn;
     g.B = src; g.strideB = 2 * nn;
-    g.C1 = src; g.strideC1 = 2 * nn; g.beta1 = cplx{1.0, 0.0}; g.beta1_lo = cplx{0.0, 0.0};
+    g.C[0] = src; g.strideC[0] = 2 * nn; g.beta[0] = cplx{1.0, 0.0};
     g.C2 = src + nn; g.strideC2 = 2 * nn; g.beta2 = 1.0;
     g.D = dst; g.strideD = nn;
-    g.gamma = cplx{0.0, 0.0};
-    g.gamma_lo = cplx{0.0, 0.0};
     g.n = npad; g.batch = pairs;
     if (pairs > 0) PB_LAUNCH(k4_gemm(g, st));
     if (count & 1) {
@@ -440,15 +441,15 @@ Parament_ErrorCode tree_reduce_all(Context *c, double2 *buf, int count, double2 
 struct F3Plan { int S; int cap; };
 
 // Chunk length S: a whole number of GEMM waves (S * tiles == k * co-resident CTAs: a launch that spills a few CTAs
-// into an extra wave costs a full wave) with the four S x npad^2 work arrays (Y, W, two recurrence registers)
-// L2-resident (<= ~80 MB).  `cap` bounds the buffer of pending partial products.
+// into an extra wave costs a full wave) with the six S x npad^2 work arrays (Y, Y^2, Y^3, Y^4, two recurrence
+// registers; <= ~110 MB, mostly L2-resident).  `cap` bounds the buffer of pending partial products.
 F3Plan plan_family3(const Context *c, const CallSpec &s) {
     const size_t nn = (size_t)c->npad * c->npad;
     const int tiles = k4_tiles(c->npad);
     const int slots = c->k4_slots > 0 ? c->k4_slots : 2 * c->num_sms;
     F3Plan f;
     const long long per_wave = std::max<long long>(1, slots / tiles);
-    const long long budget = std::max<long long>(1, (long long)(80e6 / (4.0 * nn * sizeof(double2))));
+    const long long budget = std::max<long long>(1, (long long)(110e6 / ((double)kSeriesSlots * nn * sizeof(double2))));
     long long waves = std::max<long long>(1, budget / per_wave);
     if (waves > 4) waves = 4;
     f.S = (int)std::max<long long>(2, std::min<long long>(per_wave * waves, std::max<long long>(budget, per_wave)));
@@ -464,15 +465,14 @@ int chain_grid(const Context *c, const CallSpec &s) {
 
 bool alloc_family3(Context *c, const F3Plan &f) {
     const size_t nn = (size_t)c->npad * c->npad;
-    return ensure_dev(c->d_Y, (size_t)f.S * nn * sizeof(double2)) && ensure_dev(c->d_W, (size_t)f.S * nn * sizeof(double2)) &&
-           ensure_dev(c->d_S0, (size_t)f.S * nn * sizeof(double2)) && ensure_dev(c->d_S1, (size_t)f.S * nn * sizeof(double2)) &&
+    return ensure_dev(c->d_Y, (size_t)kSeriesSlots * f.S * nn * sizeof(double2)) &&
            ensure_dev(c->d_pending, (size_t)(f.cap + f.S) * nn * sizeof(double2)) &&
            ensure_dev(c->d_tree, (size_t)((f.cap + f.S) / 2 + 1) * nn * sizeof(double2));
 }
 
 bool alloc_family2(Context *c, int grid) {
     const size_t nn = (size_t)c->npad * c->npad;
-    return ensure_dev(c->d_Y, (size_t)grid * 6 * nn * sizeof(double2)) &&          // per-CTA scratch: 6 matrices
+    return ensure_dev(c->d_Y, (size_t)grid * (kSeriesSlots + 2) * nn * sizeof(double2)) &&   // per-CTA scratch
            ensure_dev(c->d_pending, (size_t)grid * nn * sizeof(double2)) &&
            ensure_dev(c->d_tree, (size_t)(grid / 2 + 1) * nn * sizeof(double2));
 }
@@ -506,26 +506,32 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
     const F3Plan f = plan_family3(c, s);
     const int S = f.S, cap = f.cap;
     const SeriesProgram prog = build_program(p);
-    double2 *slots[4] = {(double2 *)c->d_Y.ptr, (double2 *)c->d_W.ptr, (double2 *)c->d_S0.ptr, (double2 *)c->d_S1.ptr};
+    double2 *slots[kSeriesSlots];
+    for (int i = 0; i < kSeriesSlots; ++i) slots[i] = (double2 *)c->d_Y.ptr + (size_t)i * S * nn;
     double2 *pend = (double2 *)c->d_pending.ptr, *tree = (double2 *)c->d_tree.ptr;
     for (unsigned int b = 0; b < s.batch; ++b) {
         const char *cb = (const char *)carr_dev + (size_t)b * s.amps * s.stride * io;
         int pending = 0;
         for (unsigned long long step0 = 0; step0 < s.nsteps; step0 += S) {
             const int Sc = (int)std::min<unsigned long long>(S, s.nsteps - step0);
-            PB_LAUNCH(k4_assemble(c->fp64, p, prog, cb, (const double2 *)c->d_H.ptr, slots[0], slots[2], slots[3], step0, Sc, st));
+            PB_LAUNCH(k4_assemble(c->fp64, p, prog, cb, (const double2 *)c->d_H.ptr, slots[0], slots[4], slots[5], step0, Sc, st));
             for (int o = 0; o < prog.nops; ++o) {
                 const SeriesOp &op = prog.ops[o];
                 GemmArgs g{};
-                g.A = slots[op.A]; g.B = slots[op.B]; g.C1 = op.C1 >= 0 ? slots[op.C1] : nullptr; g.D = slots[op.D];
-                g.strideA = g.strideB = g.strideC1 = g.strideD = (long long)nn;
-                g.beta1 = op.beta1; g.beta1_lo = op.beta1_lo; g.gamma = op.gamma; g.gamma_lo = op.gamma_lo;
+                g.A = slots[op.A]; g.B = slots[op.B]; g.D = slots[op.D];
+                g.Dprod = op.Dprod >= 0 ? slots[op.Dprod] : nullptr;
+                g.strideA = g.strideB = g.strideD = g.strideDprod = (long long)nn;
+                for (int j = 0; j < kMaxAddends; ++j) {
+                    g.C[j] = op.C[j] >= 0 ? slots[op.C[j]] : nullptr; g.strideC[j] = (long long)nn;
+                    g.beta[j] = op.beta[j]; g.beta_lo[j] = op.beta_lo[j];
+                }
+                g.alpha = op.alpha; g.scaled = op.scaled; g.gamma = op.gamma; g.gamma_lo = op.gamma_lo;
                 g.C2 = nullptr; g.beta2 = 0.0; g.n = np; g.batch = Sc;
                 PB_LAUNCH(k4_gemm(g, st));
             }
             // ordered product inside the chunk while the launches still fill the machine
             double2 *src = slots[prog.e_slot];
-            double2 *other = slots[prog.e_slot == 2 ? 3 : 2];
+            double2 *other = slots[prog.e_slot == 4 ? 5 : 4];
             int count = Sc;
             while (count > 1 && (count / 2) * tiles >= 48) {
                 int nc = 0;
@@ -955,6 +961,7 @@ double Parament_lastStat(void *h, int key) {
         case 10: {   // complex matrix products executed per effective step (series + ordered product)
             const int M = c->stat_M_used;
             if (M <= 0) return 0.0;
+            if (c->stat_horner == 2) return 4.0 + (M >> 2);
             return c->stat_horner ? 2.0 + (M >> 1) : (double)std::max(M, 1);
         }
         default: return -1.0;
@@ -971,7 +978,7 @@ Parament_ErrorCode Parament_setDevice(void *h, int device) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
-    free_dev(c->d_Y); free_dev(c->d_W); free_dev(c->d_S0); free_dev(c->d_S1); free_dev(c->d_pending); free_dev(c->d_tree);
+    free_dev(c->d_Y); free_dev(c->d_pending); free_dev(c->d_tree);
     cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); destroy_copy_events(c);
     cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->stream);
     c->device = device;

@@ -39,13 +39,51 @@ struct K4Smem {
 };
 
 struct TileArgs {
-    const double2 *A, *B, *C1, *C2;   // matrix bases (n x n row-major)
-    double2 *D;
-    cplx beta1, beta1_lo;
+    const double2 *A, *B;             // matrix bases (n x n row-major)
+    const double2 *C[kMaxAddends];
+    const double2 *C2;
+    double2 *D, *Dprod;
+    cplx alpha; int scaled;
+    cplx beta[kMaxAddends], beta_lo[kMaxAddends];
     double beta2;
     cplx gamma, gamma_lo;
     int n;
 };
+
+// Shared epilogue arithmetic for two horizontally adjacent elements (row r, columns c and c+1): on entry (vr, vi) hold the
+// product, z[j][i] the addends; small terms are added first, the dominant ones last with a single-rounding FMA.
+__device__ __forceinline__ void epilogue_pair(double (&vr)[2], double (&vi)[2], const double2 (&z)[kMaxAddends][2], const bool (&has)[kMaxAddends],
+                                              int scaled, cplx alpha, const cplx (&beta)[kMaxAddends], const cplx (&beta_lo)[kMaxAddends],
+                                              cplx gamma, cplx gamma_lo, bool diag0, bool diag1) {
+    if (scaled) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double pr = vr[i], pi = vi[i];
+            vr[i] = alpha.re * pr - alpha.im * pi;
+            vi[i] = alpha.re * pi + alpha.im * pr;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxAddends; ++j)
+        if (has[j]) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                vr[i] += beta_lo[j].re * z[j][i].x - beta_lo[j].im * z[j][i].y;
+                vi[i] += beta_lo[j].re * z[j][i].y + beta_lo[j].im * z[j][i].x;
+            }
+        }
+    if (diag0) { vr[0] = (vr[0] + gamma_lo.re) + gamma.re; vi[0] = (vi[0] + gamma_lo.im) + gamma.im; }
+    if (diag1) { vr[1] = (vr[1] + gamma_lo.re) + gamma.re; vi[1] = (vi[1] + gamma_lo.im) + gamma.im; }
+#pragma unroll
+    for (int j = kMaxAddends - 1; j >= 0; --j)     // addend 0 carries the dominant (lowest-order) term: last
+        if (has[j]) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                vr[i] = fma(beta[j].re, z[j][i].x, fma(-beta[j].im, z[j][i].y, vr[i]));
+                vi[i] = fma(beta[j].re, z[j][i].y, fma(beta[j].im, z[j][i].x, vi[i]));
+            }
+        }
+}
 
 // All threads of the CTA call this; returns with every thread's part of D written (no trailing barrier).
 template <int BM, int BN, int WM, int WN>
@@ -119,8 +157,11 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
     cp_async_wait<0>();
     __syncthreads();   // every warp is done with the stage buffers: the next tile_gemm may refill them
 
-    // ---- epilogue: D = acc + beta2 C2 + beta1_lo C1 + gamma_lo I  + gamma I  + beta1 C1   (small terms first) ----
+    // ---- epilogue ----
     const size_t row0 = (size_t)tile_m * BM + wm0, col0 = (size_t)tile_n * BN + wn0;
+    bool has[kMaxAddends];
+#pragma unroll
+    for (int j = 0; j < kMaxAddends; ++j) has[j] = g.C[j] != nullptr;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -128,29 +169,20 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
             const size_t r = row0 + 8 * mt + gq, c = col0 + 8 * nt + 2 * q;
             const size_t off = r * g.n + c;
             double vr[2] = {cre[mt][nt][0], cre[mt][nt][1]}, vi[2] = {cim[mt][nt][0], cim[mt][nt][1]};
-            if (g.C2) {
-                const double2 x0 = g.C2[off], x1 = g.C2[off + 1];
-                vr[0] += g.beta2 * x0.x; vi[0] += g.beta2 * x0.y; vr[1] += g.beta2 * x1.x; vi[1] += g.beta2 * x1.y;
+            if (g.Dprod) {
+                g.Dprod[off] = make_double2(vr[0], vi[0]);
+                g.Dprod[off + 1] = make_double2(vr[1], vi[1]);
             }
-            double2 y[2] = {make_double2(0, 0), make_double2(0, 0)};
-            if (g.C1) {
-                y[0] = g.C1[off]; y[1] = g.C1[off + 1];
+            double2 z[kMaxAddends][2];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    vr[i] += g.beta1_lo.re * y[i].x - g.beta1_lo.im * y[i].y;
-                    vi[i] += g.beta1_lo.re * y[i].y + g.beta1_lo.im * y[i].x;
-                }
+            for (int j = 0; j < kMaxAddends; ++j) {
+                z[j][0] = z[j][1] = make_double2(0.0, 0.0);
+                if (has[j]) { z[j][0] = g.C[j][off]; z[j][1] = g.C[j][off + 1]; }
             }
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-                if (r == c + i) { vr[i] = (vr[i] + g.gamma_lo.re) + g.gamma.re; vi[i] = (vi[i] + g.gamma_lo.im) + g.gamma.im; }
-            if (g.C1) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    vr[i] = fma(g.beta1.re, y[i].x, fma(-g.beta1.im, y[i].y, vr[i]));
-                    vi[i] = fma(g.beta1.re, y[i].y, fma(g.beta1.im, y[i].x, vi[i]));
-                }
-            }
+            double2 x0 = make_double2(0.0, 0.0), x1 = x0;
+            if (g.C2) { x0 = g.C2[off]; x1 = g.C2[off + 1]; }
+            epilogue_pair(vr, vi, z, has, g.scaled, g.alpha, g.beta, g.beta_lo, g.gamma, g.gamma_lo, r == c, r == c + 1);
+            if (g.C2) { vr[0] += g.beta2 * x0.x; vi[0] += g.beta2 * x0.y; vr[1] += g.beta2 * x1.x; vi[1] += g.beta2 * x1.y; }
             g.D[off] = make_double2(vr[0], vi[0]);
             g.D[off + 1] = make_double2(vr[1], vi[1]);
         }
@@ -166,16 +198,22 @@ k4_zgemm_kernel(const GemmArgs g) {
     TileArgs t;
     t.A = g.A + b * g.strideA;
     t.B = g.B + b * g.strideB;
-    t.C1 = g.C1 ? g.C1 + b * g.strideC1 : nullptr;
+#pragma unroll
+    for (int j = 0; j < kMaxAddends; ++j) {
+        t.C[j] = g.C[j] ? g.C[j] + b * g.strideC[j] : nullptr;
+        t.beta[j] = g.beta[j]; t.beta_lo[j] = g.beta_lo[j];
+    }
     t.C2 = g.C2 ? g.C2 + b * g.strideC2 : nullptr;
     t.D = g.D + b * g.strideD;
-    t.beta1 = g.beta1; t.beta1_lo = g.beta1_lo; t.beta2 = g.beta2; t.gamma = g.gamma; t.gamma_lo = g.gamma_lo;
+    t.Dprod = g.Dprod ? g.Dprod + b * g.strideDprod : nullptr;
+    t.alpha = g.alpha; t.scaled = g.scaled;
+    t.beta2 = g.beta2; t.gamma = g.gamma; t.gamma_lo = g.gamma_lo;
     t.n = g.n;
     tile_gemm<BM, BN, WM, WN>(smem, t, blockIdx.x / tiles_n, blockIdx.x % tiles_n);
 }
 
 // ------------------------------------------------------------------------------------------------
-// persistent chain kernel (npad == BM): scratch slots per CTA: 0 Y, 1 W, 2, 3 recurrence, 4, 5 running product
+// persistent chain kernel (npad == BM): scratch per CTA: the kSeriesSlots series slots, then 2 slots of the running product
 // ------------------------------------------------------------------------------------------------
 template <int BM, int WM, int WN, typename IO>
 __global__ void __launch_bounds__((BM / WM) * (BM / WN) * 32)
@@ -188,9 +226,9 @@ k4_chain_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__rest
     __shared__ cplx coef[kMaxTerms];
 
     const int tid = threadIdx.x;
-    double2 *slot = scratch + (size_t)blockIdx.x * 6 * NN;
+    double2 *slot = scratch + (size_t)blockIdx.x * (kSeriesSlots + 2) * NN;
     const unsigned long long lo = nsteps * blockIdx.x / gridDim.x, hi = nsteps * (blockIdx.x + 1) / gridDim.x;
-    int f_cur = 4;
+    int f_cur = kSeriesSlots;
     bool have_f = false;
 
     for (unsigned long long j = lo; j < hi; ++j) {
@@ -209,9 +247,9 @@ k4_chain_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__rest
             const double yr = x.x * p.sigma, yi = x.y * p.sigma;
             const bool diag = (e / BM == e % BM);
             slot[e] = make_double2(yr, yi);
-            slot[2 * NN + e] = make_double2(((prog.u.re * yr - prog.u.im * yi) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
+            slot[4 * NN + e] = make_double2(((prog.u.re * yr - prog.u.im * yi) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
                                             ((prog.u.re * yi + prog.u.im * yr) + (diag ? prog.v_lo.im : 0.0)) + (diag ? prog.v.im : 0.0));
-            if (prog.init3) slot[3 * NN + e] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
+            if (prog.init5) slot[5 * NN + e] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
         }
         __syncthreads();
         // ---- series program ----
@@ -220,10 +258,16 @@ k4_chain_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__rest
             TileArgs t;
             t.A = slot + (size_t)op.A * NN;
             t.B = slot + (size_t)op.B * NN;
-            t.C1 = op.C1 >= 0 ? slot + (size_t)op.C1 * NN : nullptr;
+#pragma unroll
+            for (int a = 0; a < kMaxAddends; ++a) {
+                t.C[a] = op.C[a] >= 0 ? slot + (size_t)op.C[a] * NN : nullptr;
+                t.beta[a] = op.beta[a]; t.beta_lo[a] = op.beta_lo[a];
+            }
             t.C2 = nullptr;
             t.D = slot + (size_t)op.D * NN;
-            t.beta1 = op.beta1; t.beta1_lo = op.beta1_lo; t.beta2 = 0.0; t.gamma = op.gamma; t.gamma_lo = op.gamma_lo;
+            t.Dprod = op.Dprod >= 0 ? slot + (size_t)op.Dprod * NN : nullptr;
+            t.alpha = op.alpha; t.scaled = op.scaled;
+            t.beta2 = 0.0; t.gamma = op.gamma; t.gamma_lo = op.gamma_lo;
             t.n = BM;
             tile_gemm<BM, BM, WM, WN>(smem, t, 0, 0);
             __syncthreads();
@@ -234,14 +278,14 @@ k4_chain_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__rest
             for (int e = tid; e < NN; e += NTHREADS) slot[(size_t)f_cur * NN + e] = E[e];
             have_f = true;
         } else {
-            TileArgs t;
-            t.A = E; t.B = slot + (size_t)f_cur * NN; t.C1 = E; t.C2 = slot + (size_t)f_cur * NN;
-            t.D = slot + (size_t)(f_cur ^ 1) * NN;
-            t.beta1 = cplx{1.0, 0.0}; t.beta1_lo = cplx{0.0, 0.0}; t.beta2 = 1.0;
-            t.gamma = cplx{0.0, 0.0}; t.gamma_lo = cplx{0.0, 0.0};
+            const int f_nxt = (f_cur == kSeriesSlots) ? kSeriesSlots + 1 : kSeriesSlots;
+            TileArgs t{};
+            t.A = E; t.B = slot + (size_t)f_cur * NN; t.C[0] = E; t.C2 = slot + (size_t)f_cur * NN;
+            t.D = slot + (size_t)f_nxt * NN;
+            t.beta[0] = cplx{1.0, 0.0}; t.beta2 = 1.0;
             t.n = BM;
             tile_gemm<BM, BM, WM, WN>(smem, t, 0, 0);
-            f_cur ^= 1;
+            f_cur = f_nxt;
         }
         __syncthreads();
     }
@@ -253,7 +297,7 @@ k4_chain_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__rest
 template <typename IO>
 __global__ void __launch_bounds__(256)
 k4_assemble_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__restrict__ carr, const double2 *__restrict__ H,
-                   double2 *__restrict__ Y, double2 *__restrict__ S2, double2 *__restrict__ S3,
+                   double2 *__restrict__ Y, double2 *__restrict__ S4, double2 *__restrict__ S5,
                    unsigned long long step0, int S) {
     __shared__ cplx coef[kMaxTerms][8];
     const int sg0 = blockIdx.y * 8;
@@ -287,9 +331,9 @@ k4_assemble_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__r
             const size_t o = (size_t)(sg0 + s) * nn + e;
             const double yr = xr[s] * p.sigma, yi = xi[s] * p.sigma;
             Y[o] = make_double2(yr, yi);
-            S2[o] = make_double2(((prog.u.re * yr - prog.u.im * yi) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
+            S4[o] = make_double2(((prog.u.re * yr - prog.u.im * yi) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
                                  ((prog.u.re * yi + prog.u.im * yr) + (diag ? prog.v_lo.im : 0.0)) + (diag ? prog.v.im : 0.0));
-            if (prog.init3) S3[o] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
+            if (prog.init5) S5[o] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
         }
     }
 }
@@ -310,39 +354,75 @@ __global__ void k4_finish_kernel(const double2 *__restrict__ E, int n, int npad,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-// The series as a program over slots (k4_gemm.hpp).  Clenshaw: B_k = B_{k+1} Y - B_{k+2} + a_k I, E = B_1 Y - 2 B_2 + a0' I
-// (parament.cpp:569-652 restated in E-form).  Horner: W = Y^2, R <- R W + c_{2i+1} Y + c_{2i} I on the monomial
-// coefficients of the same polynomial (p.horner, coefficients in p.a).
+// The series as a program over slots (k4_gemm.hpp).
+//   p.horner == 0  Clenshaw: B_k = B_{k+1} Y - B_{k+2} + a_k I, E = B_1 Y - 2 B_2 + a0' I   (parament.cpp:569-652, E-form)
+//   p.horner == 1  Horner in W = Y^2 on the monomial coefficients c_m of the same polynomial (p.a = c):
+//                  R <- R W + c_{2i+1} Y + c_{2i} I                                   1 + floor(M/2) products
+//   p.horner == 2  Paterson-Stockmeyer with V = Y^4: Y^2, Y^3, Y^4, then
+//                  R <- R V + c_{4i+3} Y^3 + c_{4i+2} Y^2 + c_{4i+1} Y + c_{4i} I      3 + floor(M/4) products
 SeriesProgram build_program(const SeriesParams &p) {
     SeriesProgram g{};
     const int M = p.M;
-    const cplx zero{0.0, 0.0};
-    auto push = [&](int A, int B, int C1, int D, cplx b1, cplx b1lo, cplx ga, cplx galo) {
+    const cplx zero{0.0, 0.0}, one{1.0, 0.0};
+    auto push = [&](int A, int B, int D) -> SeriesOp & {
         SeriesOp &o = g.ops[g.nops++];
-        o.A = A; o.B = B; o.C1 = C1; o.D = D; o.beta1 = b1; o.beta1_lo = b1lo; o.gamma = ga; o.gamma_lo = galo;
+        o = SeriesOp{};
+        o.A = A; o.B = B; o.D = D; o.Dprod = -1; o.scaled = 0; o.alpha = one;
+        for (int j = 0; j < kMaxAddends; ++j) { o.C[j] = -1; o.beta[j] = zero; o.beta_lo[j] = zero; }
+        o.gamma = zero; o.gamma_lo = zero;
+        return o;
     };
-    if (p.horner) {
-        const int L = M >> 1;
-        g.u = p.a[2 * L + 1]; g.v = p.a[2 * L]; g.v_lo = p.a_lo[2 * L]; g.init3 = 0; g.w = zero;
-        push(0, 0, -1, 1, zero, zero, zero, zero);                       // W = Y Y
-        int cur = 2;
+    auto coef = [&](int m) { return m <= M ? p.a[m] : zero; };
+    auto coef_lo = [&](int m) { return m <= M ? p.a_lo[m] : zero; };
+    if (p.horner == 2) {
+        const int L = M >> 2;                                      // top block index
+        push(0, 0, 1);                                             // Y^2
+        // Y^3 = Y^2 Y, and the top block R_L = c_{4L+3} Y^3 + c_{4L+2} Y^2 + c_{4L+1} Y + c_{4L} I from the same product
+        {
+            SeriesOp &o = push(1, 0, 4);
+            o.Dprod = 2;
+            o.scaled = 1; o.alpha = coef(4 * L + 3);
+            o.C[0] = 0; o.beta[0] = coef(4 * L + 1);
+            o.C[1] = 1; o.beta[1] = coef(4 * L + 2);
+            o.gamma = coef(4 * L);
+        }
+        push(1, 1, 3);                                             // Y^4
+        int cur = 4;
         for (int i = L - 1; i >= 0; --i) {
-            push(cur, 1, 0, cur ^ 1, p.a[2 * i + 1], p.a_lo[2 * i + 1], p.a[2 * i], p.a_lo[2 * i]);
+            SeriesOp &o = push(cur, 3, cur ^ 1);
+            o.C[0] = 0; o.beta[0] = coef(4 * i + 1); o.beta_lo[0] = coef_lo(4 * i + 1);
+            o.C[1] = 1; o.beta[1] = coef(4 * i + 2); o.beta_lo[1] = coef_lo(4 * i + 2);
+            o.C[2] = 2; o.beta[2] = coef(4 * i + 3); o.beta_lo[2] = coef_lo(4 * i + 3);
+            o.gamma = coef(4 * i); o.gamma_lo = coef_lo(4 * i);
+            cur ^= 1;
+        }
+        g.u = zero; g.v = zero; g.v_lo = zero; g.w = zero; g.init5 = 0;   // slot 4 is produced by the second op
+        g.e_slot = cur;
+    } else if (p.horner == 1) {
+        const int L = M >> 1;
+        g.u = coef(2 * L + 1); g.v = coef(2 * L); g.v_lo = coef_lo(2 * L); g.init5 = 0; g.w = zero;
+        push(0, 0, 1);                                             // W = Y Y
+        int cur = 4;
+        for (int i = L - 1; i >= 0; --i) {
+            SeriesOp &o = push(cur, 1, cur ^ 1);
+            o.C[0] = 0; o.beta[0] = p.a[2 * i + 1]; o.beta_lo[0] = p.a_lo[2 * i + 1];
+            o.gamma = p.a[2 * i]; o.gamma_lo = p.a_lo[2 * i];
             cur ^= 1;
         }
         g.e_slot = cur;
     } else if (M == 1) {
-        g.u = p.a[1]; g.v = p.a[0]; g.v_lo = p.a_lo[0]; g.init3 = 0; g.w = zero;
-        g.e_slot = 2;
+        g.u = p.a[1]; g.v = p.a[0]; g.v_lo = p.a_lo[0]; g.init5 = 0; g.w = zero;
+        g.e_slot = 4;
     } else {
-        g.u = p.a[M]; g.v = p.a[M - 1]; g.v_lo = p.a_lo[M - 1]; g.init3 = 1; g.w = p.a[M];
-        int cur = 2;                                                       // slot 2 = B_{M-1}, slot 3 = B_M
-        for (int k = M - 2; k >= 1; --k) {
-            push(cur, 0, cur ^ 1, cur ^ 1, cplx{-1.0, 0.0}, zero, p.a[k], p.a_lo[k]);
+        g.u = p.a[M]; g.v = p.a[M - 1]; g.v_lo = p.a_lo[M - 1]; g.init5 = 1; g.w = p.a[M];
+        int cur = 4;                                               // slot 4 = B_{M-1}, slot 5 = B_M
+        for (int k = M - 2; k >= 0; --k) {
+            SeriesOp &o = push(cur, 0, cur ^ 1);
+            o.C[0] = cur ^ 1; o.beta[0] = cplx{k == 0 ? -2.0 : -1.0, 0.0};
+            o.gamma = p.a[k]; o.gamma_lo = p.a_lo[k];
             cur ^= 1;
         }
-        push(cur, 0, cur ^ 1, cur ^ 1, cplx{-2.0, 0.0}, zero, p.a[0], p.a_lo[0]);
-        g.e_slot = cur ^ 1;
+        g.e_slot = cur;
     }
     return g;
 }
@@ -420,13 +500,13 @@ cudaError_t k4_chain(bool fp64_io, const SeriesParams &p, const SeriesProgram &p
 }
 
 cudaError_t k4_assemble(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,
-                        double2 *slot0, double2 *slot2, double2 *slot3, unsigned long long step0, int S, cudaStream_t stream) {
+                        double2 *slot0, double2 *slot4, double2 *slot5, unsigned long long step0, int S, cudaStream_t stream) {
     const size_t nn = (size_t)p.npad * p.npad;
     dim3 grid((unsigned)((nn + 255) / 256), (unsigned)((S + 7) / 8));
     if (fp64_io)
-        k4_assemble_kernel<double2><<<grid, 256, 0, stream>>>(p, prog, (const double2 *)carr, H, slot0, slot2, slot3, step0, S);
+        k4_assemble_kernel<double2><<<grid, 256, 0, stream>>>(p, prog, (const double2 *)carr, H, slot0, slot4, slot5, step0, S);
     else
-        k4_assemble_kernel<float2><<<grid, 256, 0, stream>>>(p, prog, (const float2 *)carr, H, slot0, slot2, slot3, step0, S);
+        k4_assemble_kernel<float2><<<grid, 256, 0, stream>>>(p, prog, (const float2 *)carr, H, slot0, slot4, slot5, step0, S);
     return cudaGetLastError();
 }
 

@@ -5,33 +5,40 @@
 
 namespace pb {
 
-// D_b = A_b * B_b + (beta1 + beta1_lo) * C1_b + beta2 * C2_b + (gamma + gamma_lo) * I   for b < batch.
-// All matrices n x n row-major interleaved complex double, n a multiple of 32 (n <= 32) or 64.
-// C1 / C2 may be null and may alias D.  The *_lo parts are sub-ulp remainders of the series constants; they are
-// added before the leading parts (DESIGN.md "Numerics").
+// D_b = alpha * (A_b * B_b) + sum_j (beta[j] + beta_lo[j]) * C[j]_b + beta2 * C2_b + (gamma + gamma_lo) * I   for b < batch,
+// and optionally Dprod_b = A_b * B_b.  All matrices n x n row-major interleaved complex double, n a multiple of 32
+// (n <= 32) or 64.  Addends may be null and may alias D.  The *_lo parts are sub-ulp remainders of the series constants;
+// they are added before the leading parts (DESIGN.md "Numerics").
+constexpr int kMaxAddends = 3;
 struct GemmArgs {
     const double2 *A; long long strideA;
     const double2 *B; long long strideB;
-    const double2 *C1; long long strideC1; cplx beta1; cplx beta1_lo;
+    const double2 *C[kMaxAddends]; long long strideC[kMaxAddends]; cplx beta[kMaxAddends]; cplx beta_lo[kMaxAddends];
     const double2 *C2; long long strideC2; double beta2;
     double2 *D; long long strideD;
+    double2 *Dprod; long long strideDprod;
+    cplx alpha; int scaled;          // scaled != 0: the product is multiplied by alpha in D
     cplx gamma; cplx gamma_lo;
     int n;
     int batch;
 };
 
 // The per-step series as a short program of fused GEMMs over matrix slots
-//   0 = Y (scaled step Hamiltonian)   1 = W (Y^2, Horner form only)   2, 3 = recurrence registers
-// `assemble` writes slot 0, slot 2 = u Y + (v + v_lo) I and, if init3, slot 3 = w I.
+//   0 = Y    1 = Y^2 (W)    2 = Y^3    3 = Y^4 (V)    4, 5 = recurrence registers
+// `assemble` writes slot 0, slot 4 = u Y + (v + v_lo) I and, if init5, slot 5 = w I.
+constexpr int kSeriesSlots = 6;
 struct SeriesOp {
-    int A, B, C1, D;             // slots; C1 < 0: no addend
-    cplx beta1, beta1_lo, gamma, gamma_lo;
+    int A, B, D, Dprod;          // slots; Dprod < 0: none
+    int scaled; cplx alpha;
+    int C[kMaxAddends];          // addend slots, < 0: unused
+    cplx beta[kMaxAddends], beta_lo[kMaxAddends];
+    cplx gamma, gamma_lo;
 };
 constexpr int kMaxOps = kMaxDegree + 2;
 struct SeriesProgram {
     int nops;
     int e_slot;                  // slot holding E = U - I after the last op
-    int init3;
+    int init5;
     cplx u, v, v_lo, w;
     SeriesOp ops[kMaxOps];
 };
@@ -46,11 +53,11 @@ int k4_chain_slots(int npad, int num_sms);    // co-resident CTAs of the persist
 
 // Batched path: slots[s] points at S consecutive matrices.
 cudaError_t k4_assemble(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,
-                        double2 *slot0, double2 *slot2, double2 *slot3, unsigned long long step0, int S, cudaStream_t stream);
+                        double2 *slot0, double2 *slot4, double2 *slot5, unsigned long long step0, int S, cudaStream_t stream);
 cudaError_t k4_finish(bool fp64_io, const double2 *E, int n, int npad, void *out, bool add_identity, cudaStream_t stream);
 
 // Persistent single-tile chain kernel (npad == 32 or 64): `grid` CTAs each walk a contiguous range of the nsteps steps
-// with their matrices in a private L2-resident scratch (6 matrices per CTA) and leave one E-form partial each.
+// with their matrices in a private L2-resident scratch (kSeriesSlots + 2 matrices per CTA) and leave one E-form partial each.
 cudaError_t k4_chain(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,
                      double2 *scratch, double2 *partials, unsigned long long nsteps, int grid, cudaStream_t stream);
 

@@ -119,7 +119,7 @@ __device__ __forceinline__ void oc_gemm(const double2 *__restrict__ sA, const do
         }
 }
 
-// scratch per CTA: 3 matrices (Y, F0, F1), row-major pitch 64.
+// scratch per CTA: 3 matrices (Y, F0, F1), row-major pitch 64 (the host allocates kSeriesSlots + 2).
 template <typename IO>
 __global__ void __launch_bounds__(OC_THREADS, 1)
 k4_onchip_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__restrict__ carr, const double2 *__restrict__ H,
