@@ -314,6 +314,33 @@ def test_magnus_many_controls(pb):
         assert rel_frobenius(U, equiprop_oracle(H0, np.array(H1), carr, 0.1, "simpson", True, "fp64")) < 1e-12
 
 
+@pytest.mark.parametrize("n,A,pts,quad,mag", [(33, 2, 40, "none", False), (48, 3, 30, "simpson", True), (63, 1, 25, "midpoint", False),
+                                              (65, 2, 9, "none", False), (100, 2, 7, "simpson", False), (17, 12, 50, "none", False),
+                                              (9, 8, 61, "simpson", True), (130, 1, 5, "midpoint", False)])
+def test_odd_dimensions_and_many_controls(pb, n, A, pts, quad, mag):
+    """Padding of every kernel family (dims just above / below the family boundaries) and large control counts
+    (Magnus with 8 controls = 44 effective terms)."""
+    rng = np.random.default_rng(n * 7 + A)
+    mk = lambda s: s * ((g := rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) + g.conj().T) / (2 * n)
+    H0, H1 = mk(0.5), [mk(0.5 / A) for _ in range(A)]
+    carr = rng.uniform(-1, 1, (A, pts))
+    with pb.Parament("fp64") as ctx:
+        ctx.set_hamiltonian(H0, *H1, use_magnus=mag, quadrature_mode=quad)
+        U = ctx.equiprop(0.08, *carr)
+    assert rel_frobenius(U, equiprop_oracle(H0, np.array(H1), carr, 0.08, quad, mag, "fp64")) < 1e-12
+
+
+def test_too_many_effective_terms_is_an_error(pb):
+    """Magnus with 11 controls needs 77 effective terms; the kernels take at most 64 -> code 50 (invalid value), not garbage."""
+    n, A = 4, 11
+    rng = np.random.default_rng(0)
+    H = [rng.standard_normal((n, n)) for _ in range(A + 1)]
+    with pb.Parament("fp64") as ctx:
+        ctx.set_hamiltonian(H[0], *H[1:], use_magnus=True, quadrature_mode="simpson")
+        with pytest.raises(ValueError, match="Invalid value"):
+            ctx.equiprop(0.001, *rng.uniform(-1, 1, (A, 9)))
+
+
 def test_device_resident_operands(pb):
     """Parament_equipropDevice: amplitudes and result stay in HBM (torch only provides the device memory)."""
     torch = pytest.importorskip("torch")
