@@ -179,6 +179,12 @@ PARAMENT_API Parament_ErrorCode Parament_combine(struct Parament_Context_f32 *ha
 PARAMENT_API Parament_ErrorCode Parament_combine_fp64(struct Parament_Context_f64 *handle, const Parament_c128 *parts,
                                                       unsigned int count, Parament_c128 *out);
 
+/* Device-resident combine (either context type): parts_dev holds `count` dim x dim propagators in the context precision on
+ * the context's device, earliest slice first; out_dev receives their ordered product.  Enqueued on `stream` (cudaStream_t
+ * as void*) without synchronising, or on the context's stream followed by a synchronisation when stream is NULL. */
+PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void *parts_dev, unsigned int count, void *out_dev,
+                                                       void *stream);
+
 /* Introspection of the last equiprop on this context (either context type).  Keys:
  *   0 device milliseconds between first and last kernel (CUDA events on the context stream)
  *   1 number of kernels launched          2 Chebyshev degree used (MMAX actually evaluated)

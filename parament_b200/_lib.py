@@ -61,6 +61,7 @@ lib.OneNorm_fp64.argtypes = [c128_p, u32]
 lib.OneNorm_fp64.restype = f64
 lib.device_info.argtypes = []
 lib.device_info.restype = None
+lib.Parament_combineDevice.argtypes = [ctx_p, ctypes.c_void_p, u32, ctypes.c_void_p, ctypes.c_void_p]
 lib.Parament_lastStat.argtypes = [ctx_p, ctypes.c_int]
 lib.Parament_lastStat.restype = f64
 lib.Parament_setDevice.argtypes = [ctx_p, ctypes.c_int]
@@ -80,5 +81,5 @@ EXPORTED = [
     # section 2: additive
     "Parament_equipropBatch", "Parament_equipropBatch_fp64", "Parament_equipropDevice",
     "Parament_equipropDevice_fp64", "Parament_equipropSlice", "Parament_equipropSlice_fp64", "Parament_combine",
-    "Parament_combine_fp64", "Parament_lastStat", "Parament_setDevice", "Parament_measurePeak", "Parament_version",
+    "Parament_combine_fp64", "Parament_combineDevice", "Parament_lastStat", "Parament_setDevice", "Parament_measurePeak", "Parament_version",
 ]

@@ -110,7 +110,7 @@ Parament_ErrorCode destroy_ctx(Context *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
-    free_dev(c->d_Y); free_dev(c->d_pending); free_dev(c->d_tree);
+    free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_out) cudaFreeHost(c->h_out);
     cudaEventDestroy(c->ev_start);
@@ -765,48 +765,53 @@ Parament_ErrorCode equiprop_device(Context *c, const T *carr_dev, double dt, uns
     return PARAMENT_STATUS_SUCCESS;
 }
 
-// out = parts[count-1] ... parts[0] on the device (multi-GPU combine of time slices)
+// out = parts[count-1] ... parts[0]: ordered E-form tree on the GEMM kernel (multi-GPU combine of time slices).
+// Device-resident core: parts_dev / out_dev in the IO precision, scratch from the context (grow-only), no synchronisation.
+Parament_ErrorCode combine_device_core(Context *c, const void *parts_dev, unsigned int count, void *out_dev, cudaStream_t st) {
+    const int n = c->dim;
+    const int gp = k4_pad(n);
+    const size_t gnn = (size_t)gp * gp;
+    if (!ensure_dev(c->d_comb, (size_t)count * gnn * sizeof(double2)) ||
+        !ensure_dev(c->d_comb2, (size_t)(count / 2 + 1) * gnn * sizeof(double2)))
+        return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+    c->stat_launches = 0;
+    PB_LAUNCH(k4_eform(c->fp64, parts_dev, n, gp, (int)count, (double2 *)c->d_comb.ptr, st));
+    Parament_ErrorCode ec = tree_reduce_all(c, (double2 *)c->d_comb.ptr, (int)count, (double2 *)c->d_comb2.ptr, gp, st);
+    if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+    PB_LAUNCH(k4_finish(c->fp64, (const double2 *)c->d_comb.ptr, n, gp, out_dev, true, st));
+    return PARAMENT_STATUS_SUCCESS;
+}
+
 template <typename T>
 Parament_ErrorCode combine_host(Context *c, const T *parts, unsigned int count, T *out) {
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
     cudaSetDevice(c->device);
     if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);
     if (!parts || !out || count == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
-    const int n = c->dim;
-    const int gp = k4_pad(n);   // the combine always runs on the GEMM kernels
-    const size_t gnn = (size_t)gp * gp;
-    // E-form copies in double, zero padded: E = P - I
-    std::vector<double2> padded((size_t)count * gnn, make_double2(0, 0));
-    for (unsigned int i = 0; i < count; ++i)
-        for (int r = 0; r < n; ++r)
-            for (int col = 0; col < n; ++col) {
-                const T v = parts[((size_t)i * n + r) * n + col];
-                padded[(size_t)i * gnn + (size_t)r * gp + col] = make_double2((double)v.re - (r == col ? 1.0 : 0.0), (double)v.im);
-            }
-    const double2 *src_host = padded.data();
-    DeviceBuffer a, b;
-    const size_t out_bytes = (size_t)n * n * sizeof(T);
-    if (!ensure_dev(a, (size_t)count * gnn * sizeof(double2)) || !ensure_dev(b, (size_t)(count / 2 + 1) * gnn * sizeof(double2)) ||
-        !ensure_dev(c->d_out, out_bytes)) {
-        free_dev(a); free_dev(b);
-        return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
-    }
-    Parament_ErrorCode ec = PARAMENT_STATUS_SUCCESS;
-    c->stat_launches = 0;
-    if (!PB_CUDA_OK(cudaMemcpyAsync(a.ptr, src_host, (size_t)count * gnn * sizeof(double2), cudaMemcpyHostToDevice, c->stream)))
-        ec = PARAMENT_STATUS_CUBLAS_FAILED;
-    if (ec == PARAMENT_STATUS_SUCCESS) ec = tree_reduce_all(c, (double2 *)a.ptr, (int)count, (double2 *)b.ptr, gp, c->stream);
-    if (ec == PARAMENT_STATUS_SUCCESS && k4_finish(c->fp64, (const double2 *)a.ptr, n, gp, c->d_out.ptr, true, c->stream) != cudaSuccess)
-        ec = PARAMENT_STATUS_CUBLAS_FAILED;
-    if (ec == PARAMENT_STATUS_SUCCESS &&
-        (!PB_CUDA_OK(cudaMemcpyAsync(out, c->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, c->stream)) ||
-         !PB_CUDA_OK(cudaStreamSynchronize(c->stream))))
-        ec = PARAMENT_STATUS_CUBLAS_FAILED;
-    cudaStreamSynchronize(c->stream);
-    free_dev(a); free_dev(b);
+    const size_t in_bytes = (size_t)count * c->dim * c->dim * sizeof(T), out_bytes = (size_t)c->dim * c->dim * sizeof(T);
+    if (!ensure_dev(c->d_carr, in_bytes) || !ensure_dev(c->d_out, out_bytes)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
+    if (!PB_CUDA_OK(cudaMemcpyAsync(c->d_carr.ptr, parts, in_bytes, cudaMemcpyHostToDevice, c->stream)))
+        return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+    Parament_ErrorCode ec = combine_device_core(c, c->d_carr.ptr, count, c->d_out.ptr, c->stream);
     if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
+    if (!PB_CUDA_OK(cudaMemcpyAsync(out, c->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, c->stream)) ||
+        !PB_CUDA_OK(cudaStreamSynchronize(c->stream)))
+        return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
     c->lastError = PARAMENT_STATUS_SUCCESS;
-    return ec;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+Parament_ErrorCode combine_device(Context *c, const void *parts_dev, unsigned int count, void *out_dev, void *stream) {
+    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    cudaSetDevice(c->device);
+    if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);
+    if (!parts_dev || !out_dev || count == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    Parament_ErrorCode ec = combine_device_core(c, parts_dev, count, out_dev, st);
+    if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
+    if (!stream && !PB_CUDA_OK(cudaStreamSynchronize(st))) return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+    c->lastError = PARAMENT_STATUS_SUCCESS;
+    return PARAMENT_STATUS_SUCCESS;
 }
 
 }  // namespace
@@ -871,6 +876,10 @@ Parament_ErrorCode Parament_combine(struct Parament_Context_f32 *h, const Parame
 }
 Parament_ErrorCode Parament_combine_fp64(struct Parament_Context_f64 *h, const Parament_c128 *parts, unsigned int count, Parament_c128 *out) {
     return combine_host<Parament_c128>(as_ctx(h), parts, count, out);
+}
+
+Parament_ErrorCode Parament_combineDevice(void *h, const void *parts_dev, unsigned int count, void *out_dev, void *stream) {
+    return combine_device(as_ctx(h), parts_dev, count, out_dev, stream);
 }
 
 int Parament_selectIterationCycles_fp32(double H_norm, double dt) { return select_cycles_fp32(H_norm, dt); }
@@ -978,7 +987,7 @@ Parament_ErrorCode Parament_setDevice(void *h, int device) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
-    free_dev(c->d_Y); free_dev(c->d_pending); free_dev(c->d_tree);
+    free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
     cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); destroy_copy_events(c);
     cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->stream);
     c->device = device;

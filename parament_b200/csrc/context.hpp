@@ -50,6 +50,7 @@ struct Context {
     // per-call scratch (grow-only)
     DeviceBuffer d_carr, d_out, d_partials;
     DeviceBuffer d_Y, d_pending, d_tree;   // families 2 / 3: series slots, pending partial products, tree scratch
+    DeviceBuffer d_comb, d_comb2;   // combine of time-slice partials
     void *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for carr
     void *h_out = nullptr;   size_t h_out_bytes = 0;    // pinned staging for results
 

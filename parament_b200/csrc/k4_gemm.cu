@@ -351,6 +351,21 @@ __global__ void k4_finish_kernel(const double2 *__restrict__ E, int n, int npad,
     out[e] = o;
 }
 
+// E[b] (npad x npad, zero padded) = P[b] - I  for `count` propagators in the IO precision (multi-GPU combine input)
+template <typename IO>
+__global__ void k4_eform_kernel(const IO *__restrict__ P, int n, int npad, int count, double2 *__restrict__ E) {
+    const size_t nn = (size_t)npad * npad;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nn * count) return;
+    const int b = (int)(e / nn), r = (int)((e % nn) / npad), c = (int)(e % npad);
+    double2 v = make_double2(0.0, 0.0);
+    if (r < n && c < n) {
+        const IO x = P[((size_t)b * n + r) * n + c];
+        v = make_double2((double)x.x - (r == c ? 1.0 : 0.0), (double)x.y);
+    }
+    E[e] = v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -507,6 +522,14 @@ cudaError_t k4_assemble(bool fp64_io, const SeriesParams &p, const SeriesProgram
         k4_assemble_kernel<double2><<<grid, 256, 0, stream>>>(p, prog, (const double2 *)carr, H, slot0, slot4, slot5, step0, S);
     else
         k4_assemble_kernel<float2><<<grid, 256, 0, stream>>>(p, prog, (const float2 *)carr, H, slot0, slot4, slot5, step0, S);
+    return cudaGetLastError();
+}
+
+cudaError_t k4_eform(bool fp64_io, const void *P, int n, int npad, int count, double2 *E, cudaStream_t stream) {
+    const size_t total = (size_t)npad * npad * count;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (fp64_io) k4_eform_kernel<double2><<<blocks, 256, 0, stream>>>((const double2 *)P, n, npad, count, E);
+    else         k4_eform_kernel<float2><<<blocks, 256, 0, stream>>>((const float2 *)P, n, npad, count, E);
     return cudaGetLastError();
 }
 

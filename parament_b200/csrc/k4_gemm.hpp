@@ -54,6 +54,7 @@ int k4_chain_slots(int npad, int num_sms);    // co-resident CTAs of the persist
 // Batched path: slots[s] points at S consecutive matrices.
 cudaError_t k4_assemble(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,
                         double2 *slot0, double2 *slot4, double2 *slot5, unsigned long long step0, int S, cudaStream_t stream);
+cudaError_t k4_eform(bool fp64_io, const void *P, int n, int npad, int count, double2 *E, cudaStream_t stream);   // E = P - I, padded
 cudaError_t k4_finish(bool fp64_io, const double2 *E, int n, int npad, void *out, bool add_identity, cudaStream_t stream);
 
 // Persistent single-tile chain kernel (npad == 32 or 64): `grid` CTAs each walk a contiguous range of the nsteps steps

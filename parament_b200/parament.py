@@ -156,6 +156,12 @@ class Parament:
         self._check_error(self._fn("Parament_combine")(self._handle, parts.ravel(), parts.shape[0], out))
         return out.reshape(self.dim, self.dim)
 
+    def combine_device(self, parts_ptr, count, out_ptr, stream=None):
+        """Ordered product of `count` device-resident partial propagators (raw device pointers, context precision)."""
+        self._alive()
+        self._check_error(lib.Parament_combineDevice(self._handle, ctypes.c_void_p(parts_ptr), int(count), ctypes.c_void_p(out_ptr),
+                                                     ctypes.c_void_p(stream) if stream else None))
+
     def equiprop_device(self, dt, carr_ptr, pts, amps, out_ptr, batch=1, stream=None):
         """Device-resident operands (raw device pointers, e.g. torch.Tensor.data_ptr())."""
         self._alive()

@@ -222,6 +222,25 @@ def test_time_slices_compose(pb, name, pts, slices):
     assert rel_frobenius(combined, host) < tol
 
 
+def test_device_resident_combine(pb):
+    """Parament_combineDevice: the ordered product of slice propagators that already sit in HBM (what bench.py does with
+    the NCCL all-gather output)."""
+    torch = pytest.importorskip("torch")
+    w = make_workload("C2", pts=40001)
+    with pb.Parament(w.precision) as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, quadrature_mode="simpson")
+        N = w.steps
+        b = [N * g // 5 for g in range(6)]
+        parts = np.stack([ctx.equiprop_slice(w.dt, w.carr, b[g], b[g + 1]) for g in range(5)])
+        host = ctx.combine(parts)
+        d_parts = torch.from_numpy(parts).cuda()
+        d_out = torch.zeros(16, 16, dtype=torch.complex64, device="cuda")
+        ctx.combine_device(d_parts.data_ptr(), 5, d_out.data_ptr())
+        assert np.array_equal(d_out.cpu().numpy(), host)
+        whole = ctx.equiprop(w.dt, *w.carr)
+    assert rel_frobenius(host, whole) < 2e-6
+
+
 def test_time_reversal_property(pb):
     """U(H, c)^-1 = U(-H, reversed c) for QUADRATURE_NONE -- a full-size, oracle-free check."""
     w = make_workload("C2", pts=200001)
