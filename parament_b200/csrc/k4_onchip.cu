@@ -3,8 +3,16 @@
 // One persistent CTA (256 threads, 8 warps of 32x16 DMMA tiles) per SM walks a contiguous range of time steps.  Three
 // 64x64 complex128 buffers (pitch 68, 209 KB) hold, per step, Y / W = Y^2 / the recurrence matrices; every product of the
 // series reads both operands from shared memory with LDS.128 straight into mma.sync.m8n8k4.f64 fragments and writes its
-// result back to shared memory in the epilogue, so inside a step nothing but the Horner addend Y (epilogue, thread-private)
-// and the running product F touch L2, and there is no cp.async pipeline to fill or drain between the ~7 dependent products.
+// result back to shared memory in the epilogue; the Horner addend Y is thread-private and stays in registers for the whole
+// step, so inside a step only the running product F touches L2 (one read, one write), and there is no cp.async pipeline
+// to fill or drain between the ~7 dependent products.
+// Because one CTA owns the SM, every phase without DMMAs leaves the FP64 tensor pipe idle; therefore
+//   * the assembly of Y_{j+1} = sigma (H0 + sum_t c_t H_t) is software-pipelined INTO the main loop of the last product
+//     of step j (the running-product update): one matrix element per thread and k-tile, its table loads issued one
+//     k-tile ahead, so their L2 latency hides behind the DMMAs;
+//   * the start value of the Horner recurrence is folded into the first product
+//     (R_{L-1} = c_{2L+1} (Y W) + c_{2L} W + c_{2L-1} Y + c_{2L-2} I), no separate elementwise pass;
+//   * epilogues are specialised at compile time.
 // Replaces, for these dimensions, the MMAX batched cuBLAS GEMMs + diagonal_add launches of parament.cpp:569-652 and the
 // reduction of parament.cpp:657-718; supersedes k4_chain_kernel (operands streamed from an L2 scratch) for npad == 64.
 #include "coef.cuh"
@@ -16,51 +24,117 @@ constexpr int OC_N = 64;            // padded dimension
 constexpr int OC_P = OC_N + 4;      // pitch in double2: rows 8 apart fall into different bank groups for the A-fragment loads
 constexpr int OC_BUF = OC_N * OC_P; // elements per buffer
 constexpr int OC_THREADS = 256;
+constexpr int OC_NN = OC_N * OC_N;
+constexpr int OC_EPT = OC_NN / OC_THREADS;   // matrix elements per thread in elementwise phases (16 == k-tiles per product)
+constexpr int OC_MAXT = 8;                   // control terms the fused assembly keeps in registers
 constexpr size_t OC_SMEM = 3 * (size_t)OC_BUF * sizeof(double2);
+static_assert(OC_EPT == OC_N / 4, "one assembled element per k-tile");
 
-struct OcEpilogue {
-    const double2 *c1_smem;    // addend read from a shared-memory buffer (own elements), or null
-    const double2 *c1_glob;    // addend read from a global row-major matrix, or null
-    const double2 *c2_glob;    // second global addend, or null
-    cplx beta1, beta1_lo;
-    double beta2;
-    cplx gamma, gamma_lo;
-    double2 *d_smem;           // destination buffer in shared memory, or null
-    double2 *d_glob;           // destination in global memory (row-major, pitch OC_N), or null
+enum OcEpi : int {
+    EPI_STORE = 0,     // D_smem = A B
+    EPI_FIRST = 1,     // D_smem = alpha (A B) + bw * Wown(smem) + by * Y(global) + gamma I          (first Horner product)
+    EPI_HORNER = 2,    // D_smem = A B + i ci Y(global) + cr I                                      (+ sub-ulp remainders if LO)
+    EPI_CLENSHAW = 3,  // D_smem = A B + beta * Cown(smem, == D) + gamma I
+    EPI_CHAIN = 4      // D_glob = A B + Eown(smem) + F(global)
 };
 
-// D = A * B + addends, A and B in shared memory (pitch OC_P).  All 256 threads; no barrier inside.
-__device__ __forceinline__ void oc_gemm(const double2 *__restrict__ sA, const double2 *__restrict__ sB, const OcEpilogue &ep) {
+// Shared-memory buffers are named by their element OFFSET into the dynamic shared array, never by pointer: a pointer that
+// travels through a struct loses its address space and the compiler falls back to generic LD/ST (measured: 233 generic
+// loads in the SASS and ~20 % of the kernel time).
+extern __shared__ __align__(16) double2 oc_smem[];
+
+struct OcArgs {
+    int sA, sB;                 // operands (offsets into oc_smem)
+    int d_smem;                 // destination buffer (all but EPI_CHAIN)
+    double2 *d_glob;            // destination in global memory (EPI_CHAIN)
+    int c_smem;                 // shared-memory addend, own elements (EPI_FIRST: W, EPI_CLENSHAW: B_{k+2}, EPI_CHAIN: E)
+    int c_smem2;                // second shared-memory addend, own elements (EPI_CHAIN: F, which is also the B operand)
+    cplx alpha, bw, by;         // EPI_FIRST
+    double ci, ci_lo, cr, cr_lo;   // EPI_HORNER
+    double beta;                // EPI_CLENSHAW
+    cplx gamma, gamma_lo;
+};
+
+// Fused assembly of the next step's Y (one element per thread and k-tile).
+struct OcAssemble {
+    const double2 *H;           // table, [mat][64*64]
+    const cplx *coef;           // shared memory, nterms coefficients of the NEXT step
+    const Term *terms;
+    int nterms;
+    double sigma;
+    int y_smem;                 // destination buffer (offset into oc_smem, pitch OC_P)
+};
+
+__device__ __forceinline__ void oc_issue_loads(const OcAssemble &as, int e, double2 &h0, double2 (&h)[OC_MAXT]) {
+    h0 = __ldg(as.H + e);
+#pragma unroll
+    for (int t = 0; t < OC_MAXT; ++t)
+        if (t < as.nterms) h[t] = __ldg(as.H + (size_t)as.terms[t].mat * OC_NN + e);
+}
+
+__device__ __forceinline__ double2 oc_combine(const OcAssemble &as, double2 x, const double2 (&h)[OC_MAXT]) {
+#pragma unroll
+    for (int t = 0; t < OC_MAXT; ++t)
+        if (t < as.nterms) {
+            const cplx ct = as.coef[t];
+            x.x += ct.re * h[t].x - ct.im * h[t].y;
+            x.y += ct.re * h[t].y + ct.im * h[t].x;
+        }
+    return make_double2(x.x * as.sigma, x.y * as.sigma);
+}
+
+// D = A * B (+ epilogue), A and B in shared memory (pitch OC_P).  All 256 threads; no barrier inside.
+constexpr int OC_MT = 4, OC_NTL = 2;
+typedef double2 OcOwn[OC_MT][OC_NTL][2];   // a thread's own 16 elements of a matrix, in epilogue order
+
+// own elements of a shared-memory matrix -> registers
+__device__ __forceinline__ void oc_load_own(OcOwn &y, int m) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, q = lane & 3;
+    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16;
+#pragma unroll
+    for (int mt = 0; mt < OC_MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < OC_NTL; ++nt) {
+            const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q;
+            y[mt][nt][0] = oc_smem[m + r * OC_P + c];
+            y[mt][nt][1] = oc_smem[m + r * OC_P + c + 1];
+        }
+}
+
+// `y`: the thread's own elements of Y (EPI_FIRST / EPI_HORNER), loaded once per step by oc_load_own.
+template <int EPI, bool LO, bool ASSEMBLE>
+__device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, const OcOwn &y) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, q = lane & 3;
     const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16;
     constexpr int MT = 4, NTL = 2;
+    const double2 *sA = oc_smem + g.sA;
+    const double2 *sB = oc_smem + g.sB;
 
-    // the global addend is thread-private: fetch it before the main loop so its latency hides behind the products
-    double2 y[MT][NTL][2];
-    if (ep.c1_glob) {
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NTL; ++nt) {
-                const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q;
-                y[mt][nt][0] = ep.c1_glob[r * OC_N + c];
-                y[mt][nt][1] = ep.c1_glob[r * OC_N + c + 1];
-            }
-    }
     double cre[MT][NTL][2], cim[MT][NTL][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NTL; ++nt) { cre[mt][nt][0] = cre[mt][nt][1] = 0.0; cim[mt][nt][0] = cim[mt][nt][1] = 0.0; }
 
-#pragma unroll 4
+    double2 h0, h[OC_MAXT];
+    if (ASSEMBLE) oc_issue_loads(as, tid, h0, h);
+
+#pragma unroll 2
     for (int kt = 0; kt < OC_N / 4; ++kt) {
         double2 af[MT], bf[NTL];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) af[mt] = sA[(wm0 + 8 * mt + gq) * OC_P + 4 * kt + q];
 #pragma unroll
         for (int nt = 0; nt < NTL; ++nt) bf[nt] = sB[(4 * kt + q) * OC_P + wn0 + 8 * nt + gq];
+        if (ASSEMBLE) {
+            // element e = tid + 256 kt of the next step's Y: consume the loads issued one k-tile ago, issue the next ones
+            const int e = tid + kt * OC_THREADS;
+            const double2 v = oc_combine(as, h0, h);
+            if (kt + 1 < OC_N / 4) oc_issue_loads(as, e + OC_THREADS, h0, h);
+            oc_smem[as.y_smem + (e >> 6) * OC_P + (e & 63)] = v;
+        }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -76,173 +150,209 @@ __device__ __forceinline__ void oc_gemm(const double2 *__restrict__ sA, const do
         }
     }
 
-    // epilogue (small terms first, DESIGN.md "Numerics")
+    // ---- epilogue (small terms first, dominant term last with one FMA rounding: DESIGN.md "Numerics") ----
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NTL; ++nt) {
             const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q;
             double vr[2] = {cre[mt][nt][0], cre[mt][nt][1]}, vi[2] = {cim[mt][nt][0], cim[mt][nt][1]};
-            if (ep.c2_glob) {
-                const double2 x0 = ep.c2_glob[r * OC_N + c], x1 = ep.c2_glob[r * OC_N + c + 1];
-                vr[0] += ep.beta2 * x0.x; vi[0] += ep.beta2 * x0.y; vr[1] += ep.beta2 * x1.x; vi[1] += ep.beta2 * x1.y;
-            }
-            double2 z[2] = {make_double2(0, 0), make_double2(0, 0)};
-            const bool has_c1 = ep.c1_glob || ep.c1_smem;
-            if (ep.c1_glob) { z[0] = y[mt][nt][0]; z[1] = y[mt][nt][1]; }
-            else if (ep.c1_smem) { z[0] = ep.c1_smem[r * OC_P + c]; z[1] = ep.c1_smem[r * OC_P + c + 1]; }
-            if (has_c1) {
+            if (EPI == EPI_FIRST) {
+                const double2 w0 = oc_smem[g.c_smem + r * OC_P + c], w1 = oc_smem[g.c_smem + r * OC_P + c + 1];
+                const double2 ws[2] = {w0, w1};
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    vr[i] += ep.beta1_lo.re * z[i].x - ep.beta1_lo.im * z[i].y;
-                    vi[i] += ep.beta1_lo.re * z[i].y + ep.beta1_lo.im * z[i].x;
+                    const double pr = vr[i], pi = vi[i];
+                    double tr = g.alpha.re * pr - g.alpha.im * pi + (g.bw.re * ws[i].x - g.bw.im * ws[i].y);
+                    double ti = g.alpha.re * pi + g.alpha.im * pr + (g.bw.re * ws[i].y + g.bw.im * ws[i].x);
+                    if (r == c + i) { tr += g.gamma.re; ti += g.gamma.im; }
+                    vr[i] = fma(g.by.re, y[mt][nt][i].x, fma(-g.by.im, y[mt][nt][i].y, tr));
+                    vi[i] = fma(g.by.re, y[mt][nt][i].y, fma(g.by.im, y[mt][nt][i].x, ti));
                 }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-                if (r == c + i) { vr[i] = (vr[i] + ep.gamma_lo.re) + ep.gamma.re; vi[i] = (vi[i] + ep.gamma_lo.im) + ep.gamma.im; }
-            if (has_c1) {
+            } else if (EPI == EPI_HORNER) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    vr[i] = fma(ep.beta1.re, z[i].x, fma(-ep.beta1.im, z[i].y, vr[i]));
-                    vi[i] = fma(ep.beta1.re, z[i].y, fma(ep.beta1.im, z[i].x, vi[i]));
+                    const double yr = y[mt][nt][i].x, yi = y[mt][nt][i].y;
+                    if (LO) {
+                        vr[i] = fma(-g.ci_lo, yi, vr[i]);
+                        vi[i] = fma(g.ci_lo, yr, vi[i]);
+                        if (r == c + i) vr[i] = (vr[i] + g.cr_lo) + g.cr;
+                    } else if (r == c + i) {
+                        vr[i] += g.cr;
+                    }
+                    vr[i] = fma(-g.ci, yi, vr[i]);
+                    vi[i] = fma(g.ci, yr, vi[i]);
                 }
+            } else if (EPI == EPI_CLENSHAW) {
+                const double2 w0 = oc_smem[g.c_smem + r * OC_P + c], w1 = oc_smem[g.c_smem + r * OC_P + c + 1];
+                vr[0] = fma(g.beta, w0.x, vr[0]); vi[0] = fma(g.beta, w0.y, vi[0]);
+                vr[1] = fma(g.beta, w1.x, vr[1]); vi[1] = fma(g.beta, w1.y, vi[1]);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (r == c + i) { vr[i] = (vr[i] + g.gamma_lo.re) + g.gamma.re; vi[i] = (vi[i] + g.gamma_lo.im) + g.gamma.im; }
+            } else if (EPI == EPI_CHAIN) {
+                const double2 e0 = oc_smem[g.c_smem + r * OC_P + c], e1 = oc_smem[g.c_smem + r * OC_P + c + 1];
+                const double2 f0 = oc_smem[g.c_smem2 + r * OC_P + c], f1 = oc_smem[g.c_smem2 + r * OC_P + c + 1];
+                vr[0] += e0.x + f0.x; vi[0] += e0.y + f0.y;
+                vr[1] += e1.x + f1.x; vi[1] += e1.y + f1.y;
             }
-            if (ep.d_smem) {
-                ep.d_smem[r * OC_P + c] = make_double2(vr[0], vi[0]);
-                ep.d_smem[r * OC_P + c + 1] = make_double2(vr[1], vi[1]);
-            }
-            if (ep.d_glob) {
-                ep.d_glob[r * OC_N + c] = make_double2(vr[0], vi[0]);
-                ep.d_glob[r * OC_N + c + 1] = make_double2(vr[1], vi[1]);
+            if (EPI == EPI_CHAIN) {
+                g.d_glob[r * OC_N + c] = make_double2(vr[0], vi[0]);
+                g.d_glob[r * OC_N + c + 1] = make_double2(vr[1], vi[1]);
+            } else {
+                oc_smem[g.d_smem + r * OC_P + c] = make_double2(vr[0], vi[0]);
+                oc_smem[g.d_smem + r * OC_P + c + 1] = make_double2(vr[1], vi[1]);
             }
         }
 }
 
-// scratch per CTA: 3 matrices (Y, F0, F1), row-major pitch 64 (the host allocates kSeriesSlots + 2).
+// scratch per CTA: 2 matrices (F0, F1), row-major pitch 64 (the host allocates kSeriesSlots + 2).
 template <typename IO>
 __global__ void __launch_bounds__(OC_THREADS, 1)
-k4_onchip_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__restrict__ carr, const double2 *__restrict__ H,
+k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__ SeriesProgram prog, const IO *__restrict__ carr, const double2 *__restrict__ H,
                  double2 *__restrict__ scratch, double2 *__restrict__ partials, unsigned long long nsteps) {
-    constexpr int NN = OC_N * OC_N;
-    extern __shared__ __align__(16) unsigned char oc_smem_raw[];
-    double2 *P0 = reinterpret_cast<double2 *>(oc_smem_raw), *P1 = P0 + OC_BUF, *P2 = P1 + OC_BUF;
     __shared__ cplx coef[kMaxTerms];
 
     const int tid = threadIdx.x;
-    double2 *Yg = scratch + (size_t)blockIdx.x * 3 * NN;
-    double2 *Fg[2] = {Yg + NN, Yg + 2 * NN};
+    double2 *Fg[2] = {scratch + (size_t)blockIdx.x * 2 * OC_NN, scratch + (size_t)blockIdx.x * 2 * OC_NN + OC_NN};
     const unsigned long long lo = nsteps * blockIdx.x / gridDim.x, hi = nsteps * (blockIdx.x + 1) / gridDim.x;
     int f_cur = 0;
     bool have_f = false;
     const int M = p.M;
-    const cplx zero{0.0, 0.0};
+    const bool horner = p.horner != 0;
+    const bool fuse = p.nterms <= OC_MAXT;   // next step's assembly rides in the running-product update
+    constexpr bool LO = sizeof(IO) == sizeof(double2);   // sub-ulp remainders of the constants: complex128 contexts only
+
+    OcAssemble as{};
+    as.H = H; as.coef = coef; as.terms = p.terms; as.nterms = p.nterms; as.sigma = p.sigma;
+    const OcAssemble none{};
+
+    int iy = 0;              // buffer index holding Y of the current step
+    bool y_ready = false;    // Y of the current step was assembled by the previous step's fused pass
 
     for (unsigned long long j = lo; j < hi; ++j) {
-        for (int t = tid; t < p.nterms; t += OC_THREADS)
-            coef[t] = step_coefficient<IO>(p.terms[t], carr, p.pts, p.quad, p.magfac, j);
-        __syncthreads();
-        // ---- assemble Y into P0 (operand of the first product); Horner also keeps a global copy for the epilogues ----
-        // 16 elements per thread; the table reads of 4 elements (up to 9 matrices each) are issued back to back so that
-        // their L2 latency overlaps -- this phase has no other CTA on the SM to hide behind
-#pragma unroll 4
-        for (int it = 0; it < NN / OC_THREADS; ++it) {
-            const int e = tid + it * OC_THREADS;
-            double2 x = __ldg(H + e);
-            double2 h[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-                if (t < p.nterms) h[t] = __ldg(H + (size_t)p.terms[t].mat * NN + e);
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-                if (t < p.nterms) {
-                    const cplx ct = coef[t];
-                    x.x += ct.re * h[t].x - ct.im * h[t].y;
-                    x.y += ct.re * h[t].y + ct.im * h[t].x;
-                }
-            for (int t = 8; t < p.nterms; ++t) {
-                const double2 hh = __ldg(H + (size_t)p.terms[t].mat * NN + e);
-                const cplx ct = coef[t];
-                x.x += ct.re * hh.x - ct.im * hh.y;
-                x.y += ct.re * hh.y + ct.im * hh.x;
-            }
-            const double yr = x.x * p.sigma, yi = x.y * p.sigma;
-            const int r = e >> 6, c = e & 63;
-            const bool diag = (r == c);
-            const double2 s2 = make_double2(((prog.u.re * yr - prog.u.im * yi) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
-                                            ((prog.u.re * yi + prog.u.im * yr) + (diag ? prog.v_lo.im : 0.0)) + (diag ? prog.v.im : 0.0));
-            if (p.horner) {
-                P0[r * OC_P + c] = make_double2(yr, yi);
-                P2[r * OC_P + c] = s2;                                  // R_L
-                Yg[e] = make_double2(yr, yi);
-            } else {
-                P2[r * OC_P + c] = make_double2(yr, yi);                // Y stays the right operand of every product
-                P0[r * OC_P + c] = s2;                                  // B_{M-1}  (or E itself when M == 1)
-                P1[r * OC_P + c] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);   // B_M
-            }
-        }
-        __syncthreads();
-
-        double2 *E;
-        if (p.horner) {
-            OcEpilogue ep{};
-            ep.beta1 = ep.beta1_lo = ep.gamma = ep.gamma_lo = zero;
-            ep.d_smem = P1;
-            oc_gemm(P0, P0, ep);                                        // W = Y Y  -> P1
+        if (!y_ready) {
+            // ---- standalone assembly (first step of the CTA, or more control terms than the fused pass keeps) ----
+            for (int t = tid; t < p.nterms; t += OC_THREADS)
+                coef[t] = step_coefficient<IO>(p.terms[t], carr, p.pts, p.quad, p.magfac, j);
             __syncthreads();
-            double2 *cur = P2, *oth = P0;
-            for (int i = (M >> 1) - 1; i >= 0; --i) {                   // R <- R W + c_{2i+1} Y + c_{2i} I
-                OcEpilogue eh{};
-                eh.c1_glob = Yg;
-                eh.beta1 = p.a[2 * i + 1]; eh.beta1_lo = p.a_lo[2 * i + 1];
-                eh.gamma = p.a[2 * i]; eh.gamma_lo = p.a_lo[2 * i];
-                eh.d_smem = oth;
-                oc_gemm(cur, P1, eh);
-                __syncthreads();
-                double2 *t = cur; cur = oth; oth = t;
+#pragma unroll 4
+            for (int it = 0; it < OC_EPT; ++it) {
+                const int e = tid + it * OC_THREADS;
+                double2 x = __ldg(H + e);
+                for (int t = 0; t < p.nterms; ++t) {
+                    const double2 hh = __ldg(H + (size_t)p.terms[t].mat * OC_NN + e);
+                    const cplx ct = coef[t];
+                    x.x += ct.re * hh.x - ct.im * hh.y;
+                    x.y += ct.re * hh.y + ct.im * hh.x;
+                }
+                const double2 v = make_double2(x.x * p.sigma, x.y * p.sigma);
+                oc_smem[iy * OC_BUF + (e >> 6) * OC_P + (e & 63)] = v;
             }
-            E = cur;
-        } else if (M == 1) {
-            E = P0;
+            __syncthreads();
+        }
+        const int PY = iy * OC_BUF, PA = ((iy + 1) % 3) * OC_BUF, PB = ((iy + 2) % 3) * OC_BUF;   // buffer offsets
+        int E;       // result of the series
+        int Fb;      // buffer that will receive F for the running-product update
+        int Yn;      // buffer that will receive the next step's Y
+
+        OcOwn y;
+        if (horner) {
+            oc_load_own(y, PY);             // own elements of Y: addend of every Horner epilogue of this step
+            // W = Y Y -> PA
+            OcArgs a{};
+            a.sA = PY; a.sB = PY; a.d_smem = PA;
+            oc_gemm<EPI_STORE, false, false>(a, none, y);
+            __syncthreads();
+            // R_{L-1} = c_{2L+1} (Y W) + c_{2L} W + c_{2L-1} Y + c_{2L-2} I -> PB          (L = M / 2 >= 1)
+            const int L = M >> 1;
+            OcArgs f{};
+            f.sA = PY; f.sB = PA; f.d_smem = PB; f.c_smem = PA;
+            f.alpha = (2 * L + 1 <= M) ? p.a[2 * L + 1] : cplx{0.0, 0.0};
+            f.bw = p.a[2 * L]; f.by = p.a[2 * L - 1]; f.gamma = p.a[2 * L - 2];
+            oc_gemm<EPI_FIRST, false, false>(f, none, y);
+            __syncthreads();
+            int cur = PB, oth = PY;           // Y is dead as an operand from here on (its own elements are in registers)
+            for (int i = L - 2; i >= 0; --i) {
+                OcArgs hA{};
+                hA.sA = cur; hA.sB = PA; hA.d_smem = oth;
+                hA.ci = p.a[2 * i + 1].im; hA.ci_lo = p.a_lo[2 * i + 1].im; hA.cr = p.a[2 * i].re; hA.cr_lo = p.a_lo[2 * i].re;
+                if (LO && i <= 1) oc_gemm<EPI_HORNER, true, false>(hA, none, y);
+                else              oc_gemm<EPI_HORNER, false, false>(hA, none, y);
+                __syncthreads();
+                const int t = cur; cur = oth; oth = t;
+            }
+            E = cur; Fb = oth; Yn = PA;       // W is dead
         } else {
-            double2 *cur = P0, *oth = P1;
-            for (int k = M - 2; k >= 0; --k) {                          // B_k = B_{k+1} Y - B_{k+2} + a_k I ; last: E = B_1 Y - 2 B_2 + a0' I
-                OcEpilogue ec{};
-                ec.c1_smem = oth;
-                ec.beta1 = cplx{k == 0 ? -2.0 : -1.0, 0.0}; ec.beta1_lo = zero;
-                ec.gamma = p.a[k]; ec.gamma_lo = p.a_lo[k];
-                ec.d_smem = oth;
-                oc_gemm(cur, P2, ec);
-                __syncthreads();
-                double2 *t = cur; cur = oth; oth = t;
+            // Clenshaw: PY keeps Y as the right operand; PA = B_{M-1} = a_M Y + a_{M-1} I, PB = B_M = a_M I
+            for (int it = 0; it < OC_EPT; ++it) {
+                const int e = tid + it * OC_THREADS;
+                const int r = e >> 6, c = e & 63;
+                const bool diag = (r == c);
+                const double2 v = oc_smem[PY + r * OC_P + c];
+                oc_smem[PA + r * OC_P + c] = make_double2(((prog.u.re * v.x - prog.u.im * v.y) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
+                                                ((prog.u.re * v.y + prog.u.im * v.x) + (diag ? prog.v_lo.im : 0.0)) + (diag ? prog.v.im : 0.0));
+                oc_smem[PB + r * OC_P + c] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
             }
-            E = cur;
+            __syncthreads();
+            int cur = PA, oth = PB;
+            for (int k = M - 2; k >= 0; --k) {       // B_k = B_{k+1} Y - B_{k+2} + a_k I ; k = 0: E = B_1 Y - 2 B_2 + a0' I
+                OcArgs cA{};
+                cA.sA = cur; cA.sB = PY; cA.d_smem = oth; cA.c_smem = oth;
+                cA.beta = (k == 0) ? -2.0 : -1.0; cA.gamma = p.a[k]; cA.gamma_lo = p.a_lo[k];
+                oc_gemm<EPI_CLENSHAW, false, false>(cA, none, y);
+                __syncthreads();
+                const int t = cur; cur = oth; oth = t;
+            }
+            E = cur; Fb = oth; Yn = PY;      // for M == 1 the loop is empty and E = PA = a_1 Y + a0' I
         }
 
         // ---- running product in E-form:  F <- E + F + E F  (later step on the left); F lives in L2 ----
+        const bool more = (j + 1 < hi);
+        const bool fuse_now = more && fuse && have_f;
+        if (more && fuse) {   // coefficients of the next step (read by the fused pass or by nobody)
+            for (int t = tid; t < p.nterms; t += OC_THREADS)
+                coef[t] = step_coefficient<IO>(p.terms[t], carr, p.pts, p.quad, p.magfac, j + 1);
+        }
         if (!have_f) {
-            for (int e = tid; e < NN; e += OC_THREADS) Fg[f_cur][e] = E[(e >> 6) * OC_P + (e & 63)];
-            have_f = true;
-        } else {
-            double2 *fb = (E == P0) ? P1 : P0;                          // any buffer that is not E
 #pragma unroll
-            for (int it = 0; it < NN / OC_THREADS; ++it) {
+            for (int it = 0; it < OC_EPT; ++it) {
                 const int e = tid + it * OC_THREADS;
-                fb[(e >> 6) * OC_P + (e & 63)] = Fg[f_cur][e];
+                Fg[f_cur][e] = oc_smem[E + (e >> 6) * OC_P + (e & 63)];
+            }
+            have_f = true;
+            __syncthreads();
+            y_ready = false;
+            iy = Yn / OC_BUF;
+        } else {
+            {   // F (L2) -> shared memory without staging through registers: 16 x 16-byte cp.async per thread in flight
+                const double2 *fsrc = Fg[f_cur];
+#pragma unroll
+                for (int it = 0; it < OC_EPT; ++it) {
+                    const int e = tid + it * OC_THREADS;
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Fb + (e >> 6) * OC_P + (e & 63));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(fsrc + e));
+                }
+                asm volatile("cp.async.commit_group;\n" ::);
+                asm volatile("cp.async.wait_group 0;\n" ::);
             }
             __syncthreads();
-            OcEpilogue ef{};
-            ef.c1_smem = E; ef.beta1 = cplx{1.0, 0.0}; ef.beta1_lo = zero;
-            ef.c2_glob = Fg[f_cur]; ef.beta2 = 1.0;
-            ef.gamma = ef.gamma_lo = zero;
-            ef.d_glob = Fg[f_cur ^ 1];
-            oc_gemm(E, fb, ef);
+            OcArgs ch{};
+            ch.sA = E; ch.sB = Fb; ch.c_smem = E; ch.c_smem2 = Fb; ch.d_glob = Fg[f_cur ^ 1];
+            if (fuse_now) {
+                as.y_smem = Yn;
+                oc_gemm<EPI_CHAIN, false, true>(ch, as, y);
+            } else {
+                oc_gemm<EPI_CHAIN, false, false>(ch, none, y);
+            }
             f_cur ^= 1;
+            __syncthreads();
+            y_ready = fuse_now;
+            iy = Yn / OC_BUF;
         }
-        __syncthreads();
     }
-    double2 *out = partials + (size_t)blockIdx.x * NN;
-    for (int e = tid; e < NN; e += OC_THREADS) out[e] = have_f ? Fg[f_cur][e] : make_double2(0.0, 0.0);
+    double2 *out = partials + (size_t)blockIdx.x * OC_NN;
+    for (int e = tid; e < OC_NN; e += OC_THREADS) out[e] = have_f ? Fg[f_cur][e] : make_double2(0.0, 0.0);
 }
 
 int k4_onchip_slots(int num_sms) {
