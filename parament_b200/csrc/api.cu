@@ -454,7 +454,8 @@ F3Plan plan_family3(const Context *c, const CallSpec &s) {
     if (waves > 4) waves = 4;
     f.S = (int)std::max<long long>(2, std::min<long long>(per_wave * waves, std::max<long long>(budget, per_wave)));
     if ((unsigned long long)f.S > s.nsteps) f.S = (int)std::max<unsigned long long>(s.nsteps, 1);
-    const size_t want = std::min<size_t>(2048, std::max<size_t>(64, ((size_t)2 << 30) / (nn * sizeof(double2))));
+    // pending partial products: enough for the first tree levels to run in whole waves (16 chunks), bounded by 1.5 GiB
+    const size_t want = std::min<size_t>(std::max<size_t>(64, (size_t)16 * f.S), std::max<size_t>(64, ((size_t)3 << 29) / (nn * sizeof(double2))));
     f.cap = (int)std::max<size_t>(2, std::min<size_t>(want, (size_t)std::min<unsigned long long>(s.nsteps, 1ull << 30)));
     return f;
 }
@@ -529,11 +530,12 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
                 g.C2 = nullptr; g.beta2 = 0.0; g.n = np; g.batch = Sc;
                 PB_LAUNCH(k4_gemm(g, st));
             }
-            // ordered product inside the chunk while the launches still fill the machine
+            // ordered product inside the chunk only while a level still fills a whole wave of CTAs; smaller levels are
+            // deferred to the pending buffer, whose reduction runs on hundreds of matrices at a time (full waves)
             double2 *src = slots[prog.e_slot];
             double2 *other = slots[prog.e_slot == 4 ? 5 : 4];
             int count = Sc;
-            while (count > 1 && (count / 2) * tiles >= 48) {
+            while (count > 1 && (count / 2) * tiles >= c->k4_slots) {
                 int nc = 0;
                 Parament_ErrorCode ec = tree_level(c, src, count, other, np, st, nc);
                 if (ec != PARAMENT_STATUS_SUCCESS) return ec;
