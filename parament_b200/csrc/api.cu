@@ -201,7 +201,35 @@ bool upload_matrices(Context *c) {
                 tab[((size_t)m * np + r) * np + col] = make_double2(v.real(), v.imag());
             }
     if (!ensure_dev(c->d_H, tab.size() * sizeof(double2))) return false;
-    return PB_CUDA_OK(cudaMemcpy(c->d_H.ptr, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    if (!PB_CUDA_OK(cudaMemcpy(c->d_H.ptr, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice))) return false;
+    if (c->enable_magnus) {
+        // commutator slots on the device: T = B A, then C = A B - T (two launches of the tensor-pipe GEMM per commutator;
+        // the reference does the same with cuBLAS, parament.cpp:300-355)
+        const size_t nn = (size_t)np * np;
+        const int A = c->amps;
+        double2 *H = (double2 *)c->d_H.ptr;
+        DeviceBuffer tmp;
+        if (!ensure_dev(tmp, nn * sizeof(double2))) return false;
+        auto comm = [&](int ia, int ib, int iout) -> bool {
+            GemmArgs g{};
+            g.n = np; g.batch = 1;
+            g.A = H + (size_t)ib * nn; g.B = H + (size_t)ia * nn; g.D = (double2 *)tmp.ptr;        // T = B A
+            if (k4_gemm(g, c->stream) != cudaSuccess) return false;
+            GemmArgs h{};
+            h.n = np; h.batch = 1;
+            h.A = H + (size_t)ia * nn; h.B = H + (size_t)ib * nn; h.D = H + (size_t)iout * nn;    // A B - T
+            h.C[0] = (const double2 *)tmp.ptr; h.beta[0] = cplx{-1.0, 0.0};
+            return k4_gemm(h, c->stream) == cudaSuccess;
+        };
+        bool ok = true;
+        for (int j = 0; j < A && ok; ++j) ok = comm(0, 1 + j, 1 + A + j);
+        for (int j = 0; j < A && ok; ++j)
+            for (int k = j + 1; k < A && ok; ++k) ok = comm(1 + j, 1 + k, 1 + 2 * A + pair_index(j, k, A));
+        ok = ok && PB_CUDA_OK(cudaStreamSynchronize(c->stream));
+        free_dev(tmp);
+        if (!ok) return false;
+    }
+    return true;
 }
 
 template <typename T>
@@ -235,15 +263,6 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     c->Hnorm = one_norm_t<T>(H0, dim);
     for (int a = 0; a < A; ++a) c->Hnorm += one_norm_t<T>(H1 + (size_t)a * nn, dim);
 
-    if (use_magnus) {   // physical commutators [H0,H_j] and [H_j,H_k], j<k (parament.cpp:289-359)
-        const zc *h0 = c->mats.data();
-        for (int j = 0; j < A; ++j) commutator(h0, h0 + (size_t)(1 + j) * nn, c->mats.data() + (size_t)(1 + A + j) * nn, (int)dim);
-        for (int j = 0; j < A; ++j)
-            for (int k = j + 1; k < A; ++k)
-                commutator(h0 + (size_t)(1 + j) * nn, h0 + (size_t)(1 + k) * nn,
-                           c->mats.data() + (size_t)(1 + 2 * A + pair_index(j, k, A)) * nn, (int)dim);
-    }
-
     if (dim <= 16) { c->family = 1; c->npad = dim <= 8 ? 8 : 16; }
     else if (dim <= 64) {
         c->family = 2; c->npad = k4_pad((int)dim);
@@ -252,6 +271,18 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
         c->k4_slots = c->onchip ? oc : k4_chain_slots(c->npad, c->num_sms);
     }
     else                { c->family = 3; c->npad = k4_pad((int)dim); c->k4_slots = k4_wave_slots(c->npad, c->num_sms); }
+
+    // physical commutators [H0,H_j] and [H_j,H_k], j<k (parament.cpp:289-359): on the host for the
+    // register-resident family (tiny matrices), on the device GEMM kernel otherwise (upload_matrices)
+    if (use_magnus && c->family == 1) {
+        const zc *h0 = c->mats.data();
+        for (int j = 0; j < A; ++j) commutator(h0, h0 + (size_t)(1 + j) * nn, c->mats.data() + (size_t)(1 + A + j) * nn, (int)dim);
+        for (int j = 0; j < A; ++j)
+            for (int k = j + 1; k < A; ++k)
+                commutator(h0 + (size_t)(1 + j) * nn, h0 + (size_t)(1 + k) * nn,
+                           c->mats.data() + (size_t)(1 + 2 * A + pair_index(j, k, A)) * nn, (int)dim);
+    }
+
     if (!upload_matrices(c)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
     c->have_hamiltonian = true;
     c->lastError = PARAMENT_STATUS_SUCCESS;

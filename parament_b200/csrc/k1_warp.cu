@@ -15,6 +15,7 @@
 // control_expansion.cu / diagonal_add.cu for these dimensions.  The running product is kept transposed,
 // Q = (U_{hi-1} ... U_lo)^T = U_lo^T ... U_{hi-1}^T, see frag.cuh.
 #include "coef.cuh"
+#include <cstdlib>
 #include "k1_warp.hpp"
 
 namespace pb {
@@ -43,8 +44,9 @@ __device__ __forceinline__ void cta_ordered_product(AccFrag<NT> &Q, double2 *sme
 }
 
 // Hfrag layout: [matrix][layout 0 = AccFrag order, 1 = BFrag order][element e < 2*NT*NT][lane] as double2.
-template <int NT, typename IO, int HORNER>
-__global__ void __launch_bounds__(32 * K1_WARPS, (NT == 1) ? 6 : (HORNER ? 2 : 3))
+// OCC: CTAs per SM the register allocation is bounded for (NT == 2: 2 -> 255 registers, 3 -> 168 registers with spills)
+template <int NT, typename IO, int HORNER, int OCC>
+__global__ void __launch_bounds__(32 * K1_WARPS, OCC)
 k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ Hfrag,
                 double2 *__restrict__ partials, unsigned int batch, unsigned int chunks_per_pulse,
                 unsigned long long step_lo, unsigned long long step_hi, int reduce_in_cta) {
@@ -250,14 +252,23 @@ k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, unsigned
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
+template <int NT, typename IO, int HORNER, int OCC>
+static cudaError_t launch_chain_ttt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
+                                   unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
+                                   unsigned long long step_hi, cudaStream_t stream) {
+    k1_chain_kernel<NT, IO, HORNER, OCC><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
+                                                                                   plan.chunks_per_pulse, step_lo, step_hi,
+                                                                                   plan.reduce_in_cta);
+    return cudaGetLastError();
+}
+
 template <int NT, typename IO, int HORNER>
 static cudaError_t launch_chain_tt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                    unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
                                    unsigned long long step_hi, cudaStream_t stream) {
-    k1_chain_kernel<NT, IO, HORNER><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
-                                                                              plan.chunks_per_pulse, step_lo, step_hi,
-                                                                              plan.reduce_in_cta);
-    return cudaGetLastError();
+    if (NT == 1) return launch_chain_ttt<NT, IO, HORNER, 6>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
+    if (plan.ctas_per_sm == 3) return launch_chain_ttt<NT, IO, HORNER, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
+    return launch_chain_ttt<NT, IO, HORNER, 2>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
 }
 
 template <int NT, typename IO>
@@ -272,7 +283,9 @@ int k3_warps_for(unsigned int partials_per_pulse);
 
 K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms, bool horner) {
     K1Plan plan{};
-    const int ctas_per_sm = (npad == 8) ? 6 : (horner ? 2 : 3);
+    static const int occ_env = getenv("PARAMENT_K1_OCC") ? atoi(getenv("PARAMENT_K1_OCC")) : 0;
+    const int ctas_per_sm = (npad == 8) ? 6 : (occ_env == 2 || occ_env == 3 ? occ_env : (horner ? 2 : 3));
+    plan.ctas_per_sm = ctas_per_sm;
     const unsigned long long warps_total = (unsigned long long)num_sms * ctas_per_sm * K1_WARPS;
     if (batch >= warps_total / 2 || nsteps < 2ull * K1_WARPS) {
         plan.chunks_per_pulse = 1;                 // a warp owns a whole pulse

@@ -12,6 +12,7 @@ struct K1Plan {
     unsigned int partials_per_pulse;   // matrices the reduce kernel combines per pulse
     int reduce_in_cta;                 // 1: the warps of a CTA belong to one pulse and combine in shared memory
     int k3_warps;                      // warps per CTA of the reduce kernel
+    int ctas_per_sm;                   // occupancy the chain kernel variant is compiled for
     size_t partial_elems;              // double2 elements of the partial buffer
 };
 

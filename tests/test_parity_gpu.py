@@ -335,7 +335,7 @@ def test_magnus_many_controls(pb):
 
 @pytest.mark.parametrize("n,A,pts,quad,mag", [(33, 2, 40, "none", False), (48, 3, 30, "simpson", True), (63, 1, 25, "midpoint", False),
                                               (65, 2, 9, "none", False), (100, 2, 7, "simpson", False), (17, 12, 50, "none", False),
-                                              (9, 8, 61, "simpson", True), (130, 1, 5, "midpoint", False)])
+                                              (9, 8, 61, "simpson", True), (130, 1, 5, "midpoint", False), (70, 2, 11, "simpson", True)])
 def test_odd_dimensions_and_many_controls(pb, n, A, pts, quad, mag):
     """Padding of every kernel family (dims just above / below the family boundaries) and large control counts
     (Magnus with 8 controls = 44 effective terms)."""
