@@ -1,0 +1,30 @@
+"""pip-installable build of parament_b200 (the reference's src/setup.py:28-77 shells out to nvcc the same way).
+
+    pip install --no-build-isolation .          # builds parament_b200/lib/libparament.so for sm_100a with nvcc
+    NVCC=/path/to/nvcc pip install .            # honour a specific compiler (the reference honours NVCC_ARGS, setup.py:43)
+"""
+import os
+import subprocess
+
+from setuptools import setup
+from setuptools.command.build_py import build_py
+
+
+class BuildWithCuda(build_py):
+    def run(self):
+        here = os.path.dirname(os.path.abspath(__file__))
+        env = dict(os.environ)
+        subprocess.check_call(["make", "-C", os.path.join(here, "parament_b200", "csrc"), "-j4"], env=env)
+        super().run()
+
+
+setup(
+    name="parament-b200",
+    version="0.1.0",
+    description="B200-native Parament_equiprop: drop-in libparament.so (FP64 tensor pipe) and its ctypes interface",
+    packages=["parament_b200"],
+    package_data={"parament_b200": ["lib/libparament.so"]},
+    cmdclass={"build_py": BuildWithCuda},
+    python_requires=">=3.9",
+    install_requires=["numpy"],
+)
