@@ -266,7 +266,7 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     if (dim <= 16) { c->family = 1; c->npad = dim <= 8 ? 8 : 16; }
     else if (dim <= 64) {
         c->family = 2; c->npad = k4_pad((int)dim);
-        const int oc = (c->npad == 64 && !getenv("PARAMENT_NO_ONCHIP")) ? k4_onchip_slots(c->num_sms) : 0;
+        const int oc = !getenv("PARAMENT_NO_ONCHIP") ? k4_onchip_slots(c->npad, c->num_sms) : 0;
         c->onchip = oc > 0;
         c->k4_slots = c->onchip ? oc : k4_chain_slots(c->npad, c->num_sms);
     }

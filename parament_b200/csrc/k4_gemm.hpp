@@ -62,8 +62,8 @@ cudaError_t k4_finish(bool fp64_io, const double2 *E, int n, int npad, void *out
 cudaError_t k4_chain(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,
                      double2 *scratch, double2 *partials, unsigned long long nsteps, int grid, cudaStream_t stream);
 
-// dim 33..64: persistent kernel with the step's operands resident in shared memory (k4_onchip.cu); scratch: 3 matrices per CTA.
-int k4_onchip_slots(int num_sms);             // 0 if the device cannot host it
+// dim 17..64: persistent kernel with the step's operands resident in shared memory (k4_onchip.cu); scratch: 2 matrices per CTA.
+int k4_onchip_slots(int npad, int num_sms);   // co-resident CTAs; 0 if the device cannot host it
 cudaError_t k4_onchip(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,
                       double2 *scratch, double2 *partials, unsigned long long nsteps, int grid, cudaStream_t stream);
 

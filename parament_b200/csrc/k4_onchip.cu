@@ -20,15 +20,21 @@
 
 namespace pb {
 
-constexpr int OC_N = 64;            // padded dimension
-constexpr int OC_P = OC_N + 4;      // pitch in double2: rows 8 apart fall into different bank groups for the A-fragment loads
-constexpr int OC_BUF = OC_N * OC_P; // elements per buffer
-constexpr int OC_THREADS = 256;
-constexpr int OC_NN = OC_N * OC_N;
-constexpr int OC_EPT = OC_NN / OC_THREADS;   // matrix elements per thread in elementwise phases (16 == k-tiles per product)
-constexpr int OC_MAXT = 8;                   // control terms the fused assembly keeps in registers
-constexpr size_t OC_SMEM = 3 * (size_t)OC_BUF * sizeof(double2);
-static_assert(OC_EPT == OC_N / 4, "one assembled element per k-tile");
+// Geometry for padded dimension N (64: 8 warps of 32x16 tiles; 32: 4 warps of 16x16 tiles).
+template <int N>
+struct Oc {
+    static constexpr int P = N + 4;                 // pitch in double2: rows 8 apart fall into different bank groups (A fragments)
+    static constexpr int BUF = N * P;               // elements per buffer
+    static constexpr int WM = N / 2, WN = N / 4 < 16 ? 16 : N / 4;   // warp tile
+    static constexpr int WARPS_N = N / WN, WARPS = (N / WM) * WARPS_N;
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int MT = WM / 8, NTL = WN / 8;
+    static constexpr int NN = N * N;
+    static constexpr int EPT = NN / THREADS;        // matrix elements per thread in elementwise phases
+    static constexpr size_t SMEM = 3 * (size_t)BUF * sizeof(double2);
+    static_assert(EPT == N / 4, "one assembled element per k-tile");
+};
+constexpr int OC_MAXT = 8;                          // control terms the fused assembly keeps in registers
 
 enum OcEpi : int {
     EPI_STORE = 0,     // D_smem = A B
@@ -65,11 +71,12 @@ struct OcAssemble {
     int y_smem;                 // destination buffer (offset into oc_smem, pitch OC_P)
 };
 
+template <int N>
 __device__ __forceinline__ void oc_issue_loads(const OcAssemble &as, int e, double2 &h0, double2 (&h)[OC_MAXT]) {
     h0 = __ldg(as.H + e);
 #pragma unroll
     for (int t = 0; t < OC_MAXT; ++t)
-        if (t < as.nterms) h[t] = __ldg(as.H + (size_t)as.terms[t].mat * OC_NN + e);
+        if (t < as.nterms) h[t] = __ldg(as.H + (size_t)as.terms[t].mat * Oc<N>::NN + e);
 }
 
 __device__ __forceinline__ double2 oc_combine(const OcAssemble &as, double2 x, const double2 (&h)[OC_MAXT]) {
@@ -84,31 +91,35 @@ __device__ __forceinline__ double2 oc_combine(const OcAssemble &as, double2 x, c
 }
 
 // D = A * B (+ epilogue), A and B in shared memory (pitch OC_P).  All 256 threads; no barrier inside.
-constexpr int OC_MT = 4, OC_NTL = 2;
-typedef double2 OcOwn[OC_MT][OC_NTL][2];   // a thread's own 16 elements of a matrix, in epilogue order
+// a thread's own elements of a matrix, in epilogue order (sized for the larger geometry)
+typedef double2 OcOwn[4][2][2];
 
 // own elements of a shared-memory matrix -> registers
+template <int N>
 __device__ __forceinline__ void oc_load_own(OcOwn &y, int m) {
+    using G = Oc<N>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, q = lane & 3;
-    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16;
+    const int wm0 = (warp / G::WARPS_N) * G::WM, wn0 = (warp % G::WARPS_N) * G::WN;
 #pragma unroll
-    for (int mt = 0; mt < OC_MT; ++mt)
+    for (int mt = 0; mt < G::MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < OC_NTL; ++nt) {
+        for (int nt = 0; nt < G::NTL; ++nt) {
             const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q;
-            y[mt][nt][0] = oc_smem[m + r * OC_P + c];
-            y[mt][nt][1] = oc_smem[m + r * OC_P + c + 1];
+            y[mt][nt][0] = oc_smem[m + r * G::P + c];
+            y[mt][nt][1] = oc_smem[m + r * G::P + c + 1];
         }
 }
 
 // `y`: the thread's own elements of Y (EPI_FIRST / EPI_HORNER), loaded once per step by oc_load_own.
-template <int EPI, bool LO, bool ASSEMBLE>
+template <int N, int EPI, bool LO, bool ASSEMBLE>
 __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, const OcOwn &y) {
+    using G = Oc<N>;
+    constexpr int OC_P = G::P, OC_N = N, OC_THREADS = G::THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, q = lane & 3;
-    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16;
-    constexpr int MT = 4, NTL = 2;
+    const int wm0 = (warp / G::WARPS_N) * G::WM, wn0 = (warp % G::WARPS_N) * G::WN;
+    constexpr int MT = G::MT, NTL = G::NTL;
     const double2 *sA = oc_smem + g.sA;
     const double2 *sB = oc_smem + g.sB;
 
@@ -119,7 +130,7 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
         for (int nt = 0; nt < NTL; ++nt) { cre[mt][nt][0] = cre[mt][nt][1] = 0.0; cim[mt][nt][0] = cim[mt][nt][1] = 0.0; }
 
     double2 h0, h[OC_MAXT];
-    if (ASSEMBLE) oc_issue_loads(as, tid, h0, h);
+    if (ASSEMBLE) oc_issue_loads<N>(as, tid, h0, h);
 
 #pragma unroll 2
     for (int kt = 0; kt < OC_N / 4; ++kt) {
@@ -132,8 +143,8 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
             // element e = tid + 256 kt of the next step's Y: consume the loads issued one k-tile ago, issue the next ones
             const int e = tid + kt * OC_THREADS;
             const double2 v = oc_combine(as, h0, h);
-            if (kt + 1 < OC_N / 4) oc_issue_loads(as, e + OC_THREADS, h0, h);
-            oc_smem[as.y_smem + (e >> 6) * OC_P + (e & 63)] = v;
+            if (kt + 1 < OC_N / 4) oc_issue_loads<N>(as, e + OC_THREADS, h0, h);
+            oc_smem[as.y_smem + (e / OC_N) * OC_P + (e % OC_N)] = v;
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -207,10 +218,12 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
 }
 
 // scratch per CTA: 2 matrices (F0, F1), row-major pitch 64 (the host allocates kSeriesSlots + 2).
-template <typename IO>
-__global__ void __launch_bounds__(OC_THREADS, 1)
+template <int N, typename IO>
+__global__ void __launch_bounds__(Oc<N>::THREADS, N == 64 ? 1 : 2)
 k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__ SeriesProgram prog, const IO *__restrict__ carr, const double2 *__restrict__ H,
                  double2 *__restrict__ scratch, double2 *__restrict__ partials, unsigned long long nsteps) {
+    using G = Oc<N>;
+    constexpr int OC_P = G::P, OC_N = N, OC_THREADS = G::THREADS, OC_NN = G::NN, OC_EPT = G::EPT, OC_BUF = G::BUF;
     __shared__ cplx coef[kMaxTerms];
 
     const int tid = threadIdx.x;
@@ -247,7 +260,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                     x.y += ct.re * hh.y + ct.im * hh.x;
                 }
                 const double2 v = make_double2(x.x * p.sigma, x.y * p.sigma);
-                oc_smem[iy * OC_BUF + (e >> 6) * OC_P + (e & 63)] = v;
+                oc_smem[iy * OC_BUF + (e / OC_N) * OC_P + (e % OC_N)] = v;
             }
             __syncthreads();
         }
@@ -258,11 +271,11 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 
         OcOwn y;
         if (horner) {
-            oc_load_own(y, PY);             // own elements of Y: addend of every Horner epilogue of this step
+            oc_load_own<N>(y, PY);             // own elements of Y: addend of every Horner epilogue of this step
             // W = Y Y -> PA
             OcArgs a{};
             a.sA = PY; a.sB = PY; a.d_smem = PA;
-            oc_gemm<EPI_STORE, false, false>(a, none, y);
+            oc_gemm<N, EPI_STORE, false, false>(a, none, y);
             __syncthreads();
             // R_{L-1} = c_{2L+1} (Y W) + c_{2L} W + c_{2L-1} Y + c_{2L-2} I -> PB          (L = M / 2 >= 1)
             const int L = M >> 1;
@@ -270,15 +283,15 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             f.sA = PY; f.sB = PA; f.d_smem = PB; f.c_smem = PA;
             f.alpha = (2 * L + 1 <= M) ? p.a[2 * L + 1] : cplx{0.0, 0.0};
             f.bw = p.a[2 * L]; f.by = p.a[2 * L - 1]; f.gamma = p.a[2 * L - 2];
-            oc_gemm<EPI_FIRST, false, false>(f, none, y);
+            oc_gemm<N, EPI_FIRST, false, false>(f, none, y);
             __syncthreads();
             int cur = PB, oth = PY;           // Y is dead as an operand from here on (its own elements are in registers)
             for (int i = L - 2; i >= 0; --i) {
                 OcArgs hA{};
                 hA.sA = cur; hA.sB = PA; hA.d_smem = oth;
                 hA.ci = p.a[2 * i + 1].im; hA.ci_lo = p.a_lo[2 * i + 1].im; hA.cr = p.a[2 * i].re; hA.cr_lo = p.a_lo[2 * i].re;
-                if (LO && i <= 1) oc_gemm<EPI_HORNER, true, false>(hA, none, y);
-                else              oc_gemm<EPI_HORNER, false, false>(hA, none, y);
+                if (LO && i <= 1) oc_gemm<N, EPI_HORNER, true, false>(hA, none, y);
+                else              oc_gemm<N, EPI_HORNER, false, false>(hA, none, y);
                 __syncthreads();
                 const int t = cur; cur = oth; oth = t;
             }
@@ -287,7 +300,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             // Clenshaw: PY keeps Y as the right operand; PA = B_{M-1} = a_M Y + a_{M-1} I, PB = B_M = a_M I
             for (int it = 0; it < OC_EPT; ++it) {
                 const int e = tid + it * OC_THREADS;
-                const int r = e >> 6, c = e & 63;
+                const int r = e / OC_N, c = e % OC_N;
                 const bool diag = (r == c);
                 const double2 v = oc_smem[PY + r * OC_P + c];
                 oc_smem[PA + r * OC_P + c] = make_double2(((prog.u.re * v.x - prog.u.im * v.y) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
@@ -300,7 +313,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                 OcArgs cA{};
                 cA.sA = cur; cA.sB = PY; cA.d_smem = oth; cA.c_smem = oth;
                 cA.beta = (k == 0) ? -2.0 : -1.0; cA.gamma = p.a[k]; cA.gamma_lo = p.a_lo[k];
-                oc_gemm<EPI_CLENSHAW, false, false>(cA, none, y);
+                oc_gemm<N, EPI_CLENSHAW, false, false>(cA, none, y);
                 __syncthreads();
                 const int t = cur; cur = oth; oth = t;
             }
@@ -318,7 +331,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 #pragma unroll
             for (int it = 0; it < OC_EPT; ++it) {
                 const int e = tid + it * OC_THREADS;
-                Fg[f_cur][e] = oc_smem[E + (e >> 6) * OC_P + (e & 63)];
+                Fg[f_cur][e] = oc_smem[E + (e / OC_N) * OC_P + (e % OC_N)];
             }
             have_f = true;
             __syncthreads();
@@ -330,7 +343,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 #pragma unroll
                 for (int it = 0; it < OC_EPT; ++it) {
                     const int e = tid + it * OC_THREADS;
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Fb + (e >> 6) * OC_P + (e & 63));
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Fb + (e / OC_N) * OC_P + (e % OC_N));
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(fsrc + e));
                 }
                 asm volatile("cp.async.commit_group;\n" ::);
@@ -341,9 +354,9 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             ch.sA = E; ch.sB = Fb; ch.c_smem = E; ch.c_smem2 = Fb; ch.d_glob = Fg[f_cur ^ 1];
             if (fuse_now) {
                 as.y_smem = Yn;
-                oc_gemm<EPI_CHAIN, false, true>(ch, as, y);
+                oc_gemm<N, EPI_CHAIN, false, true>(ch, as, y);
             } else {
-                oc_gemm<EPI_CHAIN, false, false>(ch, none, y);
+                oc_gemm<N, EPI_CHAIN, false, false>(ch, none, y);
             }
             f_cur ^= 1;
             __syncthreads();
@@ -355,25 +368,32 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
     for (int e = tid; e < OC_NN; e += OC_THREADS) out[e] = have_f ? Fg[f_cur][e] : make_double2(0.0, 0.0);
 }
 
-int k4_onchip_slots(int num_sms) {
+template <int N>
+static int onchip_slots_t(int num_sms) {
     int per_sm = 0;
-    cudaFuncSetAttribute(k4_onchip_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_onchip_kernel<double2>, OC_THREADS, OC_SMEM);
+    cudaFuncSetAttribute(k4_onchip_kernel<N, double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Oc<N>::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_onchip_kernel<N, double2>, Oc<N>::THREADS, Oc<N>::SMEM);
     return per_sm < 1 ? 0 : per_sm * num_sms;
+}
+
+int k4_onchip_slots(int npad, int num_sms) { return npad == 64 ? onchip_slots_t<64>(num_sms) : onchip_slots_t<32>(num_sms); }
+
+template <int N, typename IO>
+static cudaError_t launch_onchip_t(const SeriesParams &p, const SeriesProgram &prog, const IO *carr, const double2 *H,
+                                   double2 *scratch, double2 *partials, unsigned long long nsteps, int grid, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(k4_onchip_kernel<N, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Oc<N>::SMEM);
+    if (e != cudaSuccess) return e;
+    k4_onchip_kernel<N, IO><<<grid, Oc<N>::THREADS, Oc<N>::SMEM, stream>>>(p, prog, carr, H, scratch, partials, nsteps);
+    return cudaGetLastError();
 }
 
 cudaError_t k4_onchip(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,
                       double2 *scratch, double2 *partials, unsigned long long nsteps, int grid, cudaStream_t stream) {
-    if (fp64_io) {
-        cudaError_t e = cudaFuncSetAttribute(k4_onchip_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM);
-        if (e != cudaSuccess) return e;
-        k4_onchip_kernel<double2><<<grid, OC_THREADS, OC_SMEM, stream>>>(p, prog, (const double2 *)carr, H, scratch, partials, nsteps);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(k4_onchip_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OC_SMEM);
-        if (e != cudaSuccess) return e;
-        k4_onchip_kernel<float2><<<grid, OC_THREADS, OC_SMEM, stream>>>(p, prog, (const float2 *)carr, H, scratch, partials, nsteps);
-    }
-    return cudaGetLastError();
+    if (p.npad == 64)
+        return fp64_io ? launch_onchip_t<64, double2>(p, prog, (const double2 *)carr, H, scratch, partials, nsteps, grid, stream)
+                       : launch_onchip_t<64, float2>(p, prog, (const float2 *)carr, H, scratch, partials, nsteps, grid, stream);
+    return fp64_io ? launch_onchip_t<32, double2>(p, prog, (const double2 *)carr, H, scratch, partials, nsteps, grid, stream)
+                   : launch_onchip_t<32, float2>(p, prog, (const float2 *)carr, H, scratch, partials, nsteps, grid, stream);
 }
 
 }  // namespace pb

@@ -48,3 +48,16 @@ if __name__ == "__main__":
         e2e("C2", pinned=pin)
         e2e("C5", pinned=pin)
         e2e("C2", pinned=pin, pts=1000000 - 1)   # even point count: strided 2-D copy path
+
+def custom(n, A, pts, prec="fp64", reps=2):
+    rng = np.random.default_rng(n)
+    mk = lambda s: s * ((g := rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) + g.conj().T) / 2
+    def norm1(m): return m / np.max(np.sum(np.abs(m), axis=1))
+    H0 = 0.5 * norm1(mk(1.0)); H1 = [0.5 / A * norm1(mk(1.0)) for _ in range(A)]
+    carr = rng.uniform(-1, 1, (A, pts))
+    with pb.Parament(prec) as ctx:
+        ctx.set_hamiltonian(H0, *H1)
+        for r in range(reps):
+            ctx.equiprop(0.2, *carr)
+            st = ctx.stats()
+        print(f"custom n={n} A={A} pts={pts} {prec} dev_ms={st['device_ms']:.3f} steps/s={pts/st['device_ms']*1e3:.3e} family={int(st['family'])} products={st['products_per_step']}", flush=True)
