@@ -1004,6 +1004,7 @@ double Parament_lastStat(void *h, int key) {
             const int M = c->stat_M_used;
             if (M <= 0) return 0.0;
             if (c->stat_horner == 2) return 4.0 + (M >> 2);
+            if (c->stat_horner == 1 && c->family == 2 && c->onchip && (M == 8 || M >= 10)) return 3.0 + M / 3;   // blocks of three
             return c->stat_horner ? 2.0 + (M >> 1) : (double)std::max(M, 1);
         }
         default: return -1.0;

@@ -15,10 +15,22 @@
 //   * epilogues are specialised at compile time.
 // Replaces, for these dimensions, the MMAX batched cuBLAS GEMMs + diagonal_add launches of parament.cpp:569-652 and the
 // reduction of parament.cpp:657-718; supersedes k4_chain_kernel (operands streamed from an L2 scratch) for npad == 64.
+#include <cstdio>
 #include "coef.cuh"
 #include "k4_gemm.hpp"
 
 namespace pb {
+
+// Per-phase cycle counters (development aid, -DPB_PHASE_TIMING): block 0 prints its accumulated clock64() deltas.
+#ifdef PB_PHASE_TIMING
+#define PB_T_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_last_ = clock64();
+#define PB_T(i) { const long long pt_now_ = clock64(); pt_[i] += pt_now_ - pt_last_; pt_last_ = pt_now_; }
+#define PB_T_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("phase cycles: assemble %lld  sq %lld  cube/first %lld  top %lld  horner %lld  fcopy %lld  chain %lld  other %lld\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[5], pt_[6], pt_[7]);
+#else
+#define PB_T_DECL
+#define PB_T(i)
+#define PB_T_PRINT
+#endif
 
 // Geometry for padded dimension N (64: 8 warps of 32x16 tiles; 32: 4 warps of 16x16 tiles).
 template <int N>
@@ -35,13 +47,16 @@ struct Oc {
     static_assert(EPT == N / 4, "one assembled element per k-tile");
 };
 constexpr int OC_MAXT = 8;                          // control terms the fused assembly keeps in registers
+constexpr int OC_BLOCK = 4;                         // time steps assembled per pass over the Hamiltonian table
 
 enum OcEpi : int {
     EPI_STORE = 0,     // D_smem = A B
     EPI_FIRST = 1,     // D_smem = alpha (A B) + bw * Wown(smem) + by * Y(global) + gamma I          (first Horner product)
     EPI_HORNER = 2,    // D_smem = A B + i ci Y(global) + cr I                                      (+ sub-ulp remainders if LO)
     EPI_CLENSHAW = 3,  // D_smem = A B + beta * Cown(smem, == D) + gamma I
-    EPI_CHAIN = 4      // D_glob = A B + Eown(smem) + F(global)
+    EPI_CHAIN = 4,     // D_glob = A B + Eown(smem) + F(global)
+    EPI_KEEP = 5,      // D_smem = A B, and the thread keeps its own elements of the product in registers (y2)
+    EPI_PS3 = 6        // D_smem = A B + b2 * Y2own(regs) + b1 * Yown(regs) + gamma I        (+ sub-ulp remainders if LO)
 };
 
 // Shared-memory buffers are named by their element OFFSET into the dynamic shared array, never by pointer: a pointer that
@@ -55,7 +70,8 @@ struct OcArgs {
     double2 *d_glob;            // destination in global memory (EPI_CHAIN)
     int c_smem;                 // shared-memory addend, own elements (EPI_FIRST: W, EPI_CLENSHAW: B_{k+2}, EPI_CHAIN: E)
     int c_smem2;                // second shared-memory addend, own elements (EPI_CHAIN: F, which is also the B operand)
-    cplx alpha, bw, by;         // EPI_FIRST
+    cplx alpha, bw, by;         // EPI_FIRST (by also: coefficient of Y in EPI_PS3)
+    cplx by_lo, b2, b2_lo;      // EPI_PS3
     double ci, ci_lo, cr, cr_lo;   // EPI_HORNER
     double beta;                // EPI_CLENSHAW
     cplx gamma, gamma_lo;
@@ -68,7 +84,9 @@ struct OcAssemble {
     const Term *terms;
     int nterms;
     double sigma;
-    int y_smem;                 // destination buffer (offset into oc_smem, pitch OC_P)
+    int y_smem;                 // destination buffer of the NEXT step's Y (offset into oc_smem, pitch OC_P)
+    int nblock;                 // steps assembled per pass of the table (1..OC_BLOCK): coef[b * kMaxTerms + t] for step j+1+b
+    double2 *y_glob;            // row-major destinations of the later steps of the block: y_glob[(b - 1) * N*N + e], b >= 1
 };
 
 template <int N>
@@ -79,11 +97,12 @@ __device__ __forceinline__ void oc_issue_loads(const OcAssemble &as, int e, doub
         if (t < as.nterms) h[t] = __ldg(as.H + (size_t)as.terms[t].mat * Oc<N>::NN + e);
 }
 
-__device__ __forceinline__ double2 oc_combine(const OcAssemble &as, double2 x, const double2 (&h)[OC_MAXT]) {
+// Y element of block step b from the loaded table values
+__device__ __forceinline__ double2 oc_combine(const OcAssemble &as, int b, double2 x, const double2 (&h)[OC_MAXT]) {
 #pragma unroll
     for (int t = 0; t < OC_MAXT; ++t)
         if (t < as.nterms) {
-            const cplx ct = as.coef[t];
+            const cplx ct = as.coef[b * kMaxTerms + t];
             x.x += ct.re * h[t].x - ct.im * h[t].y;
             x.y += ct.re * h[t].y + ct.im * h[t].x;
         }
@@ -113,7 +132,7 @@ __device__ __forceinline__ void oc_load_own(OcOwn &y, int m) {
 
 // `y`: the thread's own elements of Y (EPI_FIRST / EPI_HORNER), loaded once per step by oc_load_own.
 template <int N, int EPI, bool LO, bool ASSEMBLE>
-__device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, const OcOwn &y) {
+__device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, const OcOwn &y, OcOwn &y2) {
     using G = Oc<N>;
     constexpr int OC_P = G::P, OC_N = N, OC_THREADS = G::THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -142,9 +161,9 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
         if (ASSEMBLE) {
             // element e = tid + 256 kt of the next step's Y: consume the loads issued one k-tile ago, issue the next ones
             const int e = tid + kt * OC_THREADS;
-            const double2 v = oc_combine(as, h0, h);
+            oc_smem[as.y_smem + (e / OC_N) * OC_P + (e % OC_N)] = oc_combine(as, 0, h0, h);
+            for (int b = 1; b < as.nblock; ++b) as.y_glob[(size_t)(b - 1) * (OC_N * OC_N) + e] = oc_combine(as, b, h0, h);
             if (kt + 1 < OC_N / 4) oc_issue_loads<N>(as, e + OC_THREADS, h0, h);
-            oc_smem[as.y_smem + (e / OC_N) * OC_P + (e % OC_N)] = v;
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -201,6 +220,25 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
                     if (r == c + i) { vr[i] = (vr[i] + g.gamma_lo.re) + g.gamma.re; vi[i] = (vi[i] + g.gamma_lo.im) + g.gamma.im; }
+            } else if (EPI == EPI_KEEP) {
+                y2[mt][nt][0] = make_double2(vr[0], vi[0]);
+                y2[mt][nt][1] = make_double2(vr[1], vi[1]);
+            } else if (EPI == EPI_PS3) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double2 a1 = y[mt][nt][i], a2 = y2[mt][nt][i];
+                    if (LO) {
+                        vr[i] += (g.b2_lo.re * a2.x - g.b2_lo.im * a2.y) + (g.by_lo.re * a1.x - g.by_lo.im * a1.y);
+                        vi[i] += (g.b2_lo.re * a2.y + g.b2_lo.im * a2.x) + (g.by_lo.re * a1.y + g.by_lo.im * a1.x);
+                        if (r == c + i) { vr[i] = (vr[i] + g.gamma_lo.re) + g.gamma.re; vi[i] = (vi[i] + g.gamma_lo.im) + g.gamma.im; }
+                    } else if (r == c + i) {
+                        vr[i] += g.gamma.re; vi[i] += g.gamma.im;
+                    }
+                    vr[i] = fma(g.b2.re, a2.x, fma(-g.b2.im, a2.y, vr[i]));
+                    vi[i] = fma(g.b2.re, a2.y, fma(g.b2.im, a2.x, vi[i]));
+                    vr[i] = fma(g.by.re, a1.x, fma(-g.by.im, a1.y, vr[i]));      // the Y term dominates: last
+                    vi[i] = fma(g.by.re, a1.y, fma(g.by.im, a1.x, vi[i]));
+                }
             } else if (EPI == EPI_CHAIN) {
                 const double2 e0 = oc_smem[g.c_smem + r * OC_P + c], e1 = oc_smem[g.c_smem + r * OC_P + c + 1];
                 const double2 f0 = oc_smem[g.c_smem2 + r * OC_P + c], f1 = oc_smem[g.c_smem2 + r * OC_P + c + 1];
@@ -224,16 +262,21 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                  double2 *__restrict__ scratch, double2 *__restrict__ partials, unsigned long long nsteps) {
     using G = Oc<N>;
     constexpr int OC_P = G::P, OC_N = N, OC_THREADS = G::THREADS, OC_NN = G::NN, OC_EPT = G::EPT, OC_BUF = G::BUF;
-    __shared__ cplx coef[kMaxTerms];
+    __shared__ cplx coef[OC_BLOCK * kMaxTerms];
 
     const int tid = threadIdx.x;
-    double2 *Fg[2] = {scratch + (size_t)blockIdx.x * 2 * OC_NN, scratch + (size_t)blockIdx.x * 2 * OC_NN + OC_NN};
+    // scratch per CTA: F0, F1 and OC_BLOCK - 1 pre-assembled Y matrices (the host provides kSeriesSlots + 2 >= 5)
+    double2 *cta_scratch = scratch + (size_t)blockIdx.x * (kSeriesSlots + 2) * OC_NN;
+    double2 *Fg[2] = {cta_scratch, cta_scratch + OC_NN};
+    double2 *Yq = cta_scratch + 2 * OC_NN;
+    int ahead = 0, yq_slot = 0;     // pre-assembled future steps waiting in Yq
     const unsigned long long lo = nsteps * blockIdx.x / gridDim.x, hi = nsteps * (blockIdx.x + 1) / gridDim.x;
     int f_cur = 0;
     bool have_f = false;
     const int M = p.M;
     const bool horner = p.horner != 0;
     const bool fuse = p.nterms <= OC_MAXT;   // next step's assembly rides in the running-product update
+    const bool ps3 = (M == 8 || M >= 10);    // degrees at which blocks of three need fewer products than the Y^2 form
     constexpr bool LO = sizeof(IO) == sizeof(double2);   // sub-ulp remainders of the constants: complex128 contexts only
 
     OcAssemble as{};
@@ -243,7 +286,9 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
     int iy = 0;              // buffer index holding Y of the current step
     bool y_ready = false;    // Y of the current step was assembled by the previous step's fused pass
 
+    PB_T_DECL
     for (unsigned long long j = lo; j < hi; ++j) {
+        PB_T(7)
         if (!y_ready) {
             // ---- standalone assembly (first step of the CTA, or more control terms than the fused pass keeps) ----
             for (int t = tid; t < p.nterms; t += OC_THREADS)
@@ -264,18 +309,72 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             }
             __syncthreads();
         }
+        PB_T(0)
         const int PY = iy * OC_BUF, PA = ((iy + 1) % 3) * OC_BUF, PB = ((iy + 2) % 3) * OC_BUF;   // buffer offsets
         int E;       // result of the series
         int Fb;      // buffer that will receive F for the running-product update
         int Yn;      // buffer that will receive the next step's Y
 
-        OcOwn y;
-        if (horner) {
+        OcOwn y, y2;
+        if (horner && ps3) {
+            // ---- Paterson-Stockmeyer blocks of three:  E = sum_i (c_{3i} I + c_{3i+1} Y + c_{3i+2} Y^2) V^i,  V = Y^3:
+            //      2 + floor(M/3) products; Y and Y^2 enter only through the thread's own elements, kept in registers ----
+            const cplx zero{0.0, 0.0};
+            auto cf = [&](int m) { return m <= M ? p.a[m] : zero; };
+            auto cf_lo = [&](int m) { return m <= M ? p.a_lo[m] : zero; };
+            oc_load_own<N>(y, PY);
+            OcArgs a{};
+            a.sA = PY; a.sB = PY; a.d_smem = PA;
+            oc_gemm<N, EPI_KEEP, false, false>(a, none, y, y2);         // Y^2 -> PA, own elements -> y2
+            __syncthreads();
+            PB_T(1)
+            OcArgs b{};
+            b.sA = PA; b.sB = PY; b.d_smem = PB;
+            oc_gemm<N, EPI_STORE, false, false>(b, none, y, y2);        // V = Y^2 Y -> PB
+            // top block R_L = c_{3L+2} Y^2 + c_{3L+1} Y + c_{3L} I from the own elements -> PY (Y is dead as an operand
+            // once every warp has left the product above)
+            const int L = M / 3;
+            __syncthreads();
+            PB_T(2)
+            {
+                const cplx t2 = cf(3 * L + 2), t1 = cf(3 * L + 1), t0 = cf(3 * L);
+                const int lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
+                const int wm0 = (warp / G::WARPS_N) * G::WM, wn0 = (warp % G::WARPS_N) * G::WN;
+#pragma unroll
+                for (int mt = 0; mt < G::MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < G::NTL; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q + i;
+                            const double2 a1 = y[mt][nt][i], a2 = y2[mt][nt][i];
+                            double vr = t2.re * a2.x - t2.im * a2.y + (t1.re * a1.x - t1.im * a1.y);
+                            double vi = t2.re * a2.y + t2.im * a2.x + (t1.re * a1.y + t1.im * a1.x);
+                            if (r == c) { vr += t0.re; vi += t0.im; }
+                            oc_smem[PY + r * OC_P + c] = make_double2(vr, vi);
+                        }
+            }
+            __syncthreads();
+            PB_T(3)
+            int cur = PY, oth = PA;           // Y^2 is dead as an operand as well
+            for (int i = L - 1; i >= 0; --i) {
+                OcArgs hA{};
+                hA.sA = cur; hA.sB = PB; hA.d_smem = oth;
+                hA.b2 = cf(3 * i + 2); hA.b2_lo = cf_lo(3 * i + 2); hA.by = cf(3 * i + 1); hA.by_lo = cf_lo(3 * i + 1);
+                hA.gamma = cf(3 * i); hA.gamma_lo = cf_lo(3 * i);
+                if (LO && i == 0) oc_gemm<N, EPI_PS3, true, false>(hA, none, y, y2);
+                else              oc_gemm<N, EPI_PS3, false, false>(hA, none, y, y2);
+                __syncthreads();
+                const int t = cur; cur = oth; oth = t;
+            }
+            PB_T(4)
+            E = cur; Fb = oth; Yn = PB;       // V is dead
+        } else if (horner) {
             oc_load_own<N>(y, PY);             // own elements of Y: addend of every Horner epilogue of this step
             // W = Y Y -> PA
             OcArgs a{};
             a.sA = PY; a.sB = PY; a.d_smem = PA;
-            oc_gemm<N, EPI_STORE, false, false>(a, none, y);
+            oc_gemm<N, EPI_STORE, false, false>(a, none, y, y2);
             __syncthreads();
             // R_{L-1} = c_{2L+1} (Y W) + c_{2L} W + c_{2L-1} Y + c_{2L-2} I -> PB          (L = M / 2 >= 1)
             const int L = M >> 1;
@@ -283,15 +382,15 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             f.sA = PY; f.sB = PA; f.d_smem = PB; f.c_smem = PA;
             f.alpha = (2 * L + 1 <= M) ? p.a[2 * L + 1] : cplx{0.0, 0.0};
             f.bw = p.a[2 * L]; f.by = p.a[2 * L - 1]; f.gamma = p.a[2 * L - 2];
-            oc_gemm<N, EPI_FIRST, false, false>(f, none, y);
+            oc_gemm<N, EPI_FIRST, false, false>(f, none, y, y2);
             __syncthreads();
             int cur = PB, oth = PY;           // Y is dead as an operand from here on (its own elements are in registers)
             for (int i = L - 2; i >= 0; --i) {
                 OcArgs hA{};
                 hA.sA = cur; hA.sB = PA; hA.d_smem = oth;
                 hA.ci = p.a[2 * i + 1].im; hA.ci_lo = p.a_lo[2 * i + 1].im; hA.cr = p.a[2 * i].re; hA.cr_lo = p.a_lo[2 * i].re;
-                if (LO && i <= 1) oc_gemm<N, EPI_HORNER, true, false>(hA, none, y);
-                else              oc_gemm<N, EPI_HORNER, false, false>(hA, none, y);
+                if (LO && i <= 1) oc_gemm<N, EPI_HORNER, true, false>(hA, none, y, y2);
+                else              oc_gemm<N, EPI_HORNER, false, false>(hA, none, y, y2);
                 __syncthreads();
                 const int t = cur; cur = oth; oth = t;
             }
@@ -313,7 +412,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                 OcArgs cA{};
                 cA.sA = cur; cA.sB = PY; cA.d_smem = oth; cA.c_smem = oth;
                 cA.beta = (k == 0) ? -2.0 : -1.0; cA.gamma = p.a[k]; cA.gamma_lo = p.a_lo[k];
-                oc_gemm<N, EPI_CLENSHAW, false, false>(cA, none, y);
+                oc_gemm<N, EPI_CLENSHAW, false, false>(cA, none, y, y2);
                 __syncthreads();
                 const int t = cur; cur = oth; oth = t;
             }
@@ -322,10 +421,18 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 
         // ---- running product in E-form:  F <- E + F + E F  (later step on the left); F lives in L2 ----
         const bool more = (j + 1 < hi);
-        const bool fuse_now = more && fuse && have_f;
-        if (more && fuse) {   // coefficients of the next step (read by the fused pass or by nobody)
-            for (int t = tid; t < p.nterms; t += OC_THREADS)
-                coef[t] = step_coefficient<IO>(p.terms[t], carr, p.pts, p.quad, p.magfac, j + 1);
+        // The next step's Y: either waiting in Yq (pre-assembled by an earlier pass: fetched by cp.async under the product
+        // below) or assembled now, together with up to OC_BLOCK - 1 further steps, by one pass over the table fused into
+        // the product below -- the table (320 KB at dim 64 with 4 controls) is the dominant L2 traffic of this kernel.
+        const bool fetch_now = more && have_f && ahead > 0;
+        const bool fuse_now = more && fuse && have_f && ahead == 0;
+        int nblock = 0;
+        if (fuse_now) {
+            nblock = (int)min((unsigned long long)OC_BLOCK, hi - (j + 1));
+            for (int i = tid; i < p.nterms * nblock; i += OC_THREADS) {
+                const int b = i / p.nterms, t = i % p.nterms;
+                coef[b * kMaxTerms + t] = step_coefficient<IO>(p.terms[t], carr, p.pts, p.quad, p.magfac, j + 1 + b);
+            }
         }
         if (!have_f) {
 #pragma unroll
@@ -350,20 +457,36 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                 asm volatile("cp.async.wait_group 0;\n" ::);
             }
             __syncthreads();
+            PB_T(5)
             OcArgs ch{};
             ch.sA = E; ch.sB = Fb; ch.c_smem = E; ch.c_smem2 = Fb; ch.d_glob = Fg[f_cur ^ 1];
             if (fuse_now) {
-                as.y_smem = Yn;
-                oc_gemm<N, EPI_CHAIN, false, true>(ch, as, y);
+                as.y_smem = Yn; as.nblock = nblock; as.y_glob = Yq;
+                oc_gemm<N, EPI_CHAIN, false, true>(ch, as, y, y2);
+                ahead = nblock - 1; yq_slot = 0;
             } else {
-                oc_gemm<N, EPI_CHAIN, false, false>(ch, none, y);
+                if (fetch_now) {   // Yq[yq_slot] -> Yn, in flight during the product
+                    const double2 *ysrc = Yq + (size_t)yq_slot * OC_NN;
+#pragma unroll
+                    for (int it = 0; it < OC_EPT; ++it) {
+                        const int e = tid + it * OC_THREADS;
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Yn + (e / OC_N) * OC_P + (e % OC_N));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(ysrc + e));
+                    }
+                    asm volatile("cp.async.commit_group;\n" ::);
+                    --ahead; ++yq_slot;
+                }
+                oc_gemm<N, EPI_CHAIN, false, false>(ch, none, y, y2);
+                if (fetch_now) asm volatile("cp.async.wait_group 0;\n" ::);
             }
             f_cur ^= 1;
             __syncthreads();
-            y_ready = fuse_now;
+            PB_T(6)
+            y_ready = fuse_now || fetch_now;
             iy = Yn / OC_BUF;
         }
     }
+    PB_T_PRINT
     double2 *out = partials + (size_t)blockIdx.x * OC_NN;
     for (int e = tid; e < OC_NN; e += OC_THREADS) out[e] = have_f ? Fg[f_cur][e] : make_double2(0.0, 0.0);
 }

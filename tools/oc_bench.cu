@@ -7,7 +7,8 @@ using namespace pb;
 constexpr int N = 64, P = 68, BUF = N * P;
 
 // WM x WN warp tile, (64/WM)*(64/WN) warps.  mode: 0 = main loop only, 1 = + epilogue store to smem, 2 = + barrier per product
-template <int WM, int WN, int UNROLL, int MODE>
+// EXTRA: doubles kept live across the main loop (register pressure like the real kernel's own-element arrays)
+template <int WM, int WN, int UNROLL, int MODE, int EXTRA = 0>
 __global__ void __launch_bounds__((64 / WM) * (64 / WN) * 32, 1) oc_variant(double2 *out, int reps) {
     extern __shared__ __align__(16) unsigned char raw[];
     double2 *b0 = reinterpret_cast<double2 *>(raw), *b1 = b0 + BUF, *b2 = b1 + BUF;
@@ -20,6 +21,9 @@ __global__ void __launch_bounds__((64 / WM) * (64 / WN) * 32, 1) oc_variant(doub
     __syncthreads();
     double2 *A = b0, *B = b1, *D = b2;
     double acc_keep = 0;
+    double extra[EXTRA > 0 ? EXTRA : 1];
+#pragma unroll
+    for (int i = 0; i < EXTRA; ++i) extra[i] = b0[(tid * 7 + i) % BUF].x;
     for (int rep = 0; rep < reps; ++rep) {
         double cre[MT][NTL][2], cim[MT][NTL][2];
 #pragma unroll
@@ -47,6 +51,10 @@ __global__ void __launch_bounds__((64 / WM) * (64 / WN) * 32, 1) oc_variant(doub
                 }
             }
         }
+        if (EXTRA > 0) {   // consume the live values in the epilogue, as the real kernel does
+#pragma unroll
+            for (int i = 0; i < EXTRA; ++i) cre[(i / 4) % MT][(i / 2) % NTL][i % 2] += extra[i] * 1e-9;
+        }
         if (MODE >= 1) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
@@ -68,9 +76,9 @@ __global__ void __launch_bounds__((64 / WM) * (64 / WN) * 32, 1) oc_variant(doub
     out[blockIdx.x * NT + tid] = b2[tid];
 }
 
-template <int WM, int WN, int UNROLL, int MODE>
+template <int WM, int WN, int UNROLL, int MODE, int EXTRA = 0>
 void run(const char *name, double2 *out) {
-    auto k = oc_variant<WM, WN, UNROLL, MODE>;
+    auto k = oc_variant<WM, WN, UNROLL, MODE, EXTRA>;
     const size_t smem = 3 * BUF * sizeof(double2);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int reps = 400, threads = (64 / WM) * (64 / WN) * 32;
@@ -97,5 +105,8 @@ int main() {
     run<32, 32, 2, 0>("4 warps 32x32 unroll2 loop only", out);
     run<32, 32, 2, 2>("4 warps 32x32 unroll2 + store + barrier", out);
     run<16, 32, 2, 2>("8 warps 16x32 unroll2 + store + barrier", out);
+    run<32, 16, 2, 2, 32>("8 warps 32x16 + store + barrier, 32 live doubles", out);
+    run<32, 16, 2, 2, 64>("8 warps 32x16 + store + barrier, 64 live doubles", out);
+    run<32, 16, 2, 2, 96>("8 warps 32x16 + store + barrier, 96 live doubles", out);
     return 0;
 }
