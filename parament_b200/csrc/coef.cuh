@@ -7,8 +7,10 @@
 
 namespace pb {
 
-__device__ __forceinline__ cplx ld_amp(const float2 *p) { const float2 v = __ldg(p); return cplx{(double)v.x, (double)v.y}; }
-__device__ __forceinline__ cplx ld_amp(const double2 *p) { const double2 v = __ldg(p); return cplx{v.x, v.y}; }
+// The amplitude stream is read exactly once: streaming (evict-first) loads keep it from displacing the L2-resident
+// scratch of the kernels that have one.
+__device__ __forceinline__ cplx ld_amp(const float2 *p) { const float2 v = __ldcs(p); return cplx{(double)v.x, (double)v.y}; }
+__device__ __forceinline__ cplx ld_amp(const double2 *p) { const double2 v = __ldcs(p); return cplx{v.x, v.y}; }
 
 // `c` points at the first control array of the pulse; arrays are `pts` apart.  j is the effective step.
 template <typename IO>

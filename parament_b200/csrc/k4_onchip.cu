@@ -16,10 +16,25 @@
 // Replaces, for these dimensions, the MMAX batched cuBLAS GEMMs + diagonal_add launches of parament.cpp:569-652 and the
 // reduction of parament.cpp:657-718; supersedes k4_chain_kernel (operands streamed from an L2 scratch) for npad == 64.
 #include <cstdio>
+#include <cstdint>
 #include "coef.cuh"
 #include "k4_gemm.hpp"
 
 namespace pb {
+
+// L2 evict-last policy for the per-CTA scratch (running product F, pre-assembled steps): it is rewritten every few steps and
+// must stay in L2; without the hint ~25 % of those writes were evicted to HBM (2.4 GB per 2e5 steps at dim 64).
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_keep(double2 *a, double2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;\n" ::"l"(a), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_keep(unsigned dst, const void *src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "l"(pol));
+}
 
 // Per-phase cycle counters (development aid, -DPB_PHASE_TIMING): block 0 prints its accumulated clock64() deltas.
 #ifdef PB_PHASE_TIMING
@@ -68,6 +83,7 @@ struct OcArgs {
     int sA, sB;                 // operands (offsets into oc_smem)
     int d_smem;                 // destination buffer (all but EPI_CHAIN)
     double2 *d_glob;            // destination in global memory (EPI_CHAIN)
+    uint64_t keep;              // L2 evict-last policy for d_glob
     int c_smem;                 // shared-memory addend, own elements (EPI_FIRST: W, EPI_CLENSHAW: B_{k+2}, EPI_CHAIN: E)
     int c_smem2;                // second shared-memory addend, own elements (EPI_CHAIN: F, which is also the B operand)
     cplx alpha, bw, by;         // EPI_FIRST (by also: coefficient of Y in EPI_PS3)
@@ -87,6 +103,7 @@ struct OcAssemble {
     int y_smem;                 // destination buffer of the NEXT step's Y (offset into oc_smem, pitch OC_P)
     int nblock;                 // steps assembled per pass of the table (1..OC_BLOCK): coef[b * kMaxTerms + t] for step j+1+b
     double2 *y_glob;            // row-major destinations of the later steps of the block: y_glob[(b - 1) * N*N + e], b >= 1
+    uint64_t keep;              // L2 evict-last policy for y_glob
 };
 
 template <int N>
@@ -162,7 +179,7 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
             // element e = tid + 256 kt of the next step's Y: consume the loads issued one k-tile ago, issue the next ones
             const int e = tid + kt * OC_THREADS;
             oc_smem[as.y_smem + (e / OC_N) * OC_P + (e % OC_N)] = oc_combine(as, 0, h0, h);
-            for (int b = 1; b < as.nblock; ++b) as.y_glob[(size_t)(b - 1) * (OC_N * OC_N) + e] = oc_combine(as, b, h0, h);
+            for (int b = 1; b < as.nblock; ++b) st_keep(as.y_glob + (size_t)(b - 1) * (OC_N * OC_N) + e, oc_combine(as, b, h0, h), as.keep);
             if (kt + 1 < OC_N / 4) oc_issue_loads<N>(as, e + OC_THREADS, h0, h);
         }
 #pragma unroll
@@ -246,8 +263,8 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                 vr[1] += e1.x + f1.x; vi[1] += e1.y + f1.y;
             }
             if (EPI == EPI_CHAIN) {
-                g.d_glob[r * OC_N + c] = make_double2(vr[0], vi[0]);
-                g.d_glob[r * OC_N + c + 1] = make_double2(vr[1], vi[1]);
+                st_keep(g.d_glob + r * OC_N + c, make_double2(vr[0], vi[0]), g.keep);
+                st_keep(g.d_glob + r * OC_N + c + 1, make_double2(vr[1], vi[1]), g.keep);
             } else {
                 oc_smem[g.d_smem + r * OC_P + c] = make_double2(vr[0], vi[0]);
                 oc_smem[g.d_smem + r * OC_P + c + 1] = make_double2(vr[1], vi[1]);
@@ -265,8 +282,8 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
     __shared__ cplx coef[OC_BLOCK * kMaxTerms];
 
     const int tid = threadIdx.x;
-    // scratch per CTA: F0, F1 and OC_BLOCK - 1 pre-assembled Y matrices (the host provides kSeriesSlots + 2 >= 5)
-    double2 *cta_scratch = scratch + (size_t)blockIdx.x * (kSeriesSlots + 2) * OC_NN;
+    // scratch per CTA: F0, F1 and OC_BLOCK - 1 pre-assembled Y matrices, packed (the host provides kSeriesSlots + 2 >= 5 per CTA)
+    double2 *cta_scratch = scratch + (size_t)blockIdx.x * (2 + OC_BLOCK - 1) * OC_NN;
     double2 *Fg[2] = {cta_scratch, cta_scratch + OC_NN};
     double2 *Yq = cta_scratch + 2 * OC_NN;
     int ahead = 0, yq_slot = 0;     // pre-assembled future steps waiting in Yq
@@ -279,8 +296,9 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
     const bool ps3 = (M == 8 || M >= 10);    // degrees at which blocks of three need fewer products than the Y^2 form
     constexpr bool LO = sizeof(IO) == sizeof(double2);   // sub-ulp remainders of the constants: complex128 contexts only
 
+    const uint64_t keep = l2_keep_policy();
     OcAssemble as{};
-    as.H = H; as.coef = coef; as.terms = p.terms; as.nterms = p.nterms; as.sigma = p.sigma;
+    as.H = H; as.coef = coef; as.terms = p.terms; as.nterms = p.nterms; as.sigma = p.sigma; as.keep = keep;
     const OcAssemble none{};
 
     int iy = 0;              // buffer index holding Y of the current step
@@ -438,7 +456,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 #pragma unroll
             for (int it = 0; it < OC_EPT; ++it) {
                 const int e = tid + it * OC_THREADS;
-                Fg[f_cur][e] = oc_smem[E + (e / OC_N) * OC_P + (e % OC_N)];
+                st_keep(Fg[f_cur] + e, oc_smem[E + (e / OC_N) * OC_P + (e % OC_N)], keep);
             }
             have_f = true;
             __syncthreads();
@@ -451,7 +469,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                 for (int it = 0; it < OC_EPT; ++it) {
                     const int e = tid + it * OC_THREADS;
                     const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Fb + (e / OC_N) * OC_P + (e % OC_N));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(fsrc + e));
+                    cp_async16_keep(dst, fsrc + e, keep);
                 }
                 asm volatile("cp.async.commit_group;\n" ::);
                 asm volatile("cp.async.wait_group 0;\n" ::);
@@ -459,7 +477,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             __syncthreads();
             PB_T(5)
             OcArgs ch{};
-            ch.sA = E; ch.sB = Fb; ch.c_smem = E; ch.c_smem2 = Fb; ch.d_glob = Fg[f_cur ^ 1];
+            ch.sA = E; ch.sB = Fb; ch.c_smem = E; ch.c_smem2 = Fb; ch.d_glob = Fg[f_cur ^ 1]; ch.keep = keep;
             if (fuse_now) {
                 as.y_smem = Yn; as.nblock = nblock; as.y_glob = Yq;
                 oc_gemm<N, EPI_CHAIN, false, true>(ch, as, y, y2);
@@ -471,7 +489,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                     for (int it = 0; it < OC_EPT; ++it) {
                         const int e = tid + it * OC_THREADS;
                         const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Yn + (e / OC_N) * OC_P + (e % OC_N));
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(ysrc + e));
+                        cp_async16_keep(dst, ysrc + e, keep);
                     }
                     asm volatile("cp.async.commit_group;\n" ::);
                     --ahead; ++yq_slot;
