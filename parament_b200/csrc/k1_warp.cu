@@ -15,10 +15,22 @@
 // control_expansion.cu / diagonal_add.cu for these dimensions.  The running product is kept transposed,
 // Q = (U_{hi-1} ... U_lo)^T = U_lo^T ... U_{hi-1}^T, see frag.cuh.
 #include "coef.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include "k1_warp.hpp"
 
 namespace pb {
+
+// Per-phase cycle counters (development aid, -DPB_PHASE_TIMING): warp 0 of block 0 prints its accumulated clock64() deltas.
+#ifdef PB_PHASE_TIMING
+#define K1_T_DECL long long pt_[6] = {0, 0, 0, 0, 0, 0}; long long pt_last_ = clock64();
+#define K1_T(i) { const long long pt_now_ = clock64(); pt_[i] += pt_now_ - pt_last_; pt_last_ = pt_now_; }
+#define K1_T_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("k1 phase cycles: assemble %lld  square %lld  horner %lld  chain %lld  other %lld  steps %llu\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], hi - lo);
+#else
+#define K1_T_DECL
+#define K1_T(i)
+#define K1_T_PRINT
+#endif
 
 constexpr int K1_WARPS = 4;   // warps per CTA of the chain kernel
 
@@ -72,7 +84,9 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
         const double2 *HA = Hfrag + lane;             // + (mat * 2 + 0) * NE * 32 + e * 32
         const int M = p.M;
 
+        K1_T_DECL
         for (unsigned long long j = lo; j < hi; ++j) {
+            K1_T(4)
             // ---- assemble X = H0 + sum_t c_t H_t in both register layouts, then Y = sigma X ----
             AccFrag<NT> Ya;
             BFrag<NT> Yb;
@@ -84,7 +98,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                 (&Yb.re[0][0])[e] = hb.x;    (&Yb.im[0][0])[e] = hb.y;
             }
             for (int t = 0; t < p.nterms; ++t) {
-                const cplx ct = step_coefficient<IO>(p.terms[t], c, p.pts, p.quad, p.magfac, j);
+                const cplx ct = step_coefficient<IO, false>(p.terms[t], c, p.pts, p.quad, p.magfac, j);
                 const double2 *Ht = HA + (size_t)p.terms[t].mat * 2 * NE * 32;
                 if (ct.im == 0.0) {   // real amplitude (warp-uniform): half the FP64-pipe work of the assembly
 #pragma unroll
@@ -117,6 +131,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                 }
             }
 
+            K1_T(0)
             AccFrag<NT> S0, S1;
             if (HORNER) {
                 // ---- Horner in W = Y^2:  E = sum_i (c_2i I + c_2i+1 Y) W^i, 1 + floor(M/2) products instead of M - 1.
@@ -139,6 +154,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                 cmma<NT>(Wt, Zt, Bt);                       // (Y^T)(Y^T)
                 BFrag<NT> Wb;
                 transpose_as_bfrag<NT>(Wb, Wt);             // BFrag(Y^2)
+                K1_T(1)
                 const int L = M >> 1;
                 horner_addend<NT, false>(S0, p.a[2 * L + 1].im, 0.0, Ya, p.a[2 * L].re, 0.0, lane);   // B_L (c_{M+1} = 0 for even M)
 #pragma unroll 1
@@ -167,13 +183,16 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                 cmma<NT>(S1, S0, Yb);                                 // + B_1 Y   -> E
             }
 
+            K1_T(2)
             // ---- running product  Q <- Q (I + E)^T = Q + Q E^T ----
             BFrag<NT> Et;
             transpose_as_bfrag<NT>(Et, S1);
             AccFrag<NT> Qn = Q;
             cmma<NT>(Qn, Q, Et);
             Q = Qn;
+            K1_T(3)
         }
+        K1_T_PRINT
     }
 
     if (reduce_in_cta) {

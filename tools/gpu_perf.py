@@ -61,3 +61,21 @@ def custom(n, A, pts, prec="fp64", reps=2):
             ctx.equiprop(0.2, *carr)
             st = ctx.stats()
         print(f"custom n={n} A={A} pts={pts} {prec} dev_ms={st['device_ms']:.3f} steps/s={pts/st['device_ms']*1e3:.3e} family={int(st['family'])} products={st['products_per_step']}", flush=True)
+
+def dev(name, reps=6, **kw):
+    """Device-resident timing (the library's own CUDA events around its launches), inputs rotated over > L2 of copies."""
+    import torch
+    w = make_workload(name, **kw)
+    carr = np.ascontiguousarray(w.carr.reshape(w.batch, w.amps, w.pts))
+    nbuf = min(12, max(2, int(np.ceil(160e6 / carr.nbytes)) + 1))
+    ins = [torch.from_numpy(np.roll(carr, 17 * i, axis=-1).copy()).cuda() for i in range(nbuf)]
+    out = torch.zeros(w.batch, w.dim, w.dim, dtype=torch.complex128 if w.precision == "fp64" else torch.complex64, device="cuda")
+    with pb.Parament(w.precision) as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=w.use_magnus, quadrature_mode=w.quadrature)
+        ms = []
+        for r in range(reps):
+            ctx.equiprop_device(w.dt, ins[r % nbuf].data_ptr(), w.pts, w.amps, out.data_ptr(), batch=w.batch)
+            torch.cuda.synchronize()
+            ms.append(ctx.stats()["device_ms"])
+        best, med = min(ms[1:]), float(np.median(ms[1:]))
+        print(f"dev {name} pts={w.pts} batch={w.batch} best_ms={best:.4f} median_ms={med:.4f} steps/s(median)={w.total_steps/med*1e3:.4e}", flush=True)
