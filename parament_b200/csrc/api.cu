@@ -99,7 +99,7 @@ Parament_ErrorCode create_ctx(Context **out, bool fp64) {
         delete c;
         return PARAMENT_STATUS_CUBLAS_INIT_FAILED;
     }
-    if (const char *e = getenv("PARAMENT_SERIES")) c->series_mode = (strcmp(e, "clenshaw") == 0) ? 1 : 0;
+    if (const char *e = getenv("PARAMENT_SERIES")) c->series_mode = (strcmp(e, "clenshaw") == 0) ? 1 : (strcmp(e, "horner") == 0 ? 2 : 0);
     c->lastError = PARAMENT_STATUS_SUCCESS;
     *out = c;
     return PARAMENT_STATUS_SUCCESS;
@@ -338,11 +338,61 @@ Parament_ErrorCode choose_degree(Context *c, double h, unsigned long long total_
     return PARAMENT_STATUS_SUCCESS;
 }
 
+// Degree-8 polynomial in three matrix products (J. Sastre, "Efficient evaluation of matrix polynomials", Linear Algebra
+// Appl. 539 (2018), formulas (34)-(35)).  With A = -i X the series is the REAL polynomial E = sum_m r_m A^m
+// (r_m = c_m / (-i)^m), and
+//     A2  = A A
+//     y02 = A2 (c4 A2 + c3 A)
+//     E   = (y02 + d2 A2 + d1 A)(y02 + e2 A2) + e0 y02 + r2 A2 + r1 A + r0 I
+//         = (y02 + d2 A2 + d1 A + e0 I)(y02 + e2 A2) + (r2 - e0 e2) A2 + r1 A + r0 I
+// reproduces r_3 .. r_8 when
+//     c4^2 = r8,  2 c3 c4 = r7,  c3^2 + (d2 + e2) c4 = r6,  (d2 + e2) c3 + d1 c4 = r5,
+//     d1 c3 + d2 e2 + e0 c4 = r4,  d1 e2 + e0 c3 = r3.
+// Solved in long double; p.a[0..8].re (+ a_lo) = c4, c3, d2, d1, e2, e0, r2 - e0 e2, r1, r0.  Returns false (keep the Horner
+// form) when the system has no real solution.  p.a must hold the monomial coefficients c_0 .. c_8 on entry.
+enum { S8_C4 = 0, S8_C3, S8_D2, S8_D1, S8_E2, S8_E0, S8_R2, S8_R1, S8_R0 };
+bool solve_degree8(SeriesParams &p) {
+    long double r[9];
+    for (int m = 0; m <= 8; ++m) {
+        const long double re = (long double)p.a[m].re + (long double)p.a_lo[m].re;
+        const long double im = (long double)p.a[m].im + (long double)p.a_lo[m].im;
+        switch (m & 3) {   // c_m / (-i)^m
+            case 0: r[m] = re; break;
+            case 1: r[m] = -im; break;
+            case 2: r[m] = -re; break;
+            default: r[m] = im; break;
+        }
+    }
+    if (!(r[8] > 0.0L) || r[7] == 0.0L) return false;
+    const long double c4 = sqrtl(r[8]), c3 = r[7] / (2.0L * c4);
+    const long double s = (r[6] - c3 * c3) / c4;            // d2 + e2
+    const long double d1 = (r[5] - s * c3) / c4;
+    // e2^2 - B e2 - C = 0
+    const long double B = s - c4 * d1 / c3, C = c4 * r[3] / c3 - (r[4] - d1 * c3);
+    const long double disc = B * B + 4.0L * C;
+    if (!(disc >= 0.0L)) return false;
+    const long double e2 = 0.5L * (B + sqrtl(disc));       // the root with the smaller |e0|
+    const long double d2 = s - e2, e0 = (r[3] - d1 * e2) / c3;
+    // the kernel folds e0 y02 into the left factor, (y02 + d2 A2 + d1 A + e0 I)(y02 + e2 A2), which adds e0 e2 A2
+    const long double v[9] = {c4, c3, d2, d1, e2, e0, r[2] - e0 * e2, r[1], r[0]};
+    for (int k = 0; k < 9; ++k) {
+        if (!std::isfinite((double)v[k])) return false;
+        p.a[k] = cplx{(double)v[k], 0.0};
+        p.a_lo[k] = cplx{(double)(v[k] - (long double)p.a[k].re), 0.0};
+    }
+    return true;
+}
+
 Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) {
     const double h = (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) ? 2.0 * s.dt : s.dt;   // parament.cpp:800-802
     int M_ref = 0, M_used = 0;
     Parament_ErrorCode ec = choose_degree(c, h, s.total_steps, M_ref, M_used);
     if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+    // complex64 contexts of the register-resident family evaluate degrees 6..8 as ONE degree-8 polynomial in three matrix
+    // products (below); the Y^2 Horner form needs four for degree 6 or 7.
+    const bool want_s8 = c->family == 1 && !c->fp64 && !c->MMAX_manual && c->series_mode == 0 && M_used >= 6 && M_used <= 8 &&
+                         c->Hnorm * h <= 1.0;
+    if (want_s8) M_used = 8;
     c->stat_M_ref = M_ref;
     c->stat_M_used = M_used;
     c->stat_horner = 0;
@@ -410,6 +460,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
         // Paterson-Stockmeyer blocks of four (3 + floor(M/4) products instead of 1 + floor(M/2)) where the kernels keep their
         // operands in global memory; the register- and shared-memory-resident kernels evaluate the Y^2 form.
         if (M_used >= 10 && (c->family == 3 || (c->family == 2 && !c->onchip))) p.horner = 2;
+        if (want_s8 && solve_degree8(p)) p.horner = 3;
     }
     c->stat_horner = p.horner;
     const int A = c->amps, Ain = (int)s.amps;
@@ -1004,6 +1055,7 @@ double Parament_lastStat(void *h, int key) {
             const int M = c->stat_M_used;
             if (M <= 0) return 0.0;
             if (c->stat_horner == 2) return 4.0 + (M >> 2);
+            if (c->stat_horner == 3) return 4.0;   // degree 8 in three products + the ordered product
             if (c->stat_horner == 1 && c->family == 2 && c->onchip && (M == 8 || M >= 10)) return 3.0 + M / 3;   // blocks of three
             return c->stat_horner ? 2.0 + (M >> 1) : (double)std::max(M, 1);
         }

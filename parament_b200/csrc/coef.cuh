@@ -10,29 +10,48 @@ namespace pb {
 // The amplitude stream is read once from HBM.  STREAM = true: evict-first loads keep it from displacing the L2-resident
 // scratch of the kernels that have one.  STREAM = false (register kernel, no scratch): read-only cached loads, so the 16
 // (8) points of a 128-byte line are served from L1 after the first touch -- measured 12 % faster on C2 than streaming.
-template <bool STREAM>
-__device__ __forceinline__ cplx ld_amp(const float2 *p) {
-    const float2 v = STREAM ? __ldcs(p) : __ldg(p);
-    return cplx{(double)v.x, (double)v.y};
-}
-template <bool STREAM>
-__device__ __forceinline__ cplx ld_amp(const double2 *p) {
-    const double2 v = STREAM ? __ldcs(p) : __ldg(p);
-    return cplx{v.x, v.y};
+
+// The up to four raw samples a term needs for effective step j, loaded without branches so that the loads can be issued
+// ahead of the arithmetic (the register kernel issues them one product early):
+//   PLAIN  NONE: c[j]            MIDPOINT: c[j], c[j+1]           SIMPSON: c[2j], c[2j+1], c[2j+2]
+//   MAG_DRIFT:   c[2j], c[2j+2]  MAG_PAIR: a[2j], a[2j+2], b[2j], b[2j+2]
+// Unused slots repeat an address that is read anyway.  `c` points at the first control array of the pulse; arrays are
+// `pts` apart.
+template <typename IO>
+struct RawAmp { IO v[4]; };
+
+template <typename IO, bool STREAM>
+__device__ __forceinline__ IO ld_raw(const IO *p) { return STREAM ? __ldcs(p) : __ldg(p); }
+
+template <typename IO, bool STREAM = true>
+__device__ __forceinline__ RawAmp<IO> load_raw(const Term &t, const IO *__restrict__ c, unsigned int pts, int quad,
+                                               unsigned long long j) {
+    const bool plain = t.type == TERM_PLAIN, pair = t.type == TERM_MAG_PAIR;
+    const IO *ca = c + (size_t)t.j * pts + ((plain && quad != QUAD_SIMPSON) ? j : 2 * j);
+    const IO *cb = pair ? c + (size_t)t.k * pts + 2 * j : ca;
+    const unsigned int o1 = plain ? (quad == QUAD_NONE ? 0u : 1u) : 2u;
+    const unsigned int o2 = plain ? (quad == QUAD_NONE ? 0u : (quad == QUAD_MIDPOINT ? 1u : 2u)) : 0u;
+    RawAmp<IO> r;
+    r.v[0] = ld_raw<IO, STREAM>(ca);
+    r.v[1] = ld_raw<IO, STREAM>(ca + o1);
+    r.v[2] = ld_raw<IO, STREAM>(cb + o2);
+    r.v[3] = ld_raw<IO, STREAM>(cb + (pair ? 2u : 0u));
+    return r;
 }
 
-// `c` points at the first control array of the pulse; arrays are `pts` apart.  j is the effective step.
-template <typename IO, bool STREAM = true>
-__device__ __forceinline__ cplx step_coefficient(const Term &t, const IO *__restrict__ c, unsigned int pts, int quad,
-                                                 double magfac, unsigned long long j) {
-    const IO *ca = c + (size_t)t.j * pts;
+__device__ __forceinline__ cplx widen(const float2 v) { return cplx{(double)v.x, (double)v.y}; }
+__device__ __forceinline__ cplx widen(const double2 v) { return cplx{v.x, v.y}; }
+
+// Effective coefficient of the term from its raw samples.
+template <typename IO>
+__device__ __forceinline__ cplx coef_from_raw(const Term &t, int quad, double magfac, const RawAmp<IO> &r) {
     if (t.type == TERM_PLAIN) {
-        if (quad == QUAD_NONE) return ld_amp<STREAM>(ca + j);
+        if (quad == QUAD_NONE) return widen(r.v[0]);
         if (quad == QUAD_MIDPOINT) {
-            const cplx u = ld_amp<STREAM>(ca + j), v = ld_amp<STREAM>(ca + j + 1);
+            const cplx u = widen(r.v[0]), v = widen(r.v[1]);
             return cplx{0.5 * (u.re + v.re), 0.5 * (u.im + v.im)};
         }
-        const cplx u = ld_amp<STREAM>(ca + 2 * j), v = ld_amp<STREAM>(ca + 2 * j + 1), w = ld_amp<STREAM>(ca + 2 * j + 2);
+        const cplx u = widen(r.v[0]), v = widen(r.v[1]), w = widen(r.v[2]);
         // s / 6 as s * (r_hi + r_lo): a single pre-rounded 1/6 would bias every step the same way (relative 5.6e-17,
         // coherent over 1e6 steps), a true division costs ~30 FP64-pipe instructions.  r_hi + r_lo = 1/6 to 1e-33.
         constexpr double r_hi = 0.16666666666666666, r_lo = 9.251858538542970e-18;
@@ -40,17 +59,22 @@ __device__ __forceinline__ cplx step_coefficient(const Term &t, const IO *__rest
         return cplx{fma(sr, r_hi, sr * r_lo), fma(si, r_hi, si * r_lo)};
     }
     if (t.type == TERM_MAG_DRIFT) {
-        const cplx u = ld_amp<STREAM>(ca + 2 * j), w = ld_amp<STREAM>(ca + 2 * j + 2);
+        const cplx u = widen(r.v[0]), w = widen(r.v[1]);
         const double dr = w.re - u.re, di = w.im - u.im;
         return cplx{-di * magfac, dr * magfac};   // (w - u) * i * h/12
     }
     // TERM_MAG_PAIR
-    const IO *cb = c + (size_t)t.k * pts;
-    const cplx a0 = ld_amp<STREAM>(ca + 2 * j), a2 = ld_amp<STREAM>(ca + 2 * j + 2);
-    const cplx b0 = ld_amp<STREAM>(cb + 2 * j), b2 = ld_amp<STREAM>(cb + 2 * j + 2);
+    const cplx a0 = widen(r.v[0]), a2 = widen(r.v[1]), b0 = widen(r.v[2]), b2 = widen(r.v[3]);
     const double vr = (a0.re * b2.re - a0.im * b2.im) - (a2.re * b0.re - a2.im * b0.im);
     const double vi = (a0.re * b2.im + a0.im * b2.re) - (a2.re * b0.im + a2.im * b0.re);
     return cplx{-vi * magfac, vr * magfac};
+}
+
+// j is the effective step.
+template <typename IO, bool STREAM = true>
+__device__ __forceinline__ cplx step_coefficient(const Term &t, const IO *__restrict__ c, unsigned int pts, int quad,
+                                                 double magfac, unsigned long long j) {
+    return coef_from_raw<IO>(t, quad, magfac, load_raw<IO, STREAM>(t, c, pts, quad, j));
 }
 
 }  // namespace pb

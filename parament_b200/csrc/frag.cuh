@@ -90,6 +90,32 @@ __device__ __forceinline__ void transpose_as_bfrag(BFrag<NT> &B, const AccFrag<N
         }
 }
 
+// BFrag of X from the AccFrag of the SAME matrix X (a change of layout, unlike transpose_as_bfrag) by warp shuffles.
+// Per 8x8 block, B[par](g, q) = X[2q + par][g] is accumulator element i = g & 1 of lane (g' = 2q + par, q' = g >> 1).
+// Two exchange rounds serve both parities: in round 1 the even-g lanes fetch par 0 and the odd-g lanes par 1, so every
+// source lane is asked for its element i = g' & 1 only; round 2 is the other way round.  Shuffles and selects run on the
+// crossbar / integer pipes, not on the FP64 pipe the DMMAs need; B.nim is left to the caller.
+template <int NT>
+__device__ __forceinline__ void acc_to_bfrag(BFrag<NT> &B, const AccFrag<NT> &X, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    const bool odd = g & 1;
+    const int src1 = 4 * (2 * q + (g & 1)) + (g >> 1);
+    const int src2 = 4 * (2 * q + 1 - (g & 1)) + (g >> 1);
+#pragma unroll
+    for (int kb = 0; kb < NT; ++kb)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const double r1 = __shfl_sync(0xffffffffu, odd ? X.re[kb][nt][1] : X.re[kb][nt][0], src1);
+            const double r2 = __shfl_sync(0xffffffffu, odd ? X.re[kb][nt][0] : X.re[kb][nt][1], src2);
+            const double i1 = __shfl_sync(0xffffffffu, odd ? X.im[kb][nt][1] : X.im[kb][nt][0], src1);
+            const double i2 = __shfl_sync(0xffffffffu, odd ? X.im[kb][nt][0] : X.im[kb][nt][1], src2);
+            B.re[2 * kb][nt] = odd ? r2 : r1;
+            B.re[2 * kb + 1][nt] = odd ? r1 : r2;
+            B.im[2 * kb][nt] = odd ? i2 : i1;
+            B.im[2 * kb + 1][nt] = odd ? i1 : i2;
+        }
+}
+
 template <int NT>
 __device__ __forceinline__ void set_identity(AccFrag<NT> &Q, int lane) {
     const int g = lane >> 2, q = lane & 3;

@@ -84,6 +84,45 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
         const double2 *HA = Hfrag + lane;             // + (mat * 2 + 0) * NE * 32 + e * 32
         const int M = p.M;
 
+        // Coefficients of the first KPRE terms are software-pipelined: their raw samples for step j + 1 are requested
+        // before the running-product DMMAs of step j and turned into coefficients after them, so the load -> convert ->
+        // quadrature latency chain (measured: 13 % of the step at dim 16, 22 % at dim 8 when exposed) runs under tensor work.
+        constexpr int KPRE = NT == 2 ? 2 : 0;   // (slower at dim <= 8, where six warps per scheduler hide the latency anyway)
+        constexpr bool BOTH = HORNER != 3 || NT == 1;   // assemble the right-operand layout too; else it is shuffled (faster at dim 16 only)
+        cplx ctn[KPRE > 0 ? KPRE : 1];
+#pragma unroll
+        for (int t = 0; t < KPRE; ++t) {
+            ctn[t] = cplx{0.0, 0.0};
+            if (t < p.nterms && lo < hi) ctn[t] = step_coefficient<IO, false>(p.terms[t], c, p.pts, p.quad, p.magfac, lo);
+        }
+        auto add_term = [&](AccFrag<NT> &Ya, BFrag<NT> &Yb, const cplx ct, const double2 *Ht) {
+            if (ct.im == 0.0) {   // real amplitude (warp-uniform): half the FP64-pipe work of the assembly
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const double2 ha = __ldg(Ht + e * 32);
+                    (&Ya.re[0][0][0])[e] = fma(ct.re, ha.x, (&Ya.re[0][0][0])[e]);
+                    (&Ya.im[0][0][0])[e] = fma(ct.re, ha.y, (&Ya.im[0][0][0])[e]);
+                    if (BOTH) {
+                        const double2 hb = __ldg(Ht + (NE + e) * 32);
+                        (&Yb.re[0][0])[e] = fma(ct.re, hb.x, (&Yb.re[0][0])[e]);
+                        (&Yb.im[0][0])[e] = fma(ct.re, hb.y, (&Yb.im[0][0])[e]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const double2 ha = __ldg(Ht + e * 32);
+                    (&Ya.re[0][0][0])[e] += ct.re * ha.x - ct.im * ha.y;
+                    (&Ya.im[0][0][0])[e] += ct.re * ha.y + ct.im * ha.x;
+                    if (BOTH) {
+                        const double2 hb = __ldg(Ht + (NE + e) * 32);
+                        (&Yb.re[0][0])[e] += ct.re * hb.x - ct.im * hb.y;
+                        (&Yb.im[0][0])[e] += ct.re * hb.y + ct.im * hb.x;
+                    }
+                }
+            }
+        };
+
         K1_T_DECL
         for (unsigned long long j = lo; j < hi; ++j) {
             K1_T(4)
@@ -93,35 +132,18 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
                 const double2 ha = __ldg(HA + e * 32);
-                const double2 hb = __ldg(HA + (NE + e) * 32);
                 (&Ya.re[0][0][0])[e] = ha.x; (&Ya.im[0][0][0])[e] = ha.y;
-                (&Yb.re[0][0])[e] = hb.x;    (&Yb.im[0][0])[e] = hb.y;
-            }
-            for (int t = 0; t < p.nterms; ++t) {
-                const cplx ct = step_coefficient<IO, false>(p.terms[t], c, p.pts, p.quad, p.magfac, j);
-                const double2 *Ht = HA + (size_t)p.terms[t].mat * 2 * NE * 32;
-                if (ct.im == 0.0) {   // real amplitude (warp-uniform): half the FP64-pipe work of the assembly
-#pragma unroll
-                    for (int e = 0; e < NE; ++e) {
-                        const double2 ha = __ldg(Ht + e * 32);
-                        const double2 hb = __ldg(Ht + (NE + e) * 32);
-                        (&Ya.re[0][0][0])[e] = fma(ct.re, ha.x, (&Ya.re[0][0][0])[e]);
-                        (&Ya.im[0][0][0])[e] = fma(ct.re, ha.y, (&Ya.im[0][0][0])[e]);
-                        (&Yb.re[0][0])[e] = fma(ct.re, hb.x, (&Yb.re[0][0])[e]);
-                        (&Yb.im[0][0])[e] = fma(ct.re, hb.y, (&Yb.im[0][0])[e]);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < NE; ++e) {
-                        const double2 ha = __ldg(Ht + e * 32);
-                        const double2 hb = __ldg(Ht + (NE + e) * 32);
-                        (&Ya.re[0][0][0])[e] += ct.re * ha.x - ct.im * ha.y;
-                        (&Ya.im[0][0][0])[e] += ct.re * ha.y + ct.im * ha.x;
-                        (&Yb.re[0][0])[e] += ct.re * hb.x - ct.im * hb.y;
-                        (&Yb.im[0][0])[e] += ct.re * hb.y + ct.im * hb.x;
-                    }
+                if (BOTH) {
+                    const double2 hb = __ldg(HA + (NE + e) * 32);
+                    (&Yb.re[0][0])[e] = hb.x;    (&Yb.im[0][0])[e] = hb.y;
                 }
             }
+#pragma unroll
+            for (int t = 0; t < KPRE; ++t)
+                if (t < p.nterms) add_term(Ya, Yb, ctn[t], HA + (size_t)p.terms[t].mat * 2 * NE * 32);
+            for (int t = KPRE; t < p.nterms; ++t)
+                add_term(Ya, Yb, step_coefficient<IO, false>(p.terms[t], c, p.pts, p.quad, p.magfac, j),
+                         HA + (size_t)p.terms[t].mat * 2 * NE * 32);
             if (!HORNER) {   // Horner form: sigma is folded into the monomial coefficients on the host, Y == X
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
@@ -133,7 +155,63 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
 
             K1_T(0)
             AccFrag<NT> S0, S1;
-            if (HORNER) {
+            if (HORNER == 3) {
+                // ---- degree 8 in three products (api.cu solve_degree8).  With A = -i X:  W = X^2 = -A^2,
+                //   y02 = W (c4 W + i c3 X),   E = (y02 - d2 W - i d1 X + e0 I)(y02 - e2 W) - r2' W - i r1 X + r0 I
+                // (the e0 y02 term of the published form is folded into the left factor: e0 y02 = e0 (y02 - e2 W) + e0 e2 W,
+                // r2' = r2 - e0 e2 from the host).  W and y02 are needed on both sides of a product: their right-operand
+                // layout comes from warp shuffles.  The addend only needs X and W, so it is formed under the y02 product.
+                const double c4 = p.a[0].re, c3 = p.a[1].re, d2 = p.a[2].re, d1 = p.a[3].re, e2 = p.a[4].re, e0 = p.a[5].re;
+                const double r2 = p.a[6].re, r1 = p.a[7].re, r0 = p.a[8].re;
+                const int g = lane >> 2, q = lane & 3;
+                if (!BOTH) acc_to_bfrag<NT>(Yb, Ya, lane);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) (&Yb.nim[0][0])[e] = neg((&Yb.im[0][0])[e]);
+                AccFrag<NT> Wa;
+                set_zero<NT>(Wa);
+                cmma<NT>(Wa, Ya, Yb);                       // W
+                BFrag<NT> Wb;
+                acc_to_bfrag<NT>(Wb, Wa, lane);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    (&Wb.nim[0][0])[e] = neg((&Wb.im[0][0])[e]);
+                    (&S0.re[0][0][0])[e] = fma(-c3, (&Ya.im[0][0][0])[e], c4 * (&Wa.re[0][0][0])[e]);
+                    (&S0.im[0][0][0])[e] = fma(c3, (&Ya.re[0][0][0])[e], c4 * (&Wa.im[0][0][0])[e]);
+                }
+                K1_T(1)
+                AccFrag<NT> Y2;
+                set_zero<NT>(Y2);
+                cmma<NT>(Y2, S0, Wb);                       // y02
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const bool diag = (mt == nt && g == 2 * q + i);
+                            S1.re[mt][nt][i] = fma(-r2, Wa.re[mt][nt][i], fma(r1, Ya.im[mt][nt][i], diag ? r0 : 0.0));
+                            S1.im[mt][nt][i] = fma(-r2, Wa.im[mt][nt][i], -r1 * Ya.re[mt][nt][i]);
+                        }
+                BFrag<NT> Rb;
+                acc_to_bfrag<NT>(Rb, Y2, lane);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    (&Rb.re[0][0])[e] = fma(-e2, (&Wb.re[0][0])[e], (&Rb.re[0][0])[e]);
+                    (&Rb.im[0][0])[e] = fma(-e2, (&Wb.im[0][0])[e], (&Rb.im[0][0])[e]);
+                    (&Rb.nim[0][0])[e] = neg((&Rb.im[0][0])[e]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const bool diag = (mt == nt && g == 2 * q + i);
+                            Y2.re[mt][nt][i] = fma(-d2, Wa.re[mt][nt][i], fma(d1, Ya.im[mt][nt][i], Y2.re[mt][nt][i])) + (diag ? e0 : 0.0);
+                            Y2.im[mt][nt][i] = fma(-d2, Wa.im[mt][nt][i], fma(-d1, Ya.re[mt][nt][i], Y2.im[mt][nt][i]));
+                        }
+                cmma<NT>(S1, Y2, Rb);                       // E
+            } else if (HORNER) {
                 // ---- Horner in W = Y^2:  E = sum_i (c_2i I + c_2i+1 Y) W^i, 1 + floor(M/2) products instead of M - 1.
                 // W is needed as a RIGHT operand.  (Y^T)^2 = (Y^2)^T is formed in accumulator layout from register
                 // relabelings only -- AccFrag(Y^T) is Yb, BFrag(Y^T) is Ya (frag.cuh) -- and its transpose read as BFrag.
@@ -184,12 +262,20 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
             }
 
             K1_T(2)
-            // ---- running product  Q <- Q (I + E)^T = Q + Q E^T ----
+            // ---- running product  Q <- Q (I + E)^T = Q + Q E^T, with the next step's raw samples in flight ----
+            const unsigned long long jn = j + 1 < hi ? j + 1 : j;
+            RawAmp<IO> raw[KPRE > 0 ? KPRE : 1];
+#pragma unroll
+            for (int t = 0; t < KPRE; ++t)
+                if (t < p.nterms) raw[t] = load_raw<IO, false>(p.terms[t], c, p.pts, p.quad, jn);
             BFrag<NT> Et;
             transpose_as_bfrag<NT>(Et, S1);
             AccFrag<NT> Qn = Q;
             cmma<NT>(Qn, Q, Et);
             Q = Qn;
+#pragma unroll
+            for (int t = 0; t < KPRE; ++t)
+                if (t < p.nterms) ctn[t] = coef_from_raw<IO>(p.terms[t], p.quad, p.magfac, raw[t]);
             K1_T(3)
         }
         K1_T_PRINT
@@ -294,6 +380,12 @@ template <int NT, typename IO>
 static cudaError_t launch_chain_t(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                   unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
                                   unsigned long long step_hi, cudaStream_t stream) {
+    if (p.horner == 3) {   // complex64 contexts only (api.cu build_series)
+        if constexpr (sizeof(IO) == sizeof(float2))
+            return launch_chain_tt<NT, IO, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
+        else
+            return cudaErrorInvalidValue;
+    }
     return p.horner ? launch_chain_tt<NT, IO, 1>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream)
                     : launch_chain_tt<NT, IO, 0>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
 }

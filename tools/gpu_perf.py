@@ -19,7 +19,7 @@ def sweep(name, sizes, reps=3, **kw):
                 print(f"{name} pts={pts:8d} batch={w.batch} rep={r} dev_ms={st['device_ms']:9.3f} wall_ms={wall:9.3f} steps/s(dev)={steps/st['device_ms']*1e3:.3e} "
                       f"M={int(st['degree_used'])}/{int(st['degree_reference'])} launches={int(st['launches'])}", flush=True)
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     sweep("C2", [10001, 30001, 100001, 300001, 1000001])
     sweep("C5", [1000], batch=10000)
     sweep("C1", [10000])
@@ -43,7 +43,7 @@ def e2e(name, reps=5, pinned=False, **kw):
             best = min(best, time.time() - t0)
         print(f"e2e {name} pinned={pinned} best wall_ms={best*1e3:.3f} steps/s={w.total_steps/best:.3e} kernel-region ms={ctx.stat(0):.3f} launches={int(ctx.stat(1))}", flush=True)
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     for pin in (False, True):
         e2e("C2", pinned=pin)
         e2e("C5", pinned=pin)
@@ -79,3 +79,7 @@ def dev(name, reps=6, **kw):
             ms.append(ctx.stats()["device_ms"])
         best, med = min(ms[1:]), float(np.median(ms[1:]))
         print(f"dev {name} pts={w.pts} batch={w.batch} best_ms={best:.4f} median_ms={med:.4f} steps/s(median)={w.total_steps/med*1e3:.4e}", flush=True)
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dev":
+    for name in sys.argv[2:] or ["C2", "C5", "C1"]:
+        dev(name)
