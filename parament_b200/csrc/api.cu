@@ -699,9 +699,12 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
     };
     if (s.batch > 1) {
         const unsigned int bg = (s.batch + G - 1) / G;
-        const K1Plan big = plan_k1(c->npad, bg, s.nsteps, c->num_sms, horner);
-        if (!ensure_dev(c->d_partials, (big.partial_elems + k3_mid_elems(c->npad, bg, big.partials_per_pulse)) * sizeof(double2)))
-            return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+        // scratch for the larger of the two group sizes that occur (all groups hold bg pulses, the last one the remainder)
+        const unsigned int last = s.batch - (unsigned int)((s.batch - 1) / bg) * bg;
+        const K1Plan pa = plan_k1(c->npad, bg, s.nsteps, c->num_sms, horner), pl = plan_k1(c->npad, last, s.nsteps, c->num_sms, horner);
+        const size_t part_cap = std::max(pa.partial_elems, pl.partial_elems);
+        const size_t mid_cap = std::max(k3_mid_elems(c->npad, bg, pa.partials_per_pulse), k3_mid_elems(c->npad, last, pl.partials_per_pulse));
+        if (!ensure_dev(c->d_partials, (part_cap + mid_cap) * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
         if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, c->stream))) return PARAMENT_STATUS_CUBLAS_FAILED;
         int g = 0;
         for (unsigned int b0 = 0; b0 < s.batch; b0 += bg, ++g) {
@@ -713,7 +716,7 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
             PB_LAUNCH(launch_k1_chain(c->npad, c->fp64, p, dcarr + (size_t)b0 * s.amps * seg, (const double2 *)c->d_H.ptr,
                                       (double2 *)c->d_partials.ptr, b1 - b0, plan, 0, s.nsteps, c->stream));
             PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, plan.partials_per_pulse, n,
-                                       (T *)out_dev + (size_t)b0 * n * n, b1 - b0, (double2 *)c->d_partials.ptr + big.partial_elems, c->stream));
+                                       (T *)out_dev + (size_t)b0 * n * n, b1 - b0, (double2 *)c->d_partials.ptr + part_cap, c->stream));
             c->stat_launches += k3_launches(plan.partials_per_pulse) - 1;
         }
     } else {

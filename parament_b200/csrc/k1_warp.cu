@@ -399,9 +399,19 @@ K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_
     plan.ctas_per_sm = ctas_per_sm;
     const unsigned long long warps_total = (unsigned long long)num_sms * ctas_per_sm * K1_WARPS;
     if (batch >= warps_total / 2 || nsteps < 2ull * K1_WARPS) {
-        plan.chunks_per_pulse = 1;                 // a warp owns a whole pulse
+        // A warp owns a whole pulse -- or 1/k of it where that evens out the waves: all warps take equally long, so
+        // batch / warps_total = 2.8 costs three full waves with k = 1 but 17/6 = 2.83 with k = 6.
+        unsigned int best_k = 1;
+        double best = 1e300;
+        for (unsigned int k = 1; k <= 8; ++k) {
+            if (k > 1 && nsteps / k < 64) break;
+            const unsigned long long waves = ((unsigned long long)batch * k + warps_total - 1) / warps_total;
+            const double cost = (double)waves / k * (1.0 + 0.004 * (k - 1));   // identity-start product + reduce per chunk
+            if (cost < best * 0.99) { best = cost; best_k = k; }
+        }
+        plan.chunks_per_pulse = best_k;
         plan.reduce_in_cta = 0;
-        plan.partials_per_pulse = 1;
+        plan.partials_per_pulse = best_k;
     } else {
         unsigned long long ctas_per_pulse = (warps_total / K1_WARPS + batch - 1) / batch;
         // keep at least ~8 steps per warp so the identity-start product stays a small fraction
