@@ -725,7 +725,10 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
         K1Plan plans[8];
         size_t off[9];
         off[0] = 0;
-        for (int g = 0; g <= G; ++g) bound[g] = s.nsteps * g / G;
+        // a short first group (a quarter share): its copy is the only one no kernel hides
+        bound[0] = 0;
+        bound[1] = s.nsteps / (4ull * G);
+        for (int g = 2; g <= G; ++g) bound[g] = bound[1] + (s.nsteps - bound[1]) * (unsigned long long)(g - 1) / (G - 1);
         for (int g = 0; g < G; ++g) {
             plans[g] = plan_k1(c->npad, 1, bound[g + 1] - bound[g], c->num_sms, horner);
             off[g + 1] = off[g] + plans[g].partials_per_pulse;
