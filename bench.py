@@ -268,7 +268,8 @@ def run_ours(args):
                        "x_Hnorm_h": w.meta["x"], "degree_reference": M_ref, "degree_used": M_used,
                        "series_evaluation": {0: "Clenshaw recurrence", 1: "Horner in Y^2 (same polynomial)",
                                              2: "Paterson-Stockmeyer blocks of four (same polynomial)",
-                                             3: "degree 8 in three matrix products (Sastre 2018)"}.get(horner, str(horner)),
+                                             3: "degree 8 in three matrix products (Sastre 2018)",
+                                             4: "degree 12 in four matrix products (Sastre 2018)"}.get(horner, str(horner)),
                        "matrix_products_per_step": products, "kernel_family": family,
                        "l2": f"inputs rotate over {nbuf} device copies ({nbuf * in_bytes / 1e6:.0f} MB > 126 MB L2)" if flush is None
                              else "L2 flushed by a 256 MiB write between iterations",

@@ -18,6 +18,7 @@
 #include "context.hpp"
 #include "k1_warp.hpp"
 #include "k4_gemm.hpp"
+#include "poly_solve.hpp"
 #include "series.hpp"
 
 using namespace pb;
@@ -338,48 +339,66 @@ Parament_ErrorCode choose_degree(Context *c, double h, unsigned long long total_
     return PARAMENT_STATUS_SUCCESS;
 }
 
-// Degree-8 polynomial in three matrix products (J. Sastre, "Efficient evaluation of matrix polynomials", Linear Algebra
-// Appl. 539 (2018), formulas (34)-(35)).  With A = -i X the series is the REAL polynomial E = sum_m r_m A^m
-// (r_m = c_m / (-i)^m), and
-//     A2  = A A
-//     y02 = A2 (c4 A2 + c3 A)
-//     E   = (y02 + d2 A2 + d1 A)(y02 + e2 A2) + e0 y02 + r2 A2 + r1 A + r0 I
-//         = (y02 + d2 A2 + d1 A + e0 I)(y02 + e2 A2) + (r2 - e0 e2) A2 + r1 A + r0 I
-// reproduces r_3 .. r_8 when
-//     c4^2 = r8,  2 c3 c4 = r7,  c3^2 + (d2 + e2) c4 = r6,  (d2 + e2) c3 + d1 c4 = r5,
-//     d1 c3 + d2 e2 + e0 c4 = r4,  d1 e2 + e0 c3 = r3.
-// Solved in long double; p.a[0..8].re (+ a_lo) = c4, c3, d2, d1, e2, e0, r2 - e0 e2, r1, r0.  Returns false (keep the Horner
-// form) when the system has no real solution.  p.a must hold the monomial coefficients c_0 .. c_8 on entry.
-enum { S8_C4 = 0, S8_C3, S8_D2, S8_D1, S8_E2, S8_E0, S8_R2, S8_R1, S8_R0 };
-bool solve_degree8(SeriesParams &p) {
-    long double r[9];
-    for (int m = 0; m <= 8; ++m) {
+// r_m = c_m / (-i)^m: the series as a REAL polynomial in A = -i X (p.a holds the monomial coefficients c_m on entry).
+static void real_coefficients(const SeriesParams &p, int deg, long double *r) {
+    for (int m = 0; m <= deg; ++m) {
         const long double re = (long double)p.a[m].re + (long double)p.a_lo[m].re;
         const long double im = (long double)p.a[m].im + (long double)p.a_lo[m].im;
-        switch (m & 3) {   // c_m / (-i)^m
+        switch (m & 3) {
             case 0: r[m] = re; break;
             case 1: r[m] = -im; break;
             case 2: r[m] = -re; break;
             default: r[m] = im; break;
         }
     }
-    if (!(r[8] > 0.0L) || r[7] == 0.0L) return false;
-    const long double c4 = sqrtl(r[8]), c3 = r[7] / (2.0L * c4);
-    const long double s = (r[6] - c3 * c3) / c4;            // d2 + e2
-    const long double d1 = (r[5] - s * c3) / c4;
-    // e2^2 - B e2 - C = 0
-    const long double B = s - c4 * d1 / c3, C = c4 * r[3] / c3 - (r[4] - d1 * c3);
-    const long double disc = B * B + 4.0L * C;
-    if (!(disc >= 0.0L)) return false;
-    const long double e2 = 0.5L * (B + sqrtl(disc));       // the root with the smaller |e0|
-    const long double d2 = s - e2, e0 = (r[3] - d1 * e2) / c3;
-    // the kernel folds e0 y02 into the left factor, (y02 + d2 A2 + d1 A + e0 I)(y02 + e2 A2), which adds e0 e2 A2
-    const long double v[9] = {c4, c3, d2, d1, e2, e0, r[2] - e0 * e2, r[1], r[0]};
-    for (int k = 0; k < 9; ++k) {
-        if (!std::isfinite((double)v[k])) return false;
-        p.a[k] = cplx{(double)v[k], 0.0};
-        p.a_lo[k] = cplx{(double)(v[k] - (long double)p.a[k].re), 0.0};
-    }
+}
+
+static void store_split(SeriesParams &p, int k, long double v) {
+    p.a[k] = cplx{(double)v, 0.0};
+    p.a_lo[k] = cplx{(double)(v - (long double)p.a[k].re), 0.0};
+}
+
+// Degree 8 in three matrix products (poly_solve.hpp).  The kernel (k1_warp.cu) folds e0 y02 into the left factor,
+//     E = (y02 + d2 A2 + d1 A + e0 I)(y02 + e2 A2) + (r2 - e0 e2) A2 + r1 A + r0 I,
+// and gets p.a[0..8].re (+ a_lo) = c4, c3, d2, d1, e2, e0, r2 - e0 e2, r1, r0.  Returns false (keep the Horner form)
+// when the system has no real solution.
+bool solve_degree8(SeriesParams &p) {
+    long double r[9], v[6];
+    real_coefficients(p, 8, r);
+    if (!solve_degree8_real(r, v)) return false;
+    const long double e2 = (long double)(double)v[4], e0 = (long double)(double)v[5];   // as the kernel will see them
+    for (int k = 0; k < 6; ++k) store_split(p, k, v[k]);
+    store_split(p, 6, r[2] - e0 * e2);
+    store_split(p, 7, r[1]);
+    store_split(p, 8, r[0]);
+    return true;
+}
+
+// Degree 12 in four matrix products (poly_solve.hpp), for the shared-memory and batched families.  In terms of
+// Y = X, W = X^2, V = X^3 (A = -i X, A2 = -W, A3 = i V) the kernels evaluate
+//     T' = tV V + i tW W + tY Y                      (= i (c3 A3 + c2 A2 + c1 A))
+//     y0 = T' V
+//     L  = y0 + i lV V + lW W + i lY Y + lI I        (= y0 + d3 A3 + d2 A2 + d1 A + f I)
+//     R  = y0 + i rV V + rW W                        (= y0 + e3 A3 + e2 A2)
+//     E  = L R + i sV V + sW W + i sY Y + sI I       (f y0 is folded into L: f y0 = f R - f e3 A3 - f e2 A2)
+// p.a[0..12].re = tV tW tY lV lW lY lI rV rW sV sW sY sI.  The low-order constants sV..sI are derived from the parameters AS
+// ROUNDED to double, so that the polynomial the kernel evaluates has the exact r_0 .. r_3; their sub-ulp remainders go to
+// p.a_lo (DESIGN.md "Numerics").
+enum { S12_TV = 0, S12_TW, S12_TY, S12_LV, S12_LW, S12_LY, S12_LI, S12_RV, S12_RW, S12_SV, S12_SW, S12_SY, S12_SI };
+bool solve_degree12(SeriesParams &p) {
+    long double r[13], v[9];
+    real_coefficients(p, 12, r);
+    if (!solve_degree12_real(r, v)) return false;
+    long double q[9];
+    for (int k = 0; k < 9; ++k) q[k] = (long double)(double)v[k];
+    const long double c1 = q[0], c2 = q[1], c3 = q[2], d1 = q[3], d2 = q[4], d3 = q[5], e2 = q[6], e3 = q[7], f = q[8];
+    store_split(p, S12_TV, -c3); store_split(p, S12_TW, -c2); store_split(p, S12_TY, c1);
+    store_split(p, S12_LV, d3);  store_split(p, S12_LW, -d2); store_split(p, S12_LY, -d1); store_split(p, S12_LI, f);
+    store_split(p, S12_RV, e3);  store_split(p, S12_RW, -e2);
+    store_split(p, S12_SV, (r[3] - d1 * e2) - f * e3);
+    store_split(p, S12_SW, -(r[2] - f * e2));
+    store_split(p, S12_SY, -r[1]);
+    store_split(p, S12_SI, r[0]);
     return true;
 }
 
@@ -393,6 +412,10 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     const bool want_s8 = c->family == 1 && !c->fp64 && !c->MMAX_manual && c->series_mode == 0 && M_used >= 6 && M_used <= 8 &&
                          c->Hnorm * h <= 1.0;
     if (want_s8) M_used = 8;
+    // shared-memory and batched families: degrees 9..12 as ONE degree-12 polynomial in four matrix products
+    const bool want_s12 = c->family != 1 && !c->MMAX_manual && c->series_mode == 0 && M_used >= 9 && M_used <= 12 &&
+                          c->Hnorm * h <= 1.0;
+    if (want_s12) M_used = 12;
     c->stat_M_ref = M_ref;
     c->stat_M_used = M_used;
     c->stat_horner = 0;
@@ -461,6 +484,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
         // operands in global memory; the register- and shared-memory-resident kernels evaluate the Y^2 form.
         if (M_used >= 10 && (c->family == 3 || (c->family == 2 && !c->onchip))) p.horner = 2;
         if (want_s8 && solve_degree8(p)) p.horner = 3;
+        if (want_s12 && solve_degree12(p)) p.horner = 4;
     }
     c->stat_horner = p.horner;
     const int A = c->amps, Ain = (int)s.amps;
@@ -603,10 +627,11 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
                 GemmArgs g{};
                 g.A = slots[op.A]; g.B = slots[op.B]; g.D = slots[op.D];
                 g.Dprod = op.Dprod >= 0 ? slots[op.Dprod] : nullptr;
-                g.strideA = g.strideB = g.strideD = g.strideDprod = (long long)nn;
+                g.Dalt = op.Dalt >= 0 ? slots[op.Dalt] : nullptr;
+                g.strideA = g.strideB = g.strideD = g.strideDprod = g.strideDalt = (long long)nn;
                 for (int j = 0; j < kMaxAddends; ++j) {
                     g.C[j] = op.C[j] >= 0 ? slots[op.C[j]] : nullptr; g.strideC[j] = (long long)nn;
-                    g.beta[j] = op.beta[j]; g.beta_lo[j] = op.beta_lo[j];
+                    g.beta[j] = op.beta[j]; g.beta_lo[j] = op.beta_lo[j]; g.beta_alt[j] = op.beta_alt[j];
                 }
                 g.alpha = op.alpha; g.scaled = op.scaled; g.gamma = op.gamma; g.gamma_lo = op.gamma_lo;
                 g.C2 = nullptr; g.beta2 = 0.0; g.n = np; g.batch = Sc;
@@ -1062,6 +1087,7 @@ double Parament_lastStat(void *h, int key) {
             if (M <= 0) return 0.0;
             if (c->stat_horner == 2) return 4.0 + (M >> 2);
             if (c->stat_horner == 3) return 4.0;   // degree 8 in three products + the ordered product
+            if (c->stat_horner == 4) return 5.0;   // degree 12 in four products + the ordered product
             if (c->stat_horner == 1 && c->family == 2 && c->onchip && (M == 8 || M >= 10)) return 3.0 + M / 3;   // blocks of three
             return c->stat_horner ? 2.0 + (M >> 1) : (double)std::max(M, 1);
         }

@@ -42,9 +42,9 @@ struct TileArgs {
     const double2 *A, *B;             // matrix bases (n x n row-major)
     const double2 *C[kMaxAddends];
     const double2 *C2;
-    double2 *D, *Dprod;
+    double2 *D, *Dprod, *Dalt;
     cplx alpha; int scaled;
-    cplx beta[kMaxAddends], beta_lo[kMaxAddends];
+    cplx beta[kMaxAddends], beta_lo[kMaxAddends], beta_alt[kMaxAddends];
     double beta2;
     cplx gamma, gamma_lo;
     int n;
@@ -179,6 +179,20 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
                 z[j][0] = z[j][1] = make_double2(0.0, 0.0);
                 if (has[j]) { z[j][0] = g.C[j][off]; z[j][1] = g.C[j][off + 1]; }
             }
+            if (g.Dalt) {   // second combination of the same addends (unscaled product)
+                double ar[2] = {vr[0], vr[1]}, ai[2] = {vi[0], vi[1]};
+#pragma unroll
+                for (int j = kMaxAddends - 1; j >= 0; --j)
+                    if (has[j]) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            ar[i] = fma(g.beta_alt[j].re, z[j][i].x, fma(-g.beta_alt[j].im, z[j][i].y, ar[i]));
+                            ai[i] = fma(g.beta_alt[j].re, z[j][i].y, fma(g.beta_alt[j].im, z[j][i].x, ai[i]));
+                        }
+                    }
+                g.Dalt[off] = make_double2(ar[0], ai[0]);
+                g.Dalt[off + 1] = make_double2(ar[1], ai[1]);
+            }
             double2 x0 = make_double2(0.0, 0.0), x1 = x0;
             if (g.C2) { x0 = g.C2[off]; x1 = g.C2[off + 1]; }
             epilogue_pair(vr, vi, z, has, g.scaled, g.alpha, g.beta, g.beta_lo, g.gamma, g.gamma_lo, r == c, r == c + 1);
@@ -206,6 +220,9 @@ k4_zgemm_kernel(const GemmArgs g) {
     t.C2 = g.C2 ? g.C2 + b * g.strideC2 : nullptr;
     t.D = g.D + b * g.strideD;
     t.Dprod = g.Dprod ? g.Dprod + b * g.strideDprod : nullptr;
+    t.Dalt = g.Dalt ? g.Dalt + b * g.strideDalt : nullptr;
+#pragma unroll
+    for (int j = 0; j < kMaxAddends; ++j) t.beta_alt[j] = g.beta_alt[j];
     t.alpha = g.alpha; t.scaled = g.scaled;
     t.beta2 = g.beta2; t.gamma = g.gamma; t.gamma_lo = g.gamma_lo;
     t.n = g.n;
@@ -266,6 +283,9 @@ k4_chain_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__rest
             t.C2 = nullptr;
             t.D = slot + (size_t)op.D * NN;
             t.Dprod = op.Dprod >= 0 ? slot + (size_t)op.Dprod * NN : nullptr;
+            t.Dalt = op.Dalt >= 0 ? slot + (size_t)op.Dalt * NN : nullptr;
+#pragma unroll
+            for (int a = 0; a < kMaxAddends; ++a) t.beta_alt[a] = op.beta_alt[a];
             t.alpha = op.alpha; t.scaled = op.scaled;
             t.beta2 = 0.0; t.gamma = op.gamma; t.gamma_lo = op.gamma_lo;
             t.n = BM;
@@ -375,6 +395,7 @@ __global__ void k4_eform_kernel(const IO *__restrict__ P, int n, int npad, int c
 //                  R <- R W + c_{2i+1} Y + c_{2i} I                                   1 + floor(M/2) products
 //   p.horner == 2  Paterson-Stockmeyer with V = Y^4: Y^2, Y^3, Y^4, then
 //                  R <- R V + c_{4i+3} Y^3 + c_{4i+2} Y^2 + c_{4i+1} Y + c_{4i} I      3 + floor(M/4) products
+//   p.horner == 4  degree 12 as (y0 + ...)(y0 + ...) + ... with y0 = Y^3 (...)            4 products (api.cu solve_degree12)
 SeriesProgram build_program(const SeriesParams &p) {
     SeriesProgram g{};
     const int M = p.M;
@@ -382,14 +403,45 @@ SeriesProgram build_program(const SeriesParams &p) {
     auto push = [&](int A, int B, int D) -> SeriesOp & {
         SeriesOp &o = g.ops[g.nops++];
         o = SeriesOp{};
-        o.A = A; o.B = B; o.D = D; o.Dprod = -1; o.scaled = 0; o.alpha = one;
-        for (int j = 0; j < kMaxAddends; ++j) { o.C[j] = -1; o.beta[j] = zero; o.beta_lo[j] = zero; }
+        o.A = A; o.B = B; o.D = D; o.Dprod = -1; o.Dalt = -1; o.scaled = 0; o.alpha = one;
+        for (int j = 0; j < kMaxAddends; ++j) { o.C[j] = -1; o.beta[j] = zero; o.beta_lo[j] = zero; o.beta_alt[j] = zero; }
         o.gamma = zero; o.gamma_lo = zero;
         return o;
     };
     auto coef = [&](int m) { return m <= M ? p.a[m] : zero; };
     auto coef_lo = [&](int m) { return m <= M ? p.a_lo[m] : zero; };
-    if (p.horner == 2) {
+    if (p.horner == 4) {
+        // degree 12 in four products (api.cu solve_degree12): p.a[k].re = tV tW tY lV lW lY lI rV rW sV sW sY sI
+        auto re = [&](int k) { return cplx{p.a[k].re, 0.0}; };
+        auto im = [&](int k) { return cplx{0.0, p.a[k].re}; };
+        auto re_lo = [&](int k) { return cplx{p.a_lo[k].re, 0.0}; };
+        auto im_lo = [&](int k) { return cplx{0.0, p.a_lo[k].re}; };
+        push(0, 0, 1);                                             // W = Y Y
+        {   // V = W Y  ->  slot 2;  T' = tV V + i tW W + tY Y  ->  slot 3
+            SeriesOp &o = push(1, 0, 3);
+            o.Dprod = 2;
+            o.scaled = 1; o.alpha = re(0);
+            o.C[0] = 0; o.beta[0] = re(2);
+            o.C[1] = 1; o.beta[1] = im(1);
+        }
+        {   // y0 = T' V;  L = y0 + i lV V + lW W + i lY Y + lI I  ->  slot 4;  R = y0 + i rV V + rW W  ->  slot 5
+            SeriesOp &o = push(3, 2, 4);
+            o.C[0] = 0; o.beta[0] = im(5);
+            o.C[1] = 1; o.beta[1] = re(4); o.beta_alt[1] = re(8);
+            o.C[2] = 2; o.beta[2] = im(3); o.beta_alt[2] = im(7);
+            o.gamma = re(6);
+            o.Dalt = 5;
+        }
+        {   // E = L R + i sV V + sW W + i sY Y + sI I  ->  slot 3
+            SeriesOp &o = push(4, 5, 3);
+            o.C[0] = 0; o.beta[0] = im(11); o.beta_lo[0] = im_lo(11);
+            o.C[1] = 1; o.beta[1] = re(10); o.beta_lo[1] = re_lo(10);
+            o.C[2] = 2; o.beta[2] = im(9);  o.beta_lo[2] = im_lo(9);
+            o.gamma = re(12); o.gamma_lo = re_lo(12);
+        }
+        g.u = zero; g.v = zero; g.v_lo = zero; g.w = zero; g.init5 = 0;
+        g.e_slot = 3;
+    } else if (p.horner == 2) {
         const int L = M >> 2;                                      // top block index
         push(0, 0, 1);                                             // Y^2
         // Y^3 = Y^2 Y, and the top block R_L = c_{4L+3} Y^3 + c_{4L+2} Y^2 + c_{4L+1} Y + c_{4L} I from the same product

@@ -6,7 +6,7 @@
 namespace pb {
 
 // D_b = alpha * (A_b * B_b) + sum_j (beta[j] + beta_lo[j]) * C[j]_b + beta2 * C2_b + (gamma + gamma_lo) * I   for b < batch,
-// and optionally Dprod_b = A_b * B_b.  All matrices n x n row-major interleaved complex double, n a multiple of 32
+// and optionally Dprod_b = A_b * B_b and Dalt_b = A_b * B_b + sum_j beta_alt[j] * C[j]_b (a second combination of the same addends).  All matrices n x n row-major interleaved complex double, n a multiple of 32
 // (n <= 32) or 64.  Addends may be null and may alias D.  The *_lo parts are sub-ulp remainders of the series constants;
 // they are added before the leading parts (DESIGN.md "Numerics").
 constexpr int kMaxAddends = 3;
@@ -17,6 +17,7 @@ struct GemmArgs {
     const double2 *C2; long long strideC2; double beta2;
     double2 *D; long long strideD;
     double2 *Dprod; long long strideDprod;
+    double2 *Dalt; long long strideDalt; cplx beta_alt[kMaxAddends];
     cplx alpha; int scaled;          // scaled != 0: the product is multiplied by alpha in D
     cplx gamma; cplx gamma_lo;
     int n;
@@ -25,10 +26,13 @@ struct GemmArgs {
 
 // The per-step series as a short program of fused GEMMs over matrix slots
 //   0 = Y    1 = Y^2 (W)    2 = Y^3    3 = Y^4 (V)    4, 5 = recurrence registers
+// (degree 12 in four products: 0 = Y, 1 = W, 2 = V = Y^3, 3 = T' then E, 4 = L, 5 = R; api.cu solve_degree12)
 // `assemble` writes slot 0, slot 4 = u Y + (v + v_lo) I and, if init5, slot 5 = w I.
 constexpr int kSeriesSlots = 6;
 struct SeriesOp {
     int A, B, D, Dprod;          // slots; Dprod < 0: none
+    int Dalt;                    // slot of the second combination (< 0: none), coefficients beta_alt
+    cplx beta_alt[kMaxAddends];
     int scaled; cplx alpha;
     int C[kMaxAddends];          // addend slots, < 0: unused
     cplx beta[kMaxAddends], beta_lo[kMaxAddends];

@@ -71,7 +71,10 @@ enum OcEpi : int {
     EPI_CLENSHAW = 3,  // D_smem = A B + beta * Cown(smem, == D) + gamma I
     EPI_CHAIN = 4,     // D_glob = A B + Eown(smem) + F(global)
     EPI_KEEP = 5,      // D_smem = A B, and the thread keeps its own elements of the product in registers (y2)
-    EPI_PS3 = 6        // D_smem = A B + b2 * Y2own(regs) + b1 * Yown(regs) + gamma I        (+ sub-ulp remainders if LO)
+    EPI_PS3 = 6,       // D_smem = A B + b2 * Y2own(regs) + b1 * Yown(regs) + gamma I        (+ sub-ulp remainders if LO)
+    EPI_S12_LR = 7,    // D_smem = A B + i kV Vown(smem) + kW Wown(regs) + i kY Yown(regs) + kI I, then (after a barrier: the
+                       // second destination is the A operand) D_smem2 = A B + i k2V Vown + k2W Wown     (degree 12, L and R)
+    EPI_S12_E = 8      // D_smem = A B + i kV Vown(smem) + kW Wown(regs) + i kY Yown(regs) + kI I   (+ sub-ulp remainders if LO)
 };
 
 // Shared-memory buffers are named by their element OFFSET into the dynamic shared array, never by pointer: a pointer that
@@ -91,6 +94,8 @@ struct OcArgs {
     double ci, ci_lo, cr, cr_lo;   // EPI_HORNER
     double beta;                // EPI_CLENSHAW
     cplx gamma, gamma_lo;
+    int v_smem, d_smem2;        // EPI_S12_*: own elements of V = Y^3; second destination
+    double kV, kW, kY, kI, kV_lo, kW_lo, kY_lo, kI_lo, k2V, k2W;
 };
 
 // Fused assembly of the next step's Y (one element per thread and k-tile).
@@ -256,6 +261,25 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                     vr[i] = fma(g.by.re, a1.x, fma(-g.by.im, a1.y, vr[i]));      // the Y term dominates: last
                     vi[i] = fma(g.by.re, a1.y, fma(g.by.im, a1.x, vi[i]));
                 }
+            } else if (EPI == EPI_S12_LR || EPI == EPI_S12_E) {
+                const double2 vs[2] = {oc_smem[g.v_smem + r * OC_P + c], oc_smem[g.v_smem + r * OC_P + c + 1]};
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double2 a1 = y[mt][nt][i], a2 = y2[mt][nt][i];
+                    if (LO) {
+                        vr[i] += (g.kW_lo * a2.x - g.kV_lo * vs[i].y) - g.kY_lo * a1.y;
+                        vi[i] += (g.kW_lo * a2.y + g.kV_lo * vs[i].x) + g.kY_lo * a1.x;
+                        if (r == c + i) vr[i] = (vr[i] + g.kI_lo) + g.kI;
+                    } else if (r == c + i) {
+                        vr[i] += g.kI;
+                    }
+                    vr[i] = fma(-g.kV, vs[i].y, vr[i]);
+                    vi[i] = fma(g.kV, vs[i].x, vi[i]);
+                    vr[i] = fma(g.kW, a2.x, vr[i]);
+                    vi[i] = fma(g.kW, a2.y, vi[i]);
+                    vr[i] = fma(-g.kY, a1.y, vr[i]);                             // the Y term dominates: last
+                    vi[i] = fma(g.kY, a1.x, vi[i]);
+                }
             } else if (EPI == EPI_CHAIN) {
                 const double2 e0 = oc_smem[g.c_smem + r * OC_P + c], e1 = oc_smem[g.c_smem + r * OC_P + c + 1];
                 const double2 f0 = oc_smem[g.c_smem2 + r * OC_P + c], f1 = oc_smem[g.c_smem2 + r * OC_P + c + 1];
@@ -270,6 +294,21 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                 oc_smem[g.d_smem + r * OC_P + c + 1] = make_double2(vr[1], vi[1]);
             }
         }
+    if (EPI == EPI_S12_LR) {
+        __syncthreads();   // every warp has read its A fragments: the A buffer may now receive the second combination
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+                const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double2 v = oc_smem[g.v_smem + r * OC_P + c + i], a2 = y2[mt][nt][i];
+                    oc_smem[g.d_smem2 + r * OC_P + c + i] =
+                        make_double2(fma(g.k2W, a2.x, fma(-g.k2V, v.y, cre[mt][nt][i])), fma(g.k2W, a2.y, fma(g.k2V, v.x, cim[mt][nt][i])));
+                }
+            }
+    }
 }
 
 // scratch per CTA: 2 matrices (F0, F1), row-major pitch 64 (the host allocates kSeriesSlots + 2).
@@ -334,7 +373,56 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
         int Yn;      // buffer that will receive the next step's Y
 
         OcOwn y, y2;
-        if (horner && ps3) {
+        if (p.horner == 4) {
+            // ---- degree 12 in four products (api.cu solve_degree12; p.a[k].re = tV tW tY lV lW lY lI rV rW sV sW sY sI):
+            //      W = Y Y, V = W Y, T' = tV V + i tW W + tY Y, y0 = T' V,
+            //      L = y0 + i lV V + lW W + i lY Y + lI I, R = y0 + i rV V + rW W, E = L R + i sV V + sW W + i sY Y + sI I.
+            //      Y and W enter the combinations through the thread's own elements in registers, V through its own elements
+            //      in shared memory ----
+            oc_load_own<N>(y, PY);
+            OcArgs a{};
+            a.sA = PY; a.sB = PY; a.d_smem = PA;
+            oc_gemm<N, EPI_KEEP, false, false>(a, none, y, y2);         // W -> PA, own elements -> y2
+            __syncthreads();
+            PB_T(1)
+            OcArgs b{};
+            b.sA = PA; b.sB = PY; b.d_smem = PB;
+            oc_gemm<N, EPI_STORE, false, false>(b, none, y, y2);        // V -> PB
+            __syncthreads();
+            PB_T(2)
+            {   // T' -> PA (W is dead as an operand)
+                const double tV = p.a[0].re, tW = p.a[1].re, tY = p.a[2].re;
+                const int lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
+                const int wm0 = (warp / G::WARPS_N) * G::WM, wn0 = (warp % G::WARPS_N) * G::WN;
+#pragma unroll
+                for (int mt = 0; mt < G::MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < G::NTL; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q + i;
+                            const double2 v = oc_smem[PB + r * OC_P + c], a1 = y[mt][nt][i], a2 = y2[mt][nt][i];
+                            oc_smem[PA + r * OC_P + c] = make_double2(fma(tY, a1.x, fma(-tW, a2.y, tV * v.x)), fma(tY, a1.y, fma(tW, a2.x, tV * v.y)));
+                        }
+            }
+            __syncthreads();
+            PB_T(3)
+            OcArgs lr{};
+            lr.sA = PA; lr.sB = PB; lr.d_smem = PY; lr.d_smem2 = PA; lr.v_smem = PB;
+            lr.kV = p.a[3].re; lr.kW = p.a[4].re; lr.kY = p.a[5].re; lr.kI = p.a[6].re;
+            lr.k2V = p.a[7].re; lr.k2W = p.a[8].re;
+            oc_gemm<N, EPI_S12_LR, false, false>(lr, none, y, y2);      // L -> PY (Y is dead as an operand), R -> PA
+            __syncthreads();
+            OcArgs ee{};
+            ee.sA = PY; ee.sB = PA; ee.d_smem = PB; ee.v_smem = PB;     // E overwrites V element by element (own elements only)
+            ee.kV = p.a[9].re; ee.kW = p.a[10].re; ee.kY = p.a[11].re; ee.kI = p.a[12].re;
+            ee.kV_lo = p.a_lo[9].re; ee.kW_lo = p.a_lo[10].re; ee.kY_lo = p.a_lo[11].re; ee.kI_lo = p.a_lo[12].re;
+            if (LO) oc_gemm<N, EPI_S12_E, true, false>(ee, none, y, y2);
+            else    oc_gemm<N, EPI_S12_E, false, false>(ee, none, y, y2);
+            __syncthreads();
+            PB_T(4)
+            E = PB; Fb = PY; Yn = PA;         // L and R are dead
+        } else if (horner && ps3) {
             // ---- Paterson-Stockmeyer blocks of three:  E = sum_i (c_{3i} I + c_{3i+1} Y + c_{3i+2} Y^2) V^i,  V = Y^3:
             //      2 + floor(M/3) products; Y and Y^2 enter only through the thread's own elements, kept in registers ----
             const cplx zero{0.0, 0.0};

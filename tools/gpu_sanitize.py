@@ -1,0 +1,17 @@
+"""Small run of every K1 series path for compute-sanitizer (development aid):
+   compute-sanitizer --tool memcheck python tools/gpu_sanitize.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import parament_b200 as pb
+from parament_b200.workloads import make_workload
+from oracle.equiprop_oracle import equiprop_oracle, rel_frobenius
+
+for name, kw in (("C2", dict(pts=4001)), ("C5", dict(pts=101, batch=40)), ("C1", dict(pts=501)), ("C3", dict(pts=41))):
+    w = make_workload(name, **kw)
+    with pb.Parament(w.precision) as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=w.use_magnus, quadrature_mode=w.quadrature)
+        U = ctx.equiprop_batch(w.dt, w.carr if w.batch > 1 else w.carr[None])
+        c0 = w.carr[0] if w.batch > 1 else w.carr
+        Uo = equiprop_oracle(w.H0, w.H1, c0, w.dt, w.quadrature, w.use_magnus, w.precision)
+        print(name, "series mode", int(ctx.stat(9)), "family", int(ctx.stat(5)), "err", rel_frobenius(U[0], Uo), flush=True)
