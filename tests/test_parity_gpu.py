@@ -148,6 +148,44 @@ def test_degree8_three_product_path(pb, n, A, quad, mag, complex_amps, monkeypat
     assert rel_frobenius(U, V) < 2e-6
 
 
+@pytest.mark.parametrize("n,A,quad,mag,prec,dt,onchip", [
+    (20, 2, "none", False, "fp64", 0.2, True), (32, 1, "midpoint", False, "fp64", 0.2, True),
+    (40, 3, "simpson", False, "fp64", 0.1, True), (64, 2, "simpson", True, "fp64", 0.1, True),
+    (64, 4, "none", False, "fp64", 0.1, True), (48, 2, "none", False, "fp32", 0.9, True),
+    (40, 2, "simpson", False, "fp64", 0.1, False), (96, 2, "none", False, "fp64", 0.2, True),
+    (130, 1, "simpson", False, "fp64", 0.1, True)])
+def test_degree12_four_product_path(pb, n, A, quad, mag, prec, dt, onchip, monkeypatch):
+    """Table degrees 9..12 of the shared-memory (dim 17..64) and batched (dim > 64) families are evaluated as one degree-12
+    polynomial in four matrix products (api.cu solve_degree12, k4_onchip.cu, k4_gemm.cu build_program).  It must be active,
+    meet the north_star tolerance against the oracle and agree with the Paterson-Stockmeyer / Horner evaluation."""
+    rng = np.random.default_rng(1000 * n + A)
+    herm = lambda: (lambda g: (g + g.conj().T) / 2)(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    norm1 = lambda m: m / np.max(np.sum(np.abs(m), axis=1))
+    ctype = np.complex64 if prec == "fp32" else np.complex128
+    H0 = (0.5 * norm1(herm())).astype(ctype)
+    H1 = [(0.5 / A * norm1(herm())).astype(ctype) for _ in range(A)]
+    pts = 41 if n > 64 else 161
+    carr = (rng.uniform(-1, 1, (A, pts)) + 1j * rng.uniform(-0.3, 0.3, (A, pts))).astype(ctype)
+    if not onchip:
+        monkeypatch.setenv("PARAMENT_NO_ONCHIP", "1")
+
+    def run():
+        with pb.Parament(prec) as ctx:
+            ctx.set_hamiltonian(H0, *H1, use_magnus=mag, quadrature_mode=quad)
+            U = ctx.equiprop(dt, *carr)
+            return U, ctx.stat(9), ctx.stat(2), ctx.stat(3), ctx.stat(10), ctx.stat(5)
+
+    U, mode, M_used, M_ref, products, fam = run()
+    assert fam == (2 if n <= 64 else 3)
+    assert 9 <= M_ref <= 12 and M_used == 12 and mode == 4 and products == 5
+    Uo = equiprop_oracle(H0, H1, carr, dt, quad, mag, prec)
+    assert rel_frobenius(U, Uo) < (2e-6 if prec == "fp32" else 1e-13)
+    monkeypatch.setenv("PARAMENT_SERIES", "horner")
+    V, mode_h, *_ = run()
+    assert mode_h in (1, 2)
+    assert rel_frobenius(U, V) < (2e-6 if prec == "fp32" else 1e-13)
+
+
 @pytest.mark.parametrize("case", [c for c in extended_cases() + reference_test_cases()], ids=lambda c: c["name"])
 def test_vs_reference_cuda_build(pb, case):
     if REF_CUDA is None or case["name"] not in REF_CUDA.files:
