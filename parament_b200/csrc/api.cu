@@ -407,9 +407,9 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     int M_ref = 0, M_used = 0;
     Parament_ErrorCode ec = choose_degree(c, h, s.total_steps, M_ref, M_used);
     if (ec != PARAMENT_STATUS_SUCCESS) return ec;
-    // complex64 contexts of the register-resident family evaluate degrees 6..8 as ONE degree-8 polynomial in three matrix
-    // products (below); the Y^2 Horner form needs four for degree 6 or 7.
-    const bool want_s8 = c->family == 1 && !c->fp64 && !c->MMAX_manual && c->series_mode == 0 && M_used >= 6 && M_used <= 8 &&
+    // Degrees 6..8 are evaluated as ONE degree-8 polynomial in three matrix products (below); the Y^2 Horner form needs four
+    // for degree 6 or 7.  The register-resident family does so for complex64 contexts (its path has no compensated constants).
+    const bool want_s8 = (c->family != 1 || !c->fp64) && !c->MMAX_manual && c->series_mode == 0 && M_used >= 6 && M_used <= 8 &&
                          c->Hnorm * h <= 1.0;
     if (want_s8) M_used = 8;
     // shared-memory and batched families: degrees 9..12 as ONE degree-12 polynomial in four matrix products

@@ -395,6 +395,7 @@ __global__ void k4_eform_kernel(const IO *__restrict__ P, int n, int npad, int c
 //                  R <- R W + c_{2i+1} Y + c_{2i} I                                   1 + floor(M/2) products
 //   p.horner == 2  Paterson-Stockmeyer with V = Y^4: Y^2, Y^3, Y^4, then
 //                  R <- R V + c_{4i+3} Y^3 + c_{4i+2} Y^2 + c_{4i+1} Y + c_{4i} I      3 + floor(M/4) products
+//   p.horner == 3  degree 8 as (y02 + ...)(y02 + ...) + ... with y02 = Y^2 (...)            3 products (api.cu solve_degree8)
 //   p.horner == 4  degree 12 as (y0 + ...)(y0 + ...) + ... with y0 = Y^3 (...)            4 products (api.cu solve_degree12)
 SeriesProgram build_program(const SeriesParams &p) {
     SeriesProgram g{};
@@ -410,7 +411,34 @@ SeriesProgram build_program(const SeriesParams &p) {
     };
     auto coef = [&](int m) { return m <= M ? p.a[m] : zero; };
     auto coef_lo = [&](int m) { return m <= M ? p.a_lo[m] : zero; };
-    if (p.horner == 4) {
+    if (p.horner == 3) {
+        // degree 8 in three products (api.cu solve_degree8): p.a[k].re = c4 c3 d2 d1 e2 e0 r2' r1 r0, A = -i Y, A2 = -W
+        auto re = [&](int k, double sgn) { return cplx{sgn * p.a[k].re, 0.0}; };
+        auto im = [&](int k, double sgn) { return cplx{0.0, sgn * p.a[k].re}; };
+        auto re_lo = [&](int k, double sgn) { return cplx{sgn * p.a_lo[k].re, 0.0}; };
+        auto im_lo = [&](int k, double sgn) { return cplx{0.0, sgn * p.a_lo[k].re}; };
+        {   // W = Y Y -> slot 1;  T = c4 W + i c3 Y -> slot 3
+            SeriesOp &o = push(0, 0, 3);
+            o.Dprod = 1;
+            o.scaled = 1; o.alpha = re(0, 1.0);
+            o.C[0] = 0; o.beta[0] = im(1, 1.0);
+        }
+        {   // y02 = T W;  L = y02 - d2 W - i d1 Y + e0 I -> slot 4;  R = y02 - e2 W -> slot 5
+            SeriesOp &o = push(3, 1, 4);
+            o.C[0] = 0; o.beta[0] = im(3, -1.0);
+            o.C[1] = 1; o.beta[1] = re(2, -1.0); o.beta_alt[1] = re(4, -1.0);
+            o.gamma = re(5, 1.0);
+            o.Dalt = 5;
+        }
+        {   // E = L R - r2' W - i r1 Y + r0 I -> slot 3
+            SeriesOp &o = push(4, 5, 3);
+            o.C[0] = 0; o.beta[0] = im(7, -1.0); o.beta_lo[0] = im_lo(7, -1.0);
+            o.C[1] = 1; o.beta[1] = re(6, -1.0); o.beta_lo[1] = re_lo(6, -1.0);
+            o.gamma = re(8, 1.0); o.gamma_lo = re_lo(8, 1.0);
+        }
+        g.u = zero; g.v = zero; g.v_lo = zero; g.w = zero; g.init5 = 0;
+        g.e_slot = 3;
+    } else if (p.horner == 4) {
         // degree 12 in four products (api.cu solve_degree12): p.a[k].re = tV tW tY lV lW lY lI rV rW sV sW sY sI
         auto re = [&](int k) { return cplx{p.a[k].re, 0.0}; };
         auto im = [&](int k) { return cplx{0.0, p.a[k].re}; };

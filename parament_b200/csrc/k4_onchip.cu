@@ -373,7 +373,47 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
         int Yn;      // buffer that will receive the next step's Y
 
         OcOwn y, y2;
-        if (p.horner == 4) {
+        if (p.horner == 3) {
+            // ---- degree 8 in three products (api.cu solve_degree8; p.a[k].re = c4 c3 d2 d1 e2 e0 r2' r1 r0, A = -i Y):
+            //      W = Y Y, T = c4 W + i c3 Y, y02 = T W, L = y02 - d2 W - i d1 Y + e0 I, R = y02 - e2 W,
+            //      E = L R - r2' W - i r1 Y + r0 I.  Same epilogues as the degree-12 form with the V terms switched off ----
+            oc_load_own<N>(y, PY);
+            OcArgs a{};
+            a.sA = PY; a.sB = PY; a.d_smem = PA;
+            oc_gemm<N, EPI_KEEP, false, false>(a, none, y, y2);         // W -> PA, own elements -> y2
+            PB_T(1)
+            {   // T -> PB (free)
+                const double c4 = p.a[0].re, c3 = p.a[1].re;
+#pragma unroll
+                for (int mt = 0; mt < G::MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < G::NTL; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
+                            const int r = (warp / G::WARPS_N) * G::WM + 8 * mt + gq, c = (warp % G::WARPS_N) * G::WN + 8 * nt + 2 * q + i;
+                            const double2 a1 = y[mt][nt][i], a2 = y2[mt][nt][i];
+                            oc_smem[PB + r * OC_P + c] = make_double2(fma(-c3, a1.y, c4 * a2.x), fma(c3, a1.x, c4 * a2.y));
+                        }
+            }
+            __syncthreads();
+            PB_T(3)
+            OcArgs lr{};
+            lr.sA = PB; lr.sB = PA; lr.d_smem = PY; lr.d_smem2 = PB; lr.v_smem = PA;
+            lr.kV = 0.0; lr.kW = -p.a[2].re; lr.kY = -p.a[3].re; lr.kI = p.a[5].re;
+            lr.k2V = 0.0; lr.k2W = -p.a[4].re;
+            oc_gemm<N, EPI_S12_LR, false, false>(lr, none, y, y2);      // L -> PY (Y is dead as an operand), R -> PB
+            __syncthreads();
+            OcArgs ee{};
+            ee.sA = PY; ee.sB = PB; ee.d_smem = PA; ee.v_smem = PA;     // W is dead as an operand
+            ee.kV = 0.0; ee.kW = -p.a[6].re; ee.kY = -p.a[7].re; ee.kI = p.a[8].re;
+            ee.kV_lo = 0.0; ee.kW_lo = -p.a_lo[6].re; ee.kY_lo = -p.a_lo[7].re; ee.kI_lo = p.a_lo[8].re;
+            if (LO) oc_gemm<N, EPI_S12_E, true, false>(ee, none, y, y2);
+            else    oc_gemm<N, EPI_S12_E, false, false>(ee, none, y, y2);
+            __syncthreads();
+            PB_T(4)
+            E = PA; Fb = PY; Yn = PB;         // L and R are dead
+        } else if (p.horner == 4) {
             // ---- degree 12 in four products (api.cu solve_degree12; p.a[k].re = tV tW tY lV lW lY lI rV rW sV sW sY sI):
             //      W = Y Y, V = W Y, T' = tV V + i tW W + tY Y, y0 = T' V,
             //      L = y0 + i lV V + lW W + i lY Y + lI I, R = y0 + i rV V + rW W, E = L R + i sV V + sW W + i sY Y + sI I.

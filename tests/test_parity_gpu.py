@@ -112,40 +112,44 @@ def test_extended_cases_clenshaw_path(pb, case, monkeypatch):
     assert rel_frobenius(U, V) < 1e-13
 
 
-@pytest.mark.parametrize("n,A,quad,mag,complex_amps", [
-    (2, 1, "none", False, False), (5, 2, "midpoint", False, False), (8, 2, "simpson", False, True),
-    (9, 1, "simpson", False, False), (16, 2, "simpson", False, False), (16, 3, "none", False, True),
-    (16, 2, "simpson", True, False), (13, 1, "midpoint", False, True), (7, 2, "simpson", True, True)])
-def test_degree8_three_product_path(pb, n, A, quad, mag, complex_amps, monkeypatch):
-    """complex64 contexts of the register-resident family evaluate table degrees 6..8 as one degree-8 polynomial in
-    three matrix products (api.cu solve_degree8, k1_warp.cu).  It must be active, agree with the oracle, and agree with
-    the Horner-in-Y^2 evaluation of the table degree to the output precision -- for Hermitian and non-Hermitian
-    generators (complex amplitudes), every quadrature, Magnus terms beyond the software-pipelined ones, and no controls."""
+@pytest.mark.parametrize("n,A,quad,mag,complex_amps,prec", [
+    (2, 1, "none", False, False, "fp32"), (5, 2, "midpoint", False, False, "fp32"), (8, 2, "simpson", False, True, "fp32"),
+    (9, 1, "simpson", False, False, "fp32"), (16, 2, "simpson", False, False, "fp32"), (16, 3, "none", False, True, "fp32"),
+    (16, 2, "simpson", True, False, "fp32"), (13, 1, "midpoint", False, True, "fp32"), (7, 2, "simpson", True, True, "fp32"),
+    (24, 2, "none", False, True, "fp32"), (64, 2, "simpson", False, False, "fp32"), (100, 1, "none", False, False, "fp32"),
+    (40, 2, "midpoint", False, True, "fp64"), (64, 3, "simpson", True, False, "fp64"), (96, 2, "none", False, False, "fp64")])
+def test_degree8_three_product_path(pb, n, A, quad, mag, complex_amps, prec, monkeypatch):
+    """Table degrees 6..8 are evaluated as one degree-8 polynomial in three matrix products (api.cu solve_degree8;
+    k1_warp.cu for complex64 contexts of dim <= 16, k4_onchip.cu / k4_gemm.cu build_program above that).  It must be
+    active, agree with the oracle, and agree with the Horner-in-Y^2 evaluation of the table degree -- for Hermitian and
+    non-Hermitian generators (complex amplitudes), every quadrature, and Magnus terms beyond the software-pipelined ones."""
     rng = np.random.default_rng(100 * n + A)
     herm = lambda: (lambda g: (g + g.conj().T) / 2)(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
     norm1 = lambda m: m / np.max(np.sum(np.abs(m), axis=1))
-    H0 = 0.6 * norm1(herm())
-    H1 = [0.4 / A * norm1(herm()) for _ in range(A)]
-    pts = 301
+    ctype = np.complex64 if prec == "fp32" else np.complex128
+    H0 = (0.6 * norm1(herm())).astype(ctype)
+    H1 = [(0.4 / A * norm1(herm())).astype(ctype) for _ in range(A)]
+    pts = 301 if n <= 64 else 41
     carr = rng.uniform(-1, 1, (A, pts)) + (1j * rng.uniform(-1, 1, (A, pts)) if complex_amps else 0)
-    carr = carr.astype(np.complex64)
-    dt = 0.45 if quad == "none" or quad == "midpoint" else 0.22     # Hnorm * h ~ 0.4: table degree 6 or 7
-    H0, H1 = H0.astype(np.complex64), [h.astype(np.complex64) for h in H1]
+    carr = carr.astype(ctype)
+    x = 0.44 if prec == "fp32" else 0.04                              # Hnorm * h: table degree 7
+    dt = x if quad in ("none", "midpoint") else x / 2
+    tol = 2e-6 if prec == "fp32" else 1e-13
 
     def run():
-        with pb.Parament("fp32") as ctx:
+        with pb.Parament(prec) as ctx:
             ctx.set_hamiltonian(H0, *H1, use_magnus=mag, quadrature_mode=quad)
             U = ctx.equiprop(dt, *carr)
             return U, ctx.stat(9), ctx.stat(2), ctx.stat(3), ctx.stat(10)
 
     U, mode, M_used, M_ref, products = run()
     assert 6 <= M_ref <= 8 and M_used == 8 and mode == 3 and products == 4
-    Uo = equiprop_oracle(H0, H1, carr, dt, quad, mag, "fp32")
-    assert rel_frobenius(U, Uo) < 2e-6
+    Uo = equiprop_oracle(H0, H1, carr, dt, quad, mag, prec)
+    assert rel_frobenius(U, Uo) < tol
     monkeypatch.setenv("PARAMENT_SERIES", "horner")
     V, mode_h, *_ = run()
     assert mode_h == 1
-    assert rel_frobenius(U, V) < 2e-6
+    assert rel_frobenius(U, V) < tol
 
 
 @pytest.mark.parametrize("n,A,quad,mag,prec,dt,onchip", [
