@@ -412,8 +412,8 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     const bool want_s8 = (c->family != 1 || !c->fp64) && !c->MMAX_manual && c->series_mode == 0 && M_used >= 6 && M_used <= 8 &&
                          c->Hnorm * h <= 1.0;
     if (want_s8) M_used = 8;
-    // shared-memory and batched families: degrees 9..12 as ONE degree-12 polynomial in four matrix products
-    const bool want_s12 = c->family != 1 && !c->MMAX_manual && c->series_mode == 0 && M_used >= 9 && M_used <= 12 &&
+    // degrees 9..12 as ONE degree-12 polynomial in four matrix products
+    const bool want_s12 = !c->MMAX_manual && c->series_mode == 0 && M_used >= 9 && M_used <= 12 &&
                           c->Hnorm * h <= 1.0;
     if (want_s12) M_used = 12;
     c->stat_M_ref = M_ref;

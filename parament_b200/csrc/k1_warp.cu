@@ -155,7 +155,79 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
 
             K1_T(0)
             AccFrag<NT> S0, S1;
-            if (HORNER == 3) {
+            if (HORNER == 4) {
+                // ---- degree 12 in four products (api.cu solve_degree12; p.a[k].re = tV tW tY lV lW lY lI rV rW sV sW sY sI):
+                //   W = X X, V = W X, T' = tV V + i tW W + tY X, y0 = T' V,
+                //   E = (y0 + i lV V + lW W + i lY X + lI I)(y0 + i rV V + rW W) + i sV V + sW W + i sY X + sI I.
+                // V and the right factor are needed as right operands: two layout shuffles.
+                constexpr bool LO = sizeof(IO) == sizeof(double2);
+                const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+                for (int e = 0; e < NE; ++e) (&Yb.nim[0][0])[e] = neg((&Yb.im[0][0])[e]);
+                AccFrag<NT> Wa, Va;
+                set_zero<NT>(Wa);
+                cmma<NT>(Wa, Ya, Yb);                       // W
+                set_zero<NT>(Va);
+                cmma<NT>(Va, Wa, Yb);                       // V = X^3
+                BFrag<NT> Vb;
+                acc_to_bfrag<NT>(Vb, Va, lane);
+                {
+                    const double tV = p.a[0].re, tW = p.a[1].re, tY = p.a[2].re;
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        (&Vb.nim[0][0])[e] = neg((&Vb.im[0][0])[e]);
+                        (&S0.re[0][0][0])[e] = fma(tY, (&Ya.re[0][0][0])[e], fma(-tW, (&Wa.im[0][0][0])[e], tV * (&Va.re[0][0][0])[e]));
+                        (&S0.im[0][0][0])[e] = fma(tY, (&Ya.im[0][0][0])[e], fma(tW, (&Wa.re[0][0][0])[e], tV * (&Va.im[0][0][0])[e]));
+                    }
+                }
+                AccFrag<NT> Y0;
+                set_zero<NT>(Y0);
+                cmma<NT>(Y0, S0, Vb);                       // y0
+                {   // right factor in accumulator layout (into S0), then shuffled
+                    const double rV = p.a[7].re, rW = p.a[8].re;
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        (&S0.re[0][0][0])[e] = fma(rW, (&Wa.re[0][0][0])[e], fma(-rV, (&Va.im[0][0][0])[e], (&Y0.re[0][0][0])[e]));
+                        (&S0.im[0][0][0])[e] = fma(rW, (&Wa.im[0][0][0])[e], fma(rV, (&Va.re[0][0][0])[e], (&Y0.im[0][0][0])[e]));
+                    }
+                }
+                BFrag<NT> Rb;
+                acc_to_bfrag<NT>(Rb, S0, lane);
+#pragma unroll
+                for (int e = 0; e < NE; ++e) (&Rb.nim[0][0])[e] = neg((&Rb.im[0][0])[e]);
+                {
+                    const double lV = p.a[3].re, lW = p.a[4].re, lY = p.a[5].re, lI = p.a[6].re;
+                    const double sV = p.a[9].re, sW = p.a[10].re, sY = p.a[11].re, sI = p.a[12].re;
+                    const double sV_lo = p.a_lo[9].re, sW_lo = p.a_lo[10].re, sY_lo = p.a_lo[11].re, sI_lo = p.a_lo[12].re;
+#pragma unroll
+                    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const bool diag = (mt == nt && g == 2 * q + i);
+                                const double xr = Ya.re[mt][nt][i], xi = Ya.im[mt][nt][i];
+                                const double wr = Wa.re[mt][nt][i], wi = Wa.im[mt][nt][i];
+                                const double vr = Va.re[mt][nt][i], vi = Va.im[mt][nt][i];
+                                double er, ei;
+                                if (LO) {   // sub-ulp remainders first, the dominant X term last (DESIGN.md "Numerics")
+                                    er = (sW_lo * wr - sV_lo * vi) - sY_lo * xi;
+                                    ei = (sW_lo * wi + sV_lo * vr) + sY_lo * xr;
+                                    if (diag) er = (er + sI_lo) + sI;
+                                } else {
+                                    er = diag ? sI : 0.0;
+                                    ei = 0.0;
+                                }
+                                er = fma(-sV, vi, er); ei = fma(sV, vr, ei);
+                                er = fma(sW, wr, er);  ei = fma(sW, wi, ei);
+                                S1.re[mt][nt][i] = fma(-sY, xi, er);
+                                S1.im[mt][nt][i] = fma(sY, xr, ei);
+                                Y0.re[mt][nt][i] = fma(-lY, xi, fma(lW, wr, fma(-lV, vi, Y0.re[mt][nt][i]))) + (diag ? lI : 0.0);
+                                Y0.im[mt][nt][i] = fma(lY, xr, fma(lW, wi, fma(lV, vr, Y0.im[mt][nt][i])));
+                            }
+                }
+                cmma<NT>(S1, Y0, Rb);                       // E
+            } else if (HORNER == 3) {
                 // ---- degree 8 in three products (api.cu solve_degree8).  With A = -i X:  W = X^2 = -A^2,
                 //   y02 = W (c4 W + i c3 X),   E = (y02 - d2 W - i d1 X + e0 I)(y02 - e2 W) - r2' W - i r1 X + r0 I
                 // (the e0 y02 term of the published form is folded into the left factor: e0 y02 = e0 (y02 - e2 W) + e0 e2 W,
@@ -380,6 +452,7 @@ template <int NT, typename IO>
 static cudaError_t launch_chain_t(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                   unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
                                   unsigned long long step_hi, cudaStream_t stream) {
+    if (p.horner == 4) return launch_chain_tt<NT, IO, 4>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
     if (p.horner == 3) {   // complex64 contexts only (api.cu build_series)
         if constexpr (sizeof(IO) == sizeof(float2))
             return launch_chain_tt<NT, IO, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);

@@ -157,10 +157,12 @@ def test_degree8_three_product_path(pb, n, A, quad, mag, complex_amps, prec, mon
     (40, 3, "simpson", False, "fp64", 0.1, True), (64, 2, "simpson", True, "fp64", 0.1, True),
     (64, 4, "none", False, "fp64", 0.1, True), (48, 2, "none", False, "fp32", 0.9, True),
     (40, 2, "simpson", False, "fp64", 0.1, False), (96, 2, "none", False, "fp64", 0.2, True),
-    (130, 1, "simpson", False, "fp64", 0.1, True)])
+    (130, 1, "simpson", False, "fp64", 0.1, True), (16, 2, "simpson", False, "fp64", 0.1, True),
+    (11, 3, "simpson", True, "fp64", 0.1, True), (6, 2, "midpoint", False, "fp64", 0.2, True), (2, 1, "none", False, "fp64", 0.2, True),
+    (16, 2, "none", False, "fp32", 0.9, True)])
 def test_degree12_four_product_path(pb, n, A, quad, mag, prec, dt, onchip, monkeypatch):
-    """Table degrees 9..12 of the shared-memory (dim 17..64) and batched (dim > 64) families are evaluated as one degree-12
-    polynomial in four matrix products (api.cu solve_degree12, k4_onchip.cu, k4_gemm.cu build_program).  It must be active,
+    """Table degrees 9..12 are evaluated as one degree-12 polynomial in four matrix products in every kernel family
+    (api.cu solve_degree12; k1_warp.cu, k4_onchip.cu, k4_gemm.cu build_program).  It must be active,
     meet the north_star tolerance against the oracle and agree with the Paterson-Stockmeyer / Horner evaluation."""
     rng = np.random.default_rng(1000 * n + A)
     herm = lambda: (lambda g: (g + g.conj().T) / 2)(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
@@ -180,7 +182,7 @@ def test_degree12_four_product_path(pb, n, A, quad, mag, prec, dt, onchip, monke
             return U, ctx.stat(9), ctx.stat(2), ctx.stat(3), ctx.stat(10), ctx.stat(5)
 
     U, mode, M_used, M_ref, products, fam = run()
-    assert fam == (2 if n <= 64 else 3)
+    assert fam == (1 if n <= 16 else (2 if n <= 64 else 3))
     assert 9 <= M_ref <= 12 and M_used == 12 and mode == 4 and products == 5
     Uo = equiprop_oracle(H0, H1, carr, dt, quad, mag, prec)
     assert rel_frobenius(U, Uo) < (2e-6 if prec == "fp32" else 1e-13)
