@@ -429,6 +429,16 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     p.pts = (unsigned int)s.stride;
     p.amps_in = s.amps;
     p.magfac = h / 12.0;
+    const int cache_flags = (want_s8 ? 1 : 0) | (want_s12 ? 2 : 0) | (c->series_mode << 2) | (c->fp64 ? 32 : 0);
+    Context::SeriesCache &sc = c->series_cache;
+    const bool cached = sc.valid && sc.h == h && sc.Hnorm == c->Hnorm && sc.M == M_used && sc.family == c->family &&
+                        sc.onchip == (int)c->onchip && sc.flags == cache_flags;
+    if (cached) {
+        p.sigma = sc.sigma;
+        p.horner = sc.horner;
+        memcpy(p.a, sc.a, sizeof(p.a));
+        memcpy(p.a_lo, sc.a_lo, sizeof(p.a_lo));
+    } else {
     // sigma is rounded to double FIRST and x is derived from the rounded value in long double, so that
     // sigma * x == 2 h holds to 1e-19: a relative error in sigma alone would stretch the time axis coherently.
     p.sigma = 2.0 / c->Hnorm;
@@ -485,6 +495,11 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
         if (M_used >= 10 && (c->family == 3 || (c->family == 2 && !c->onchip))) p.horner = 2;
         if (want_s8 && solve_degree8(p)) p.horner = 3;
         if (want_s12 && solve_degree12(p)) p.horner = 4;
+    }
+    sc.valid = true; sc.h = h; sc.Hnorm = c->Hnorm; sc.M = M_used; sc.family = c->family; sc.onchip = (int)c->onchip; sc.flags = cache_flags;
+    sc.horner = p.horner; sc.sigma = p.sigma;
+    memcpy(sc.a, p.a, sizeof(p.a));
+    memcpy(sc.a_lo, p.a_lo, sizeof(p.a_lo));
     }
     c->stat_horner = p.horner;
     const int A = c->amps, Ain = (int)s.amps;

@@ -58,7 +58,17 @@ struct Context {
     double stat_ms = 0.0;
     long long stat_launches = 0;
     int stat_M_used = 0, stat_M_ref = 0, stat_horner = 0;
-    int series_mode = 0;   // 0 automatic, 1 force the Clenshaw recurrence ($PARAMENT_SERIES=clenshaw)
+    int series_mode = 0;   // 0 automatic, 1 force the Clenshaw recurrence ($PARAMENT_SERIES=clenshaw), 2 Horner / PS only
+    // series constants of the last call: rebuilt only when the step size, the norm or the degree changes (the product-saving
+    // forms solve a small nonlinear system per distinct step size)
+    struct SeriesCache {
+        bool valid = false;
+        double h = 0.0, Hnorm = 0.0;
+        int M = 0, family = 0, onchip = 0, flags = 0;
+        int horner = 0;
+        double sigma = 0.0;
+        cplx a[kMaxDegree + 1], a_lo[kMaxDegree + 1];
+    } series_cache;
     unsigned long long stat_steps = 0;
     double stat_h2d = 0.0, stat_d2h = 0.0;
 };

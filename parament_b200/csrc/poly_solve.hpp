@@ -73,7 +73,7 @@ inline bool solve_degree12_real(const long double r[13], long double out[9]) {
     };
     long double best_f = 0.0L, best_d2 = 0.0L, best_d3 = 0.0L;
     bool found = false;
-    const int G = 8000;
+    const int G = 2000;
     const long double span = 5.0L * fabsl(s3);
     long double t_prev = -span, g_prev = resid(t_prev, nullptr);
     for (int i = 1; i <= G; ++i) {
