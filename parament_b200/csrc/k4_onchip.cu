@@ -58,7 +58,8 @@ struct Oc {
     static constexpr int MT = WM / 8, NTL = WN / 8;
     static constexpr int NN = N * N;
     static constexpr int EPT = NN / THREADS;        // matrix elements per thread in elementwise phases
-    static constexpr size_t SMEM = 3 * (size_t)BUF * sizeof(double2);
+    static constexpr int COEF = 3 * BUF;             // offset of the coefficient block of the fused assembly (OC_BLOCK x kMaxTerms)
+    static constexpr size_t SMEM = (3 * (size_t)BUF + 4 * kMaxTerms) * sizeof(double2);
     static_assert(EPT == N / 4, "one assembled element per k-tile");
 };
 constexpr int OC_MAXT = 8;                          // control terms the fused assembly keeps in registers
@@ -101,12 +102,13 @@ struct OcArgs {
 // Fused assembly of the next step's Y (one element per thread and k-tile).
 struct OcAssemble {
     const double2 *H;           // table, [mat][64*64]
-    const cplx *coef;           // shared memory, nterms coefficients of the NEXT step
+    int coef_off;               // offset into oc_smem of the coefficients: [b * kMaxTerms + t] for step j + 1 + b
+    int real_only;              // every coefficient of the pass is real (warp-uniform): half the multiply-adds
     const Term *terms;
     int nterms;
     double sigma;
     int y_smem;                 // destination buffer of the NEXT step's Y (offset into oc_smem, pitch OC_P)
-    int nblock;                 // steps assembled per pass of the table (1..OC_BLOCK): coef[b * kMaxTerms + t] for step j+1+b
+    int nblock;                 // steps assembled per pass of the table (1..OC_BLOCK)
     double2 *y_glob;            // row-major destinations of the later steps of the block: y_glob[(b - 1) * N*N + e], b >= 1
     uint64_t keep;              // L2 evict-last policy for y_glob
 };
@@ -124,9 +126,14 @@ __device__ __forceinline__ double2 oc_combine(const OcAssemble &as, int b, doubl
 #pragma unroll
     for (int t = 0; t < OC_MAXT; ++t)
         if (t < as.nterms) {
-            const cplx ct = as.coef[b * kMaxTerms + t];
-            x.x += ct.re * h[t].x - ct.im * h[t].y;
-            x.y += ct.re * h[t].y + ct.im * h[t].x;
+            const double2 ct = oc_smem[as.coef_off + b * kMaxTerms + t];   // explicit shared-memory access (LDS, broadcast)
+            if (as.real_only) {
+                x.x = fma(ct.x, h[t].x, x.x);
+                x.y = fma(ct.x, h[t].y, x.y);
+            } else {
+                x.x += ct.x * h[t].x - ct.y * h[t].y;
+                x.y += ct.x * h[t].y + ct.y * h[t].x;
+            }
         }
     return make_double2(x.x * as.sigma, x.y * as.sigma);
 }
@@ -318,7 +325,8 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                  double2 *__restrict__ scratch, double2 *__restrict__ partials, unsigned long long nsteps) {
     using G = Oc<N>;
     constexpr int OC_P = G::P, OC_N = N, OC_THREADS = G::THREADS, OC_NN = G::NN, OC_EPT = G::EPT, OC_BUF = G::BUF;
-    __shared__ cplx coef[OC_BLOCK * kMaxTerms];
+    static_assert(OC_BLOCK == 4, "Oc<N>::SMEM reserves 4 x kMaxTerms coefficients");
+    cplx *coef = reinterpret_cast<cplx *>(oc_smem + G::COEF);   // writes only; the fused pass reads it by offset
 
     const int tid = threadIdx.x;
     // scratch per CTA: F0, F1 and OC_BLOCK - 1 pre-assembled Y matrices, packed (the host provides kSeriesSlots + 2 >= 5 per CTA)
@@ -337,7 +345,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 
     const uint64_t keep = l2_keep_policy();
     OcAssemble as{};
-    as.H = H; as.coef = coef; as.terms = p.terms; as.nterms = p.nterms; as.sigma = p.sigma; as.keep = keep;
+    as.H = H; as.coef_off = G::COEF; as.terms = p.terms; as.nterms = p.nterms; as.sigma = p.sigma; as.keep = keep;
     const OcAssemble none{};
 
     int iy = 0;              // buffer index holding Y of the current step
@@ -572,12 +580,14 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
         // the product below -- the table (320 KB at dim 64 with 4 controls) is the dominant L2 traffic of this kernel.
         const bool fetch_now = more && have_f && ahead > 0;
         const bool fuse_now = more && fuse && have_f && ahead == 0;
-        int nblock = 0;
+        int nblock = 0, any_imag = 0;
         if (fuse_now) {
             nblock = (int)min((unsigned long long)OC_BLOCK, hi - (j + 1));
             for (int i = tid; i < p.nterms * nblock; i += OC_THREADS) {
                 const int b = i / p.nterms, t = i % p.nterms;
-                coef[b * kMaxTerms + t] = step_coefficient<IO>(p.terms[t], carr, p.pts, p.quad, p.magfac, j + 1 + b);
+                const cplx ct = step_coefficient<IO>(p.terms[t], carr, p.pts, p.quad, p.magfac, j + 1 + b);
+                coef[b * kMaxTerms + t] = ct;
+                any_imag |= (ct.im != 0.0);
             }
         }
         if (!have_f) {
@@ -602,7 +612,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                 asm volatile("cp.async.commit_group;\n" ::);
                 asm volatile("cp.async.wait_group 0;\n" ::);
             }
-            __syncthreads();
+            as.real_only = !__syncthreads_or(any_imag);
             PB_T(5)
             OcArgs ch{};
             ch.sA = E; ch.sB = Fb; ch.c_smem = E; ch.c_smem2 = Fb; ch.d_glob = Fg[f_cur ^ 1]; ch.keep = keep;
