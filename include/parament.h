@@ -192,8 +192,13 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  *   5 kernel family used (1 = register-resident DMMA warp kernel, 2 = persistent CTA chain kernel,
  *                         3 = batched GEMM pipeline over L2-resident time chunks)
  *   6 H2D bytes copied                    7 D2H bytes copied
- *   8 Hnorm of the loaded Hamiltonian     9 series evaluation (0 Clenshaw recurrence, 1 Horner in Y^2)
- *  10 complex matrix products executed per effective step (series + ordered product) */
+ *   8 Hnorm of the loaded Hamiltonian
+ *   9 series evaluation (0 Clenshaw recurrence, 1 Horner in Y^2, 2 Paterson-Stockmeyer blocks of four,
+ *                        3 degree 8 in three products, 4 degree 12 in four products -- all the same polynomial family)
+ *  10 complex matrix products executed per effective step (series + ordered product)
+ * Environment switches read at Parament_create (development / A-B testing): PARAMENT_SERIES=clenshaw forces the reference's
+ * recurrence, PARAMENT_SERIES=horner the Horner / Paterson-Stockmeyer forms; PARAMENT_NO_ONCHIP=1 selects the L2-scratch
+ * chain kernel for dim 17..64; PARAMENT_DEVICE the default CUDA device. */
 PARAMENT_API double Parament_lastStat(void *handle, int key);
 
 /* Select the CUDA device a context lives on.  Must be called before setHamiltonian; default is device 0
