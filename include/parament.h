@@ -205,6 +205,22 @@ PARAMENT_API double Parament_lastStat(void *handle, int key);
  * (reference: device 0 implicit, parament.cpp:108) or $PARAMENT_DEVICE. */
 PARAMENT_API Parament_ErrorCode Parament_setDevice(void *handle, int device);
 
+/* Single-process multi-GPU (the caller is ONE ctypes call, so one host process drives all devices).
+ * Parament_setDevices(h, n): use n devices starting at the context's own (n <= 0 or n > visible: all visible devices;
+ * n = 1: back to one device).  Parament_setDeviceList(h, devices, count): explicit list, devices[0] is where the context
+ * lives (moving it drops the Hamiltonian, like Parament_setDevice); an entry may repeat.  $PARAMENT_NUM_GPUS at
+ * Parament_create has the effect of Parament_setDevices, so the unchanged reference wrapper gets the mode as well.
+ * Afterwards every host-pointer Parament_equiprop[_fp64] cuts the time axis into contiguous slices, one per device: each
+ * device copies only its slice of the caller's arrays, reduces it to a partial propagator on its own stream (one host
+ * thread per device), the dim x dim partials travel to the first device by peer copy (NVLink when peer access exists)
+ * and are multiplied in order there.  Parament_equipropBatch[_fp64] cuts the pulses of the ensemble into contiguous
+ * ranges instead (no exchange).  Calls too small to share (fewer than max(64, 2^26 / npad^3) effective steps per
+ * device) run on the first device alone.  Parament_lastStat key 11 = devices that took part in the last call, key 12 =
+ * devices configured; key 0 is then the host wall clock of the whole shared call in milliseconds.
+ * The device-pointer entry points are not shared: they run on the context's own device. */
+PARAMENT_API Parament_ErrorCode Parament_setDevices(void *handle, int ngpus);
+PARAMENT_API Parament_ErrorCode Parament_setDeviceList(void *handle, const int *devices, int count);
+
 /* Pipe-peak microbenchmark on the current CUDA device, used as roofline denominator by bench.py.
  * kind: 0 FP32 FFMA TFLOP/s, 1 FP64 DFMA TFLOP/s, 2 FP64 tensor-pipe DMMA TFLOP/s, 3 HBM copy GB/s. */
 PARAMENT_API double Parament_measurePeak(int kind);

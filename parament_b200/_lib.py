@@ -65,6 +65,8 @@ lib.Parament_combineDevice.argtypes = [ctx_p, ctypes.c_void_p, u32, ctypes.c_voi
 lib.Parament_lastStat.argtypes = [ctx_p, ctypes.c_int]
 lib.Parament_lastStat.restype = f64
 lib.Parament_setDevice.argtypes = [ctx_p, ctypes.c_int]
+lib.Parament_setDevices.argtypes = [ctx_p, ctypes.c_int]
+lib.Parament_setDeviceList.argtypes = [ctx_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
 lib.Parament_measurePeak.argtypes = [ctypes.c_int]
 lib.Parament_measurePeak.restype = f64
 lib.Parament_version.argtypes = []
@@ -81,5 +83,6 @@ EXPORTED = [
     # section 2: additive
     "Parament_equipropBatch", "Parament_equipropBatch_fp64", "Parament_equipropDevice",
     "Parament_equipropDevice_fp64", "Parament_equipropSlice", "Parament_equipropSlice_fp64", "Parament_combine",
-    "Parament_combine_fp64", "Parament_combineDevice", "Parament_lastStat", "Parament_setDevice", "Parament_measurePeak", "Parament_version",
+    "Parament_combine_fp64", "Parament_combineDevice", "Parament_lastStat", "Parament_setDevice", "Parament_setDevices",
+    "Parament_setDeviceList", "Parament_measurePeak", "Parament_version",
 ]

@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "context.hpp"
@@ -75,7 +77,9 @@ void destroy_copy_events(Context *c) {
 // ---------------------------------------------------------------------------------------------------
 // create / destroy                                                   (reference parament.cpp:51-205)
 // ---------------------------------------------------------------------------------------------------
-Parament_ErrorCode create_ctx(Context **out, bool fp64) {
+Parament_ErrorCode set_device_list(Context *c, const int *devices, int count);
+
+Parament_ErrorCode create_ctx_on(Context **out, bool fp64, int dev) {
     if (!out) return PARAMENT_STATUS_INVALID_VALUE;
     *out = nullptr;
     Context *c = new (std::nothrow) Context();
@@ -87,8 +91,10 @@ Parament_ErrorCode create_ctx(Context **out, bool fp64) {
         delete c;
         return PARAMENT_STATUS_CUBLAS_INIT_FAILED;   // code 30: device initialisation failed
     }
-    int dev = 0;
-    if (const char *e = getenv("PARAMENT_DEVICE")) dev = atoi(e);
+    if (dev < 0) {
+        dev = 0;
+        if (const char *e = getenv("PARAMENT_DEVICE")) dev = atoi(e);
+    }
     if (dev < 0 || dev >= ndev) dev = 0;
     c->device = dev;
     if (!PB_CUDA_OK(cudaSetDevice(dev)) ||
@@ -106,10 +112,28 @@ Parament_ErrorCode create_ctx(Context **out, bool fp64) {
     return PARAMENT_STATUS_SUCCESS;
 }
 
+Parament_ErrorCode set_device_count(Context *c, int ngpus);
+
+Parament_ErrorCode create_ctx(Context **out, bool fp64) {
+    Parament_ErrorCode ec = create_ctx_on(out, fp64, -1);
+    if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+    // $PARAMENT_NUM_GPUS: the unchanged reference wrapper gets the single-process multi-GPU mode without a new call
+    // (0 = every visible device; more than there are = every visible device)
+    if (const char *e = getenv("PARAMENT_NUM_GPUS")) {
+        const int want = atoi(e);
+        if (want != 1 && set_device_count(*out, want) != PARAMENT_STATUS_SUCCESS) (*out)->lastError = PARAMENT_STATUS_SUCCESS;
+    }
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+void destroy_peers(Context *c);
+
 Parament_ErrorCode destroy_ctx(Context *c) {
     if (!c) return PARAMENT_STATUS_SUCCESS;   // NULL is a no-op (parament.cpp:190-191)
+    destroy_peers(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    free_dev(c->d_gather);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
     free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -123,6 +147,11 @@ Parament_ErrorCode destroy_ctx(Context *c) {
     delete c;
     cudaGetLastError();
     return PARAMENT_STATUS_SUCCESS;
+}
+
+void destroy_peers(Context *c) {
+    for (Context *p : c->peers) destroy_ctx(p);
+    c->peers.clear();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -285,9 +314,37 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     }
 
     if (!upload_matrices(c)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
+    // single-process multi-GPU: every helper context gets the same Hamiltonian (constants are replicated)
+    for (Context *p : c->peers) {
+        const Parament_ErrorCode ec = set_hamiltonian<T>(p, H0, H1, dim, amps, use_magnus, quad);
+        if (ec != PARAMENT_STATUS_SUCCESS) { cudaSetDevice(c->device); return fail(c, ec); }
+    }
+    cudaSetDevice(c->device);
     c->have_hamiltonian = true;
     c->lastError = PARAMENT_STATUS_SUCCESS;
     return PARAMENT_STATUS_SUCCESS;
+}
+
+// The Hamiltonian of `c` loaded into the helper context `p` (helpers created after setHamiltonian): the host copies in
+// double are exact conversions of the inputs, so converting back reproduces the caller's arrays bit for bit.
+template <typename T>
+Parament_ErrorCode replay_hamiltonian_t(const Context *c, Context *p) {
+    const size_t nn = (size_t)c->dim * c->dim, cnt = (size_t)(1 + c->amps) * nn;
+    std::vector<T> buf(cnt);
+    for (size_t e = 0; e < cnt; ++e) {
+        buf[e].re = static_cast<decltype(buf[e].re)>(c->mats[e].real());
+        buf[e].im = static_cast<decltype(buf[e].im)>(c->mats[e].imag());
+    }
+    return set_hamiltonian<T>(p, buf.data(), buf.data() + nn, (unsigned int)c->dim, (unsigned int)c->amps, c->enable_magnus, c->quadrature);
+}
+Parament_ErrorCode replay_hamiltonian(const Context *c, Context *p) {
+    p->MMAX = c->MMAX; p->MMAX_manual = c->MMAX_manual; p->series_mode = c->series_mode;
+    if (!c->have_hamiltonian) return PARAMENT_STATUS_SUCCESS;
+    try {
+        return c->fp64 ? replay_hamiltonian_t<Parament_c128>(c, p) : replay_hamiltonian_t<Parament_c64>(c, p);
+    } catch (const std::bad_alloc &) {
+        return PARAMENT_STATUS_HOST_ALLOC_FAILED;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -806,10 +863,23 @@ void write_identity(T *out, int n, unsigned int batch) {
 // Host-pointer entry: stage the needed part of the amplitude stream, run, copy the result back.
 // step range [lo, hi) of each pulse; carr holds batch * amps arrays of pts points.
 template <typename T>
+Parament_ErrorCode equiprop_multi(Context *c, const T *carr, double dt, unsigned int pts, unsigned int amps, unsigned int batch, T *out,
+                                  bool &handled);
+
+// gather_to != nullptr (single-process multi-GPU): the result is not copied to the host but to slot `slot` of
+// gather_to->d_gather by a peer copy (NVLink when the devices have peer access), and `out` is not written.
+template <typename T>
 Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned int pts, unsigned int amps, unsigned int batch,
-                                 unsigned long long lo, unsigned long long hi, bool whole, T *out) {
+                                 unsigned long long lo, unsigned long long hi, bool whole, T *out, Context *gather_to = nullptr,
+                                 unsigned int slot = 0) {
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    if (whole && !gather_to && !c->peers.empty()) {
+        bool handled = false;
+        const Parament_ErrorCode mec = equiprop_multi<T>(c, carr, dt, pts, amps, batch, out, handled);
+        if (handled) return mec;
+    }
     cudaSetDevice(c->device);
+    c->stat_devices = 1;
     if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);   // parament.cpp:795-798
     if (!out || (!carr && amps > 0 && pts > 0) || (int)amps > c->amps || batch == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
     const unsigned long long N = effective_steps(c, pts);
@@ -859,6 +929,14 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
         ec = propagate_device(c, c->d_carr.ptr, s, c->d_out.ptr, c->stream);
     }
     if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
+    if (gather_to) {
+        if (!PB_CUDA_OK(cudaMemcpyPeerAsync((T *)gather_to->d_gather.ptr + (size_t)slot * n * n, gather_to->device, c->d_out.ptr, c->device,
+                                            out_bytes, c->stream)) ||
+            !PB_CUDA_OK(cudaStreamSynchronize(c->stream)))
+            return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+        c->lastError = PARAMENT_STATUS_SUCCESS;
+        return PARAMENT_STATUS_SUCCESS;
+    }
     if (!PB_CUDA_OK(cudaMemcpyAsync(out, c->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, c->stream)) ||
         !PB_CUDA_OK(cudaStreamSynchronize(c->stream)))
         return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
@@ -944,6 +1022,145 @@ Parament_ErrorCode combine_device(Context *c, const void *parts_dev, unsigned in
     return PARAMENT_STATUS_SUCCESS;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Single-process multi-GPU ("one host process drives all devices; the caller is a single ctypes call").
+// A single pulse: the N effective steps are cut into contiguous slices, device g propagates slice g from the caller's
+// host arrays (its own H2D of just that slice, its own stream, one host thread per device), the dim x dim partials travel
+// to the first device by peer copy and are multiplied in order there (combine_device_core).  An ensemble: the pulses
+// are cut into contiguous ranges, no exchange at all.  Work that is too small to share stays on one device.
+// ---------------------------------------------------------------------------------------------------
+unsigned long long min_steps_per_device(const Context *c) {
+    const unsigned long long np3 = (unsigned long long)c->npad * c->npad * c->npad;
+    return std::max<unsigned long long>(64, (1ull << 26) / std::max<unsigned long long>(np3, 1));
+}
+
+template <typename T>
+Parament_ErrorCode equiprop_multi(Context *c, const T *carr, double dt, unsigned int pts, unsigned int amps, unsigned int batch, T *out,
+                                  bool &handled) {
+    handled = false;
+    if (!c->have_hamiltonian || !carr || !out || (int)amps > c->amps || batch == 0 || c->Hnorm == 0.0) return PARAMENT_STATUS_SUCCESS;
+    const unsigned long long N = effective_steps(c, pts);
+    const unsigned long long work = N * batch, share_min = min_steps_per_device(c);
+    unsigned int G = (unsigned int)std::min<unsigned long long>(c->peers.size() + 1, work / share_min);
+    if (batch > 1) G = std::min(G, batch);
+    if (G < 2) return PARAMENT_STATUS_SUCCESS;   // not worth sharing: the caller runs it on the first device
+    handled = true;
+    const int n = c->dim;
+    const size_t nn = (size_t)n * n;
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<Parament_ErrorCode> ecs(G, PARAMENT_STATUS_SUCCESS);
+    std::vector<std::thread> workers;
+    auto ctx_of = [&](unsigned int g) { return g == 0 ? c : c->peers[g - 1]; };
+    try {
+        workers.reserve(G);
+        if (batch == 1) {
+            cudaSetDevice(c->device);
+            if (!ensure_dev(c->d_gather, (size_t)G * nn * sizeof(T))) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
+            auto run = [&](unsigned int g) {
+                ecs[g] = equiprop_host<T>(ctx_of(g), carr, dt, pts, amps, 1, N * g / G, N * (g + 1) / G, false, out, c, g);
+            };
+            for (unsigned int g = 1; g < G; ++g) workers.emplace_back(run, g);
+            run(0);
+        } else {
+            // whole = false with the full step range [0, N): neither this context nor a helper shares the work again
+            auto run_range = [&](unsigned int g) {
+                const size_t b0 = (size_t)batch * g / G, b1 = (size_t)batch * (g + 1) / G;
+                ecs[g] = equiprop_host<T>(ctx_of(g), carr + b0 * amps * pts, dt, pts, amps, (unsigned int)(b1 - b0), 0, N, false, out + b0 * nn);
+            };
+            for (unsigned int g = 1; g < G; ++g) workers.emplace_back(run_range, g);
+            run_range(0);
+        }
+    } catch (...) {   // thread creation failed: finish what was started, report a host-side failure
+        for (auto &w : workers) if (w.joinable()) w.join();
+        cudaSetDevice(c->device);
+        return fail(c, PARAMENT_STATUS_HOST_ALLOC_FAILED);
+    }
+    for (auto &w : workers) w.join();
+    cudaSetDevice(c->device);
+    long long launches = 0;
+    double h2d = 0;
+    for (unsigned int g = 0; g < G; ++g) {
+        if (ecs[g] != PARAMENT_STATUS_SUCCESS) return fail(c, ecs[g]);
+        launches += ctx_of(g)->stat_launches;
+        h2d += ctx_of(g)->stat_h2d;
+    }
+    if (batch == 1) {
+        const size_t out_bytes = nn * sizeof(T);
+        if (!ensure_dev(c->d_out, out_bytes)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
+        Parament_ErrorCode ec = combine_device_core(c, c->d_gather.ptr, G, c->d_out.ptr, c->stream);
+        if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
+        launches += c->stat_launches;
+        if (!PB_CUDA_OK(cudaMemcpyAsync(out, c->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, c->stream)) ||
+            !PB_CUDA_OK(cudaStreamSynchronize(c->stream)))
+            return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+    }
+    c->stat_launches = launches;
+    c->stat_h2d = h2d;
+    c->stat_d2h = (double)(batch * nn * sizeof(T));
+    c->stat_steps = N;
+    c->stat_devices = (int)G;
+    c->stat_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->lastError = PARAMENT_STATUS_SUCCESS;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+// devices[0] is where the context lives (moving it drops the Hamiltonian, like Parament_setDevice); devices[1..] get helper
+// contexts.  A device may be listed more than once (its share of the work is then proportional; used by the tests on
+// one-GPU machines).
+Parament_ErrorCode move_to_device(Context *c, int device);
+
+Parament_ErrorCode set_device_list(Context *c, const int *devices, int count) {
+    if (!c || c->is_peer) return PARAMENT_STATUS_INVALID_VALUE;
+    int ndev = 0;
+    if (!devices || count < 1 || cudaGetDeviceCount(&ndev) != cudaSuccess) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    for (int i = 0; i < count; ++i)
+        if (devices[i] < 0 || devices[i] >= ndev) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    destroy_peers(c);
+    if (devices[0] != c->device) {
+        const Parament_ErrorCode ec = move_to_device(c, devices[0]);
+        if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+    }
+    for (int i = 1; i < count; ++i) {
+        Context *p = nullptr;
+        Parament_ErrorCode ec = create_ctx_on(&p, c->fp64, devices[i]);
+        if (ec == PARAMENT_STATUS_SUCCESS) {
+            p->is_peer = true;
+            ec = replay_hamiltonian(c, p);
+            if (ec != PARAMENT_STATUS_SUCCESS) destroy_ctx(p);
+        }
+        if (ec != PARAMENT_STATUS_SUCCESS) {
+            destroy_peers(c);
+            cudaSetDevice(c->device);
+            return fail(c, ec);
+        }
+        c->peers.push_back(p);
+        if (devices[i] != c->device) {   // direct NVLink path for the partials; "already enabled" / "unsupported" are both fine
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], c->device) == cudaSuccess && can) {
+                cudaSetDevice(devices[i]);
+                cudaDeviceEnablePeerAccess(c->device, 0);
+            }
+            cudaGetLastError();
+        }
+    }
+    cudaSetDevice(c->device);
+    c->lastError = PARAMENT_STATUS_SUCCESS;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
+Parament_ErrorCode set_device_count(Context *c, int ngpus) {
+    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    if (ngpus <= 0 || ngpus > ndev) ngpus = ndev;
+    std::vector<int> list(ngpus);
+    for (int i = 0; i < ngpus; ++i) list[i] = (c->device + i) % ndev;
+    return set_device_list(c, list.data(), ngpus);
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1019,12 +1236,14 @@ static Parament_ErrorCode set_cycles(Context *c, unsigned int cycles) {   // par
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
     c->MMAX = (int)cycles;
     c->MMAX_manual = true;
+    for (Context *p : c->peers) { p->MMAX = (int)cycles; p->MMAX_manual = true; }
     return PARAMENT_STATUS_SUCCESS;
 }
 static Parament_ErrorCode auto_cycles(Context *c) {   // parament.cpp:782-786
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
     c->MMAX = 11;
     c->MMAX_manual = false;
+    for (Context *p : c->peers) { p->MMAX = 11; p->MMAX_manual = false; }
     return PARAMENT_STATUS_SUCCESS;
 }
 Parament_ErrorCode Parament_setIterationCyclesManually(struct Parament_Context_f32 *h, unsigned int cycles) { return set_cycles(as_ctx(h), cycles); }
@@ -1082,6 +1301,7 @@ double Parament_lastStat(void *h, int key) {
     if (!c) return -1.0;
     switch (key) {
         case 0: {
+            if (c->stat_devices > 1) return c->stat_ms;   // shared call: host wall clock around all devices and the combine
             float ms = 0;
             cudaSetDevice(c->device);
             if (cudaEventSynchronize(c->ev_stop) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) == cudaSuccess) return ms;
@@ -1106,19 +1326,33 @@ double Parament_lastStat(void *h, int key) {
             if (c->stat_horner == 1 && c->family == 2 && c->onchip && (M == 8 || M >= 10)) return 3.0 + M / 3;   // blocks of three
             return c->stat_horner ? 2.0 + (M >> 1) : (double)std::max(M, 1);
         }
+        case 11: return c->stat_devices;
+        case 12: return (double)c->peers.size() + 1.0;
         default: return -1.0;
     }
 }
 
 Parament_ErrorCode Parament_setDevice(void *h, int device) {
     Context *c = as_ctx(h);
-    if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    if (!c || c->is_peer) return PARAMENT_STATUS_INVALID_VALUE;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
+    destroy_peers(c);   // back to one device; Parament_setDevices adds helpers again
     if (device == c->device) return PARAMENT_STATUS_SUCCESS;
+    return move_to_device(c, device);
+}
+
+Parament_ErrorCode Parament_setDevices(void *h, int ngpus) { return set_device_count(as_ctx(h), ngpus); }
+Parament_ErrorCode Parament_setDeviceList(void *h, const int *devices, int count) { return set_device_list(as_ctx(h), devices, count); }
+
+}  // extern "C"
+
+namespace {
+Parament_ErrorCode move_to_device(Context *c, int device) {
     // move: drop everything that lives on the old device
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    free_dev(c->d_gather);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
     free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
     cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); destroy_copy_events(c);
@@ -1133,6 +1367,9 @@ Parament_ErrorCode Parament_setDevice(void *h, int device) {
         return fail(c, PARAMENT_STATUS_CUBLAS_INIT_FAILED);
     return PARAMENT_STATUS_SUCCESS;
 }
+}  // namespace
+
+extern "C" {
 
 const char *Parament_version(void) { return "parament-b200 0.1 (sm_100a, FP64 tensor pipe)"; }
 

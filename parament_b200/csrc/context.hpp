@@ -51,6 +51,14 @@ struct Context {
     DeviceBuffer d_carr, d_out, d_partials;
     DeviceBuffer d_Y, d_pending, d_tree;   // families 2 / 3: series slots, pending partial products, tree scratch
     DeviceBuffer d_comb, d_comb2;   // combine of time-slice partials
+    DeviceBuffer d_gather;          // single-process multi-GPU: partial propagators of all devices, slice order
+
+    // Single-process multi-GPU (Parament_setDevices / $PARAMENT_NUM_GPUS): helper contexts on the other devices, owned
+    // by this one.  The time axis of a pulse (or the pulses of an ensemble) is cut into contiguous shares, every
+    // device reduces its share on its own stream, partials arrive by peer copy and are combined in order here.
+    std::vector<Context *> peers;
+    bool is_peer = false;
+    int stat_devices = 1;           // devices that took part in the last equiprop
     void *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for carr
     void *h_out = nullptr;   size_t h_out_bytes = 0;    // pinned staging for results
 

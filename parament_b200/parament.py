@@ -177,6 +177,17 @@ class Parament:
         else:
             self._check_error(self._fn("Parament_setIterationCyclesManually")(self._handle, int(cycles)))
 
+    def set_devices(self, devices=0):
+        """Single-process multi-GPU (include/parament.h, Parament_setDevices / Parament_setDeviceList): an int n uses n
+        devices starting at the context's own (0 = all visible, 1 = back to one device); a sequence names the devices,
+        the first one hosting the context.  Later equiprop / equiprop_batch calls with host arrays are shared."""
+        self._alive()
+        if isinstance(devices, (int, np.integer)):
+            self._check_error(lib.Parament_setDevices(self._handle, int(devices)))
+        else:
+            arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            self._check_error(lib.Parament_setDeviceList(self._handle, arr, len(devices)))
+
     def stat(self, key):
         self._alive()
         return lib.Parament_lastStat(self._handle, int(key))
