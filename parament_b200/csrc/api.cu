@@ -65,12 +65,12 @@ bool ensure_pinned(void *&p, size_t &have, size_t bytes) {
 }
 
 bool create_copy_events(Context *c) {
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < kCopyEvents; ++i)
         if (!PB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming))) return false;
     return true;
 }
 void destroy_copy_events(Context *c) {
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < kCopyEvents; ++i)
         if (c->ev_copy[i]) { cudaEventDestroy(c->ev_copy[i]); c->ev_copy[i] = nullptr; }
 }
 
@@ -141,6 +141,7 @@ Parament_ErrorCode destroy_ctx(Context *c) {
     cudaEventDestroy(c->ev_start);
     cudaEventDestroy(c->ev_stop);
     destroy_copy_events(c);
+    for (cudaStream_t &q : c->f3_streams) if (q) { cudaStreamDestroy(q); q = nullptr; }
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     c->magic = 0;
@@ -617,6 +618,12 @@ Parament_ErrorCode tree_reduce_all(Context *c, double2 *buf, int count, double2 
 }
 
 struct F3Plan { int S; int cap; };
+constexpr int kF3Streams = 4;
+int f3_stream_count() {   // chunks in flight (one stream and one work set each); $PARAMENT_F3_STREAMS = 1..4 for A/B runs
+    const char *env = getenv("PARAMENT_F3_STREAMS");
+    const int v = env ? atoi(env) : 4;   // measured at dim 256: 1 -> 3.82e4, 2 -> 4.21e4, 3 -> 4.24e4, 4 -> 4.28e4 steps/s
+    return v < 1 ? 1 : (v > kF3Streams ? kF3Streams : v);
+}
 
 // Chunk length S: a whole number of GEMM waves (S * tiles == k * co-resident CTAs: a launch that spills a few CTAs
 // into an extra wave costs a full wave) with the six S x npad^2 work arrays (Y, Y^2, Y^3, Y^4, two recurrence
@@ -644,8 +651,8 @@ int chain_grid(const Context *c, const CallSpec &s) {
 
 bool alloc_family3(Context *c, const F3Plan &f) {
     const size_t nn = (size_t)c->npad * c->npad;
-    return ensure_dev(c->d_Y, (size_t)kSeriesSlots * f.S * nn * sizeof(double2)) &&
-           ensure_dev(c->d_pending, (size_t)(f.cap + f.S) * nn * sizeof(double2)) &&
+    return ensure_dev(c->d_Y, (size_t)f3_stream_count() * kSeriesSlots * f.S * nn * sizeof(double2)) &&   // one chunk work set per stream
+           ensure_dev(c->d_pending, (size_t)2 * (f.cap + f.S) * nn * sizeof(double2)) &&   // two halves
            ensure_dev(c->d_tree, (size_t)((f.cap + f.S) / 2 + 1) * nn * sizeof(double2));
 }
 
@@ -676,7 +683,14 @@ Parament_ErrorCode run_family2(Context *c, const SeriesParams &p, const void *ca
     return PARAMENT_STATUS_SUCCESS;
 }
 
-// dim > 64: L2-resident time chunks, every series op one batched launch.
+// dim > 64: time chunks of one wave of CTAs, every series op one batched launch.  Consecutive chunks rotate over NS
+// work sets on NS streams: a launch is exactly one wave, so on one stream the SMs drain at the end of every launch and
+// refill at the start of the next (measured ~8 % of the time at dim 256); with other, independent chunks in flight the
+// CTAs of their launches take the slots as they free up.  The ordered product only needs the chunks' results in the
+// pending buffer in chunk order, which the host-side slot assignment fixes.  The pending buffer has two halves: while
+// the reduction of a full half runs on the caller's stream (its last levels are far smaller than a wave), the chunk
+// streams already fill the other half, whose slot 0 receives the reduced product as carry.
+// $PARAMENT_F3_STREAMS=1 keeps everything on one stream (A/B).
 Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *carr_dev, const CallSpec &s, void *out_dev, cudaStream_t st) {
     const int np = c->npad;
     const size_t nn = (size_t)np * np;
@@ -685,54 +699,110 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
     const F3Plan f = plan_family3(c, s);
     const int S = f.S, cap = f.cap;
     const SeriesProgram prog = build_program(p);
-    double2 *slots[kSeriesSlots];
-    for (int i = 0; i < kSeriesSlots; ++i) slots[i] = (double2 *)c->d_Y.ptr + (size_t)i * S * nn;
-    double2 *pend = (double2 *)c->d_pending.ptr, *tree = (double2 *)c->d_tree.ptr;
+    const int NS = (s.nsteps >= 4ull * S) ? f3_stream_count() : 1;
+    cudaStream_t sx[kF3Streams] = {st, nullptr, nullptr, nullptr};
+    if (NS > 1) {
+        sx[0] = c->copy_stream;
+        for (int k = 1; k < NS; ++k) {
+            if (!c->f3_streams[k - 1] && !PB_CUDA_OK(cudaStreamCreateWithFlags(&c->f3_streams[k - 1], cudaStreamNonBlocking)))
+                return PARAMENT_STATUS_CUBLAS_FAILED;
+            sx[k] = c->f3_streams[k - 1];
+        }
+    }
+    cudaEvent_t ev_main = c->ev_copy[0], *ev_chunk = c->ev_copy + 1, *ev_red = c->ev_copy + 1 + kF3Streams;
+    double2 *slots[kF3Streams][kSeriesSlots];
+    for (int k = 0; k < NS; ++k)
+        for (int i = 0; i < kSeriesSlots; ++i) slots[k][i] = (double2 *)c->d_Y.ptr + ((size_t)k * kSeriesSlots + i) * S * nn;
+    double2 *halves[2] = {(double2 *)c->d_pending.ptr, (double2 *)c->d_pending.ptr + (size_t)(cap + S) * nn};
+    double2 *tree = (double2 *)c->d_tree.ptr;
+    // the chunk streams start after everything already enqueued on the caller's stream (the H2D of the amplitudes, earlier pulses)
+    auto chunks_after_main = [&]() {
+        if (NS == 1) return true;
+        if (!PB_CUDA_OK(cudaEventRecord(ev_main, st))) return false;
+        for (int k = 0; k < NS; ++k)
+            if (!PB_CUDA_OK(cudaStreamWaitEvent(sx[k], ev_main, 0))) return false;
+        return true;
+    };
+    auto main_after_chunks = [&]() {
+        if (NS == 1) return true;
+        for (int k = 0; k < NS; ++k)
+            if (!PB_CUDA_OK(cudaEventRecord(ev_chunk[k], sx[k])) || !PB_CUDA_OK(cudaStreamWaitEvent(st, ev_chunk[k], 0))) return false;
+        return true;
+    };
     for (unsigned int b = 0; b < s.batch; ++b) {
         const char *cb = (const char *)carr_dev + (size_t)b * s.amps * s.stride * io;
-        int pending = 0;
-        for (unsigned long long step0 = 0; step0 < s.nsteps; step0 += S) {
+        if (!chunks_after_main()) return PARAMENT_STATUS_CUBLAS_FAILED;
+        bool wait_red[2][kF3Streams] = {};   // stream k must see the last reduction of that half finished before writing into it
+        int half = 0, pending = 0;
+        unsigned long long chunk = 0;
+        for (unsigned long long step0 = 0; step0 < s.nsteps; step0 += S, ++chunk) {
             const int Sc = (int)std::min<unsigned long long>(S, s.nsteps - step0);
-            PB_LAUNCH(k4_assemble(c->fp64, p, prog, cb, (const double2 *)c->d_H.ptr, slots[0], slots[4], slots[5], step0, Sc, st));
+            const int k = (int)(chunk % NS);
+            cudaStream_t q = sx[k];
+            double2 **sl = slots[k];
+            double2 *pend = halves[half];
+            if (wait_red[half][k]) {
+                if (!PB_CUDA_OK(cudaStreamWaitEvent(q, ev_red[half], 0))) return PARAMENT_STATUS_CUBLAS_FAILED;
+                wait_red[half][k] = false;
+            }
+            // no tree level inside the chunk (a level of a one-wave chunk does not fill a wave): the last series op writes
+            // its result where the ordered product will read it, instead of a device-to-device copy of the chunk
+            const bool direct = prog.nops > 0 && prog.ops[prog.nops - 1].D == prog.e_slot && !(Sc > 1 && (Sc / 2) * tiles >= c->k4_slots);
+            PB_LAUNCH(k4_assemble(c->fp64, p, prog, cb, (const double2 *)c->d_H.ptr, sl[0], sl[4], sl[5], step0, Sc, q));
             for (int o = 0; o < prog.nops; ++o) {
                 const SeriesOp &op = prog.ops[o];
                 GemmArgs g{};
-                g.A = slots[op.A]; g.B = slots[op.B]; g.D = slots[op.D];
-                g.Dprod = op.Dprod >= 0 ? slots[op.Dprod] : nullptr;
-                g.Dalt = op.Dalt >= 0 ? slots[op.Dalt] : nullptr;
+                g.A = sl[op.A]; g.B = sl[op.B]; g.D = sl[op.D];
+                g.Dprod = op.Dprod >= 0 ? sl[op.Dprod] : nullptr;
+                g.Dalt = op.Dalt >= 0 ? sl[op.Dalt] : nullptr;
                 g.strideA = g.strideB = g.strideD = g.strideDprod = g.strideDalt = (long long)nn;
                 for (int j = 0; j < kMaxAddends; ++j) {
-                    g.C[j] = op.C[j] >= 0 ? slots[op.C[j]] : nullptr; g.strideC[j] = (long long)nn;
+                    g.C[j] = op.C[j] >= 0 ? sl[op.C[j]] : nullptr; g.strideC[j] = (long long)nn;
                     g.beta[j] = op.beta[j]; g.beta_lo[j] = op.beta_lo[j]; g.beta_alt[j] = op.beta_alt[j];
                 }
                 g.alpha = op.alpha; g.scaled = op.scaled; g.gamma = op.gamma; g.gamma_lo = op.gamma_lo;
                 g.C2 = nullptr; g.beta2 = 0.0; g.n = np; g.batch = Sc;
-                PB_LAUNCH(k4_gemm(g, st));
+                if (direct && o == prog.nops - 1) g.D = pend + (size_t)pending * nn;   // E goes straight to the pending buffer
+                PB_LAUNCH(k4_gemm(g, q));
             }
-            // ordered product inside the chunk only while a level still fills a whole wave of CTAs; smaller levels are
-            // deferred to the pending buffer, whose reduction runs on hundreds of matrices at a time (full waves)
-            double2 *src = slots[prog.e_slot];
-            double2 *other = slots[prog.e_slot == 4 ? 5 : 4];
-            int count = Sc;
-            while (count > 1 && (count / 2) * tiles >= c->k4_slots) {
-                int nc = 0;
-                Parament_ErrorCode ec = tree_level(c, src, count, other, np, st, nc);
-                if (ec != PARAMENT_STATUS_SUCCESS) return ec;
-                std::swap(src, other);
-                count = nc;
+            if (direct) {
+                pending += Sc;
+            } else {
+                // ordered product inside the chunk only while a level still fills a whole wave of CTAs; smaller levels are
+                // deferred to the pending buffer, whose reduction runs on hundreds of matrices at a time (full waves)
+                double2 *src = sl[prog.e_slot];
+                double2 *other = sl[prog.e_slot == 4 ? 5 : 4];
+                int count = Sc;
+                while (count > 1 && (count / 2) * tiles >= c->k4_slots) {
+                    int nc = 0;
+                    Parament_ErrorCode ec = tree_level(c, src, count, other, np, q, nc);
+                    if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+                    std::swap(src, other);
+                    count = nc;
+                }
+                if (!PB_CUDA_OK(cudaMemcpyAsync(pend + (size_t)pending * nn, src, (size_t)count * nn * sizeof(double2), cudaMemcpyDeviceToDevice, q)))
+                    return PARAMENT_STATUS_CUBLAS_FAILED;
+                pending += count;
             }
-            if (!PB_CUDA_OK(cudaMemcpyAsync(pend + (size_t)pending * nn, src, (size_t)count * nn * sizeof(double2), cudaMemcpyDeviceToDevice, st)))
-                return PARAMENT_STATUS_CUBLAS_FAILED;
-            pending += count;
-            if (pending >= cap) {
+            if (pending >= cap && step0 + S < s.nsteps) {
+                // this half is full: reduce it on the caller's stream, carry the product into slot 0 of the other half
+                if (!main_after_chunks()) return PARAMENT_STATUS_CUBLAS_FAILED;
                 Parament_ErrorCode ec = tree_reduce_all(c, pend, pending, tree, np, st);
                 if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+                if (!PB_CUDA_OK(cudaMemcpyAsync(halves[half ^ 1], pend, nn * sizeof(double2), cudaMemcpyDeviceToDevice, st)))
+                    return PARAMENT_STATUS_CUBLAS_FAILED;
+                if (NS > 1) {
+                    if (!PB_CUDA_OK(cudaEventRecord(ev_red[half], st))) return PARAMENT_STATUS_CUBLAS_FAILED;
+                    for (int j = 0; j < NS; ++j) wait_red[half][j] = true;
+                }
+                half ^= 1;
                 pending = 1;
             }
         }
-        Parament_ErrorCode ec = tree_reduce_all(c, pend, pending, tree, np, st);
+        if (!main_after_chunks()) return PARAMENT_STATUS_CUBLAS_FAILED;
+        Parament_ErrorCode ec = tree_reduce_all(c, halves[half], pending, tree, np, st);
         if (ec != PARAMENT_STATUS_SUCCESS) return ec;
-        PB_LAUNCH(k4_finish(c->fp64, pend, c->dim, np, (char *)out_dev + (size_t)b * c->dim * c->dim * io, true, st));
+        PB_LAUNCH(k4_finish(c->fp64, halves[half], c->dim, np, (char *)out_dev + (size_t)b * c->dim * c->dim * io, true, st));
     }
     return PARAMENT_STATUS_SUCCESS;
 }
@@ -1356,6 +1426,7 @@ Parament_ErrorCode move_to_device(Context *c, int device) {
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
     free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
     cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); destroy_copy_events(c);
+    for (cudaStream_t &q : c->f3_streams) if (q) { cudaStreamDestroy(q); q = nullptr; }
     cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->stream);
     c->device = device;
     c->have_hamiltonian = false;

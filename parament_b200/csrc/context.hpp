@@ -17,14 +17,17 @@ struct DeviceBuffer {
     size_t bytes = 0;
 };
 
+constexpr int kCopyEvents = 8;
+
 struct Context {
     unsigned int magic = 0x50423230;   // "PB20"
     bool fp64 = false;                 // context precision of the I/O operands
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;        // H2D of the amplitude stream, overlapped with the kernels
-    cudaEvent_t ev_copy[8] = {};
+    cudaStream_t copy_stream = nullptr;        // H2D of the amplitude stream, overlapped with the kernels; second chunk stream of family 3
+    cudaStream_t f3_streams[3] = {};           // further chunk streams of family 3 (created on first use)
+    cudaEvent_t ev_copy[kCopyEvents] = {};     // copy groups of the host-pointer pipeline; fork / join / reduction events of family 3
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     Parament_ErrorCode lastError = PARAMENT_STATUS_SUCCESS;
 
