@@ -865,17 +865,35 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
                                             npts * sizeof(T), a1 - a0, cudaMemcpyHostToDevice, c->copy_stream));
     };
     if (s.batch > 1) {
-        const unsigned int bg = (s.batch + G - 1) / G;
-        // scratch for the larger of the two group sizes that occur (all groups hold bg pulses, the last one the remainder)
-        const unsigned int last = s.batch - (unsigned int)((s.batch - 1) / bg) * bg;
-        const K1Plan pa = plan_k1(c->npad, bg, s.nsteps, c->num_sms, horner), pl = plan_k1(c->npad, last, s.nsteps, c->num_sms, horner);
-        const size_t part_cap = std::max(pa.partial_elems, pl.partial_elems);
-        const size_t mid_cap = std::max(k3_mid_elems(c->npad, bg, pa.partials_per_pulse), k3_mid_elems(c->npad, last, pl.partials_per_pulse));
+        // Pulse groups sized in units of 1/8 wave of warps (a warp owns a pulse or 1/k of it, k <= 8: plan_k1), so that
+        // every group's launch is a whole number of equally long waves; sizes grow 1, 2, 4, ... units: the first copy
+        // is the only one no kernel hides, later groups are long enough to hide theirs behind the group before.
+        const unsigned int unit = std::max(1u, k1_warp_slots(c->npad, c->num_sms, horner) / 8);
+        unsigned int gb[9];
+        int ng = 0;
+        gb[0] = 0;
+        if (s.batch < 4 * unit) {   // less than half a wave: equal shares (the chain kernel then splits pulses over several warps)
+            const unsigned int bg = (s.batch + G - 1) / G;
+            for (unsigned int b0 = 0; b0 < s.batch; b0 += bg) gb[++ng] = std::min(s.batch, b0 + bg);
+        }
+        for (unsigned int size = unit; ng < G && gb[ng] < s.batch; size *= 2) {
+            const unsigned int left = s.batch - gb[ng];
+            // the last allowed group, or a remainder not worth a launch of its own, takes everything that is left
+            const unsigned int take = (ng == G - 1 || left < size + unit) ? left : size;
+            gb[ng + 1] = gb[ng] + take;
+            ++ng;
+            if (gb[ng] == s.batch) break;
+        }
+        size_t part_cap = 0, mid_cap = 0;
+        for (int g = 0; g < ng; ++g) {
+            const K1Plan pg = plan_k1(c->npad, gb[g + 1] - gb[g], s.nsteps, c->num_sms, horner);
+            part_cap = std::max(part_cap, pg.partial_elems);
+            mid_cap = std::max(mid_cap, k3_mid_elems(c->npad, gb[g + 1] - gb[g], pg.partials_per_pulse));
+        }
         if (!ensure_dev(c->d_partials, (part_cap + mid_cap) * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
         if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, c->stream))) return PARAMENT_STATUS_CUBLAS_FAILED;
-        int g = 0;
-        for (unsigned int b0 = 0; b0 < s.batch; b0 += bg, ++g) {
-            const unsigned int b1 = std::min(s.batch, b0 + bg);
+        for (int g = 0; g < ng; ++g) {
+            const unsigned int b0 = gb[g], b1 = gb[g + 1];
             if (!copy_arrays((size_t)b0 * s.amps, (size_t)b1 * s.amps, 0, seg) ||
                 !PB_CUDA_OK(cudaEventRecord(c->ev_copy[g], c->copy_stream)) || !PB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0)))
                 return PARAMENT_STATUS_CUBLAS_FAILED;
@@ -981,6 +999,7 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
     if (!ensure_dev(c->d_carr, in_bytes) || !ensure_dev(c->d_out, out_bytes)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
     // groups of >= 4 MB (and >= 16k steps along the time axis) for the copy / compute overlap of the register-resident family
     int G = (int)std::min<size_t>(8, in_bytes / ((size_t)4 << 20));
+    if (const char *e = getenv("PARAMENT_COPY_GROUPS")) G = std::max(1, std::min(8, atoi(e)));   // A/B runs
     if (batch == 1) G = (int)std::min<unsigned long long>(G, s.nsteps / 16384);
     else G = (int)std::min<unsigned int>(G, batch);
     Parament_ErrorCode ec;

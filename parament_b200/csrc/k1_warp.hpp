@@ -17,6 +17,7 @@ struct K1Plan {
 };
 
 K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms, bool horner);
+unsigned int k1_warp_slots(int npad, int num_sms, bool horner);   // co-resident warps of the chain kernel (one wave)
 
 // carr / out are device pointers in the context precision; Hfrag is the fragment-ordered matrix table.
 // The chain kernel (kernels 1+2) leaves plan.partials_per_pulse partial products per pulse at `partials`; the reduce
