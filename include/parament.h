@@ -198,7 +198,9 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  *  10 complex matrix products executed per effective step (series + ordered product)
  * Environment switches read at Parament_create (development / A-B testing): PARAMENT_SERIES=clenshaw forces the reference's
  * recurrence, PARAMENT_SERIES=horner the Horner / Paterson-Stockmeyer forms; PARAMENT_NO_ONCHIP=1 selects the L2-scratch
- * chain kernel for dim 17..64; PARAMENT_DEVICE the default CUDA device. */
+ * chain kernel for dim 17..64; PARAMENT_DEVICE the default CUDA device; PARAMENT_F3_STREAMS=1..4 the chunks in flight for dim > 64
+ * (default 4); PARAMENT_K4_FEED=tma the bulk-copy (TMA engine) operand feed of the batched GEMM (measured slower, default cp.async);
+ * PARAMENT_COPY_GROUPS=1..8 the copy/compute groups of the host-pointer pipeline. */
 PARAMENT_API double Parament_lastStat(void *handle, int key);
 
 /* Select the CUDA device a context lives on.  Must be called before setHamiltonian; default is device 0

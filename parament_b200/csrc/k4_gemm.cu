@@ -12,6 +12,8 @@
 // k4_zgemm_kernel       dim > 64: the same tile code as a batched launch over the S steps of an L2-resident time chunk.
 // k4_assemble_kernel    batched assembly Y_s = sigma (H0 + sum_t c_t(s) H_t) + series start values (fuses the reference's
 //                       outer-product broadcast, quadrature kernels and rank-A' GEMM, parament.cpp:491-554).
+#include <cstdlib>
+#include <cstring>
 #include "coef.cuh"
 #include "k4_gemm.hpp"
 
@@ -27,6 +29,28 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Bulk asynchronous copies (the TMA engine's 1-D path, SASS UBLKCP): one instruction moves a whole tile row into the
+// padded shared-memory layout and signals an mbarrier with the bytes it delivered.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();   // a lost copy must not hang the device
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem, const void *gmem, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(bar) : "memory");
+}
 
 template <int BM, int BN>
 struct K4Smem {
@@ -86,8 +110,11 @@ __device__ __forceinline__ void epilogue_pair(double (&vr)[2], double (&vi)[2], 
 }
 
 // All threads of the CTA call this; returns with every thread's part of D written (no trailing barrier).
-template <int BM, int BN, int WM, int WN>
-__device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int tile_m, int tile_n) {
+// FEED = 0: every thread issues 16-byte cp.async copies (commit / wait groups).  FEED = 1: warp 0 issues one bulk copy per
+// tile row (TMA engine) that completes on the stage's mbarrier `bars[stage]` (initialised by the caller, count 1; this
+// variant is called once per CTA, so stage s is filled for the (ks / STAGES)-th time in iteration ks).
+template <int BM, int BN, int WM, int WN, int FEED = 0>
+__device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int tile_m, int tile_n, unsigned long long *bars = nullptr) {
     using SM = K4Smem<BM, BN>;
     constexpr int NTHREADS = (BM / WM) * (BN / WN) * 32;
     constexpr int MT = WM / 8, NTL = WN / 8;
@@ -116,19 +143,41 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
 #pragma unroll
         for (int nt = 0; nt < NTL; ++nt) { cre[mt][nt][0] = cre[mt][nt][1] = 0.0; cim[mt][nt][0] = cim[mt][nt][1] = 0.0; }
 
+    const unsigned bar0 = FEED ? smem_u32(bars) : 0u;
+    auto load_stage_bulk = [&](int stage, int k0) {   // warp 0, all lanes
+        double2 *sA = smem + stage * SM::STAGE_ELEMS;
+        double2 *sB = sA + SM::A_ELEMS;
+        const unsigned bar = bar0 + 8u * stage;
+        if (lane == 0) mbar_expect_tx(bar, (unsigned)((BM * K4_BK + K4_BK * BN) * sizeof(double2)));
+        __syncwarp();
+        for (int r = lane; r < BM; r += 32) bulk_copy_g2s(sA + r * SM::PA, A + (size_t)r * g.n + k0, K4_BK * sizeof(double2), bar);
+        for (int r = lane; r < K4_BK; r += 32) bulk_copy_g2s(sB + r * SM::PB, B + (size_t)(k0 + r) * g.n, BN * sizeof(double2), bar);
+    };
+
     const int nk = g.n / K4_BK;
+    if (FEED) {
+        if (warp == 0)
+            for (int s = 0; s < K4_STAGES - 1; ++s)
+                if (s < nk) load_stage_bulk(s, s * K4_BK);
+    } else {
 #pragma unroll
-    for (int s = 0; s < K4_STAGES - 1; ++s) {
-        if (s < nk) load_stage(s, s * K4_BK);
-        cp_async_commit();
+        for (int s = 0; s < K4_STAGES - 1; ++s) {
+            if (s < nk) load_stage(s, s * K4_BK);
+            cp_async_commit();
+        }
     }
     for (int ks = 0; ks < nk; ++ks) {
-        cp_async_wait<K4_STAGES - 2>();
+        if (FEED) mbar_wait(bar0 + 8u * (ks % K4_STAGES), (unsigned)(ks / K4_STAGES) & 1u);
+        else cp_async_wait<K4_STAGES - 2>();
         __syncthreads();
         {   // prefetch stage ks + STAGES - 1 into the buffer consumed in iteration ks - 1
             const int nxt = ks + K4_STAGES - 1;
-            if (nxt < nk) load_stage(nxt % K4_STAGES, nxt * K4_BK);
-            cp_async_commit();
+            if (FEED) {
+                if (warp == 0 && nxt < nk) load_stage_bulk(nxt % K4_STAGES, nxt * K4_BK);
+            } else {
+                if (nxt < nk) load_stage(nxt % K4_STAGES, nxt * K4_BK);
+                cp_async_commit();
+            }
         }
         const double2 *sA = smem + (ks % K4_STAGES) * SM::STAGE_ELEMS;
         const double2 *sB = sA + SM::A_ELEMS;
@@ -154,7 +203,7 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
             }
         }
     }
-    cp_async_wait<0>();
+    if (!FEED) cp_async_wait<0>();
     __syncthreads();   // every warp is done with the stage buffers: the next tile_gemm may refill them
 
     // ---- epilogue ----
@@ -202,11 +251,20 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
         }
 }
 
-template <int BM, int BN, int WM, int WN>
+template <int BM, int BN, int WM, int WN, int FEED = 0>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 k4_zgemm_kernel(const GemmArgs g) {
     extern __shared__ __align__(16) unsigned char k4_smem_raw[];
     double2 *smem = reinterpret_cast<double2 *>(k4_smem_raw);
+    __shared__ __align__(8) unsigned long long bars[K4_STAGES];
+    if (FEED) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < K4_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        }
+        __syncthreads();
+    }
     const long long b = blockIdx.y;
     const int tiles_n = g.n / BN;
     TileArgs t;
@@ -226,7 +284,7 @@ k4_zgemm_kernel(const GemmArgs g) {
     t.alpha = g.alpha; t.scaled = g.scaled;
     t.beta2 = g.beta2; t.gamma = g.gamma; t.gamma_lo = g.gamma_lo;
     t.n = g.n;
-    tile_gemm<BM, BN, WM, WN>(smem, t, blockIdx.x / tiles_n, blockIdx.x % tiles_n);
+    tile_gemm<BM, BN, WM, WN, FEED>(smem, t, blockIdx.x / tiles_n, blockIdx.x % tiles_n, bars);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -527,10 +585,16 @@ static cudaError_t opt_in_smem(K kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// operand feed of the batched GEMM: 0 = cp.async by all threads, 1 = bulk copies (TMA engine) by one warp + mbarriers
+static int k4_feed_mode() {
+    static const int mode = [] { const char *e = getenv("PARAMENT_K4_FEED"); return e ? (strcmp(e, "tma") == 0 ? 1 : 0) : 0; }();
+    return mode;
+}
+
 template <int BM, int BN, int WM, int WN>
 static cudaError_t launch_gemm_t(const GemmArgs &g, cudaStream_t stream) {
     using SM = K4Smem<BM, BN>;
-    auto kern = k4_zgemm_kernel<BM, BN, WM, WN>;
+    auto kern = k4_feed_mode() ? k4_zgemm_kernel<BM, BN, WM, WN, 1> : k4_zgemm_kernel<BM, BN, WM, WN, 0>;
     cudaError_t e = opt_in_smem(kern, SM::BYTES);   // per-device function attribute; cheap, so set on every launch
     if (e != cudaSuccess) return e;
     // (programmatic dependent launch was measured here: 2.78e4 -> 2.50e4 steps/s at dim 256, so plain stream order is kept)
