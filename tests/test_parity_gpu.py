@@ -484,3 +484,40 @@ def test_error_growth_is_not_linear_in_steps(pb):
             U = ctx.equiprop(w.dt, *w.carr)
         errs[pts] = rel_frobenius(U, equiprop_oracle(w.H0, w.H1, w.carr, w.dt, "simpson", False, "fp32", workers=4))
     assert max(errs.values()) < 2e-6, errs
+
+
+def test_bulk_copy_operand_feed_variant(tmp_path):
+    """$PARAMENT_K4_FEED=tma: the batched GEMM fed by bulk copies (TMA engine) + mbarriers instead of cp.async (DESIGN.md 7.3:
+    measured slower, kept as the A/B alternative).  Read once per process, hence a subprocess; same results required."""
+    import subprocess
+    import sys
+    import textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f"""
+        import sys, numpy as np
+        sys.path.insert(0, {root!r})
+        import parament_b200 as pb
+        from parament_b200.workloads import make_workload
+        for name, pts in (("C4", 150), ("C3", 300)):
+            w = make_workload(name, pts=pts)
+            H0, H1 = w.H0, w.H1
+            if name == "C3":                      # C3's pulse on a dim-96 system: zero-padded to 128 in the batched pipeline
+                rng = np.random.default_rng(5)
+                from parament_b200.workloads import rand_herm
+                H0 = (0.5 * rand_herm(rng, 96)).astype(np.complex128)
+                H1 = np.stack([(0.125 * rand_herm(rng, 96)).astype(np.complex128) for _ in range(4)])
+            with pb.Parament("fp64") as ctx:
+                ctx.set_hamiltonian(H0, *H1, quadrature_mode="none")
+                U = ctx.equiprop(w.dt, *w.carr)
+                assert ctx.stat(5) == 3
+            np.save({str(tmp_path)!r} + "/" + name + ".npy", U)
+            np.savez({str(tmp_path)!r} + "/" + name + "_in.npz", H0=H0, H1=H1, carr=w.carr, dt=w.dt)
+    """)
+    env = dict(os.environ, PARAMENT_K4_FEED="tma")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for name in ("C4", "C3"):
+        U = np.load(tmp_path / f"{name}.npy")
+        d = np.load(tmp_path / f"{name}_in.npz")
+        Uo = equiprop_oracle(d["H0"], d["H1"], d["carr"], float(d["dt"]), "none", False, "fp64")
+        assert rel_frobenius(U, Uo) < 1e-12

@@ -7,7 +7,8 @@ import parament_b200 as pb
 from parament_b200.workloads import make_workload
 from oracle.equiprop_oracle import equiprop_oracle, rel_frobenius
 
-for name, kw in (("C2", dict(pts=4001)), ("C5", dict(pts=101, batch=40)), ("C1", dict(pts=501)), ("C3", dict(pts=41))):
+# C4 pts=700: the four-stream chunk pipeline with both halves of the pending list in use (cap + carry)
+for name, kw in (("C2", dict(pts=4001)), ("C5", dict(pts=101, batch=40)), ("C1", dict(pts=501)), ("C3", dict(pts=41)), ("C4", dict(pts=700))):
     w = make_workload(name, **kw)
     with pb.Parament(w.precision) as ctx:
         ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=w.use_magnus, quadrature_mode=w.quadrature)
@@ -15,3 +16,12 @@ for name, kw in (("C2", dict(pts=4001)), ("C5", dict(pts=101, batch=40)), ("C1",
         c0 = w.carr[0] if w.batch > 1 else w.carr
         Uo = equiprop_oracle(w.H0, w.H1, c0, w.dt, w.quadrature, w.use_magnus, w.precision)
         print(name, "series mode", int(ctx.stat(9)), "family", int(ctx.stat(5)), "err", rel_frobenius(U[0], Uo), flush=True)
+
+# single-process multi-device mode on one GPU (device 0 listed three times): threads, peer copies, combine
+w = make_workload("C3", pts=900)
+with pb.Parament("fp64") as ctx:
+    ctx.set_devices([0, 0, 0])
+    ctx.set_hamiltonian(w.H0, *w.H1, quadrature_mode="none")
+    U = ctx.equiprop(w.dt, *w.carr)
+    Uo = equiprop_oracle(w.H0, w.H1, w.carr, w.dt, "none", False, "fp64")
+    print("multi-device", int(ctx.stat(11)), "err", rel_frobenius(U, Uo), flush=True)
