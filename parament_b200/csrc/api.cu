@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <functional>
 #include <new>
 #include <thread>
 #include <vector>
@@ -131,6 +132,7 @@ void destroy_peers(Context *c);
 Parament_ErrorCode destroy_ctx(Context *c) {
     if (!c) return PARAMENT_STATUS_SUCCESS;   // NULL is a no-op (parament.cpp:190-191)
     destroy_peers(c);
+    if (c->worker) { c->worker->stop(); delete c->worker; c->worker = nullptr; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_dev(c->d_gather);
@@ -1004,8 +1006,12 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
     else G = (int)std::min<unsigned int>(G, batch);
     Parament_ErrorCode ec;
     c->stat_h2d = (double)in_bytes;
+    // shared call: the last kernel of this device stores its partial straight into the gather buffer on the first device
+    // (plain stores over NVLink peer memory) when that memory is addressable from here, else a peer copy follows
+    const bool direct_store = gather_to && (gather_to == c || c->peer_store_ok);
+    void *result_dev = direct_store ? (void *)((T *)gather_to->d_gather.ptr + (size_t)slot * n * n) : c->d_out.ptr;
     if (c->family == 1 && G >= 2) {
-        ec = pipelined_family1<T>(c, carr, pts, p_lo, seg, s, G, c->d_out.ptr);
+        ec = pipelined_family1<T>(c, carr, pts, p_lo, seg, s, G, result_dev);
     } else {
         if (seg == pts) {
             if (in_bytes && !PB_CUDA_OK(cudaMemcpyAsync(c->d_carr.ptr, carr, in_bytes, cudaMemcpyHostToDevice, c->stream)))
@@ -1015,12 +1021,12 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
                                               cudaMemcpyHostToDevice, c->stream)))
                 return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
         }
-        ec = propagate_device(c, c->d_carr.ptr, s, c->d_out.ptr, c->stream);
+        ec = propagate_device(c, c->d_carr.ptr, s, result_dev, c->stream);
     }
     if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
     if (gather_to) {
-        if (!PB_CUDA_OK(cudaMemcpyPeerAsync((T *)gather_to->d_gather.ptr + (size_t)slot * n * n, gather_to->device, c->d_out.ptr, c->device,
-                                            out_bytes, c->stream)) ||
+        if ((!direct_store && !PB_CUDA_OK(cudaMemcpyPeerAsync((T *)gather_to->d_gather.ptr + (size_t)slot * n * n, gather_to->device,
+                                                               c->d_out.ptr, c->device, out_bytes, c->stream))) ||
             !PB_CUDA_OK(cudaStreamSynchronize(c->stream)))
             return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
         c->lastError = PARAMENT_STATUS_SUCCESS;
@@ -1139,33 +1145,24 @@ Parament_ErrorCode equiprop_multi(Context *c, const T *carr, double dt, unsigned
     const size_t nn = (size_t)n * n;
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<Parament_ErrorCode> ecs(G, PARAMENT_STATUS_SUCCESS);
-    std::vector<std::thread> workers;
     auto ctx_of = [&](unsigned int g) { return g == 0 ? c : c->peers[g - 1]; };
-    try {
-        workers.reserve(G);
-        if (batch == 1) {
-            cudaSetDevice(c->device);
-            if (!ensure_dev(c->d_gather, (size_t)G * nn * sizeof(T))) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
-            auto run = [&](unsigned int g) {
-                ecs[g] = equiprop_host<T>(ctx_of(g), carr, dt, pts, amps, 1, N * g / G, N * (g + 1) / G, false, out, c, g);
-            };
-            for (unsigned int g = 1; g < G; ++g) workers.emplace_back(run, g);
-            run(0);
-        } else {
-            // whole = false with the full step range [0, N): neither this context nor a helper shares the work again
-            auto run_range = [&](unsigned int g) {
-                const size_t b0 = (size_t)batch * g / G, b1 = (size_t)batch * (g + 1) / G;
-                ecs[g] = equiprop_host<T>(ctx_of(g), carr + b0 * amps * pts, dt, pts, amps, (unsigned int)(b1 - b0), 0, N, false, out + b0 * nn);
-            };
-            for (unsigned int g = 1; g < G; ++g) workers.emplace_back(run_range, g);
-            run_range(0);
-        }
-    } catch (...) {   // thread creation failed: finish what was started, report a host-side failure
-        for (auto &w : workers) if (w.joinable()) w.join();
+    std::function<void(unsigned int)> run;
+    if (batch == 1) {
         cudaSetDevice(c->device);
-        return fail(c, PARAMENT_STATUS_HOST_ALLOC_FAILED);
+        if (!ensure_dev(c->d_gather, (size_t)G * nn * sizeof(T))) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
+        run = [&](unsigned int g) {
+            ecs[g] = equiprop_host<T>(ctx_of(g), carr, dt, pts, amps, 1, N * g / G, N * (g + 1) / G, false, out, c, g);
+        };
+    } else {
+        // whole = false with the full step range [0, N): neither this context nor a helper shares the work again
+        run = [&](unsigned int g) {
+            const size_t b0 = (size_t)batch * g / G, b1 = (size_t)batch * (g + 1) / G;
+            ecs[g] = equiprop_host<T>(ctx_of(g), carr + b0 * amps * pts, dt, pts, amps, (unsigned int)(b1 - b0), 0, N, false, out + b0 * nn);
+        };
     }
-    for (auto &w : workers) w.join();
+    for (unsigned int g = 1; g < G; ++g) ctx_of(g)->worker->submit([&run, g] { run(g); });   // fits std::function's inline storage
+    run(0);
+    for (unsigned int g = 1; g < G; ++g) ctx_of(g)->worker->wait();
     cudaSetDevice(c->device);
     long long launches = 0;
     double h2d = 0;
@@ -1218,6 +1215,16 @@ Parament_ErrorCode set_device_list(Context *c, const int *devices, int count) {
         if (ec == PARAMENT_STATUS_SUCCESS) {
             p->is_peer = true;
             ec = replay_hamiltonian(c, p);
+            if (ec == PARAMENT_STATUS_SUCCESS) {
+                try {
+                    p->worker = new DeviceWorker();
+                    p->worker->start();
+                } catch (...) {
+                    delete p->worker;
+                    p->worker = nullptr;
+                    ec = PARAMENT_STATUS_HOST_ALLOC_FAILED;
+                }
+            }
             if (ec != PARAMENT_STATUS_SUCCESS) destroy_ctx(p);
         }
         if (ec != PARAMENT_STATUS_SUCCESS) {
@@ -1226,11 +1233,13 @@ Parament_ErrorCode set_device_list(Context *c, const int *devices, int count) {
             return fail(c, ec);
         }
         c->peers.push_back(p);
-        if (devices[i] != c->device) {   // direct NVLink path for the partials; "already enabled" / "unsupported" are both fine
+        p->peer_store_ok = devices[i] == c->device;
+        if (devices[i] != c->device) {   // direct NVLink path for the partials: the helper's kernels store into this device's memory
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, devices[i], c->device) == cudaSuccess && can) {
                 cudaSetDevice(devices[i]);
-                cudaDeviceEnablePeerAccess(c->device, 0);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(c->device, 0);
+                p->peer_store_ok = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
             }
             cudaGetLastError();
         }

@@ -2,7 +2,11 @@
 // holds a cuBLAS handle and three dim^2 x pts work arrays; none of that exists here).
 #pragma once
 #include <complex>
+#include <condition_variable>
 #include <cstddef>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/parament.h"
@@ -18,6 +22,45 @@ struct DeviceBuffer {
 };
 
 constexpr int kCopyEvents = 8;
+
+// Host thread that drives one helper device of the single-process multi-GPU mode: it lives as long as the helper context,
+// so a shared call costs two condition-variable hand-offs per device instead of a thread creation.
+struct DeviceWorker {
+    std::thread thread;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, done = false, quit = false;
+
+    void start() { thread = std::thread([this] { run(); }); }
+    void run() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [this] { return has_job || quit; });
+            if (quit) return;
+            lk.unlock();
+            job();
+            lk.lock();
+            has_job = false;
+            done = true;
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<void()> f) {
+        { std::lock_guard<std::mutex> lk(m); job = std::move(f); has_job = true; done = false; }
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return done; });
+    }
+    void stop() {
+        if (!thread.joinable()) return;
+        { std::lock_guard<std::mutex> lk(m); quit = true; }
+        cv.notify_all();
+        thread.join();
+    }
+};
 
 struct Context {
     unsigned int magic = 0x50423230;   // "PB20"
@@ -61,6 +104,8 @@ struct Context {
     // device reduces its share on its own stream, partials arrive by peer copy and are combined in order here.
     std::vector<Context *> peers;
     bool is_peer = false;
+    bool peer_store_ok = false;     // helper: its kernels may store into the first device's memory (same device or peer access)
+    DeviceWorker *worker = nullptr; // helper: the host thread that drives this device
     int stat_devices = 1;           // devices that took part in the last equiprop
     void *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for carr
     void *h_out = nullptr;   size_t h_out_bytes = 0;    // pinned staging for results
