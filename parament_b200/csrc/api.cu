@@ -870,22 +870,8 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
         // Pulse groups sized in units of 1/8 wave of warps (a warp owns a pulse or 1/k of it, k <= 8: plan_k1), so that
         // every group's launch is a whole number of equally long waves; sizes grow 1, 2, 4, ... units: the first copy
         // is the only one no kernel hides, later groups are long enough to hide theirs behind the group before.
-        const unsigned int unit = std::max(1u, k1_warp_slots(c->npad, c->num_sms, horner) / 8);
         unsigned int gb[9];
-        int ng = 0;
-        gb[0] = 0;
-        if (s.batch < 4 * unit) {   // less than half a wave: equal shares (the chain kernel then splits pulses over several warps)
-            const unsigned int bg = (s.batch + G - 1) / G;
-            for (unsigned int b0 = 0; b0 < s.batch; b0 += bg) gb[++ng] = std::min(s.batch, b0 + bg);
-        }
-        for (unsigned int size = unit; ng < G && gb[ng] < s.batch; size *= 2) {
-            const unsigned int left = s.batch - gb[ng];
-            // the last allowed group, or a remainder not worth a launch of its own, takes everything that is left
-            const unsigned int take = (ng == G - 1 || left < size + unit) ? left : size;
-            gb[ng + 1] = gb[ng] + take;
-            ++ng;
-            if (gb[ng] == s.batch) break;
-        }
+        const int ng = ensemble_copy_groups(s.batch, std::max(1u, k1_warp_slots(c->npad, c->num_sms, horner) / 8), G, gb);   // plan.hpp
         size_t part_cap = 0, mid_cap = 0;
         for (int g = 0; g < ng; ++g) {
             const K1Plan pg = plan_k1(c->npad, gb[g + 1] - gb[g], s.nsteps, c->num_sms, horner);
@@ -912,10 +898,7 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
         K1Plan plans[8];
         size_t off[9];
         off[0] = 0;
-        // a short first group (a quarter share): its copy is the only one no kernel hides
-        bound[0] = 0;
-        bound[1] = s.nsteps / (4ull * G);
-        for (int g = 2; g <= G; ++g) bound[g] = bound[1] + (s.nsteps - bound[1]) * (unsigned long long)(g - 1) / (G - 1);
+        time_copy_groups(s.nsteps, G, bound);   // plan.hpp: a short first group, its copy is the only one no kernel hides
         for (int g = 0; g < G; ++g) {
             plans[g] = plan_k1(c->npad, 1, bound[g + 1] - bound[g], c->num_sms, horner);
             off[g + 1] = off[g] + plans[g].partials_per_pulse;
@@ -1125,20 +1108,13 @@ Parament_ErrorCode combine_device(Context *c, const void *parts_dev, unsigned in
 // to the first device by peer copy and are multiplied in order there (combine_device_core).  An ensemble: the pulses
 // are cut into contiguous ranges, no exchange at all.  Work that is too small to share stays on one device.
 // ---------------------------------------------------------------------------------------------------
-unsigned long long min_steps_per_device(const Context *c) {
-    const unsigned long long np3 = (unsigned long long)c->npad * c->npad * c->npad;
-    return std::max<unsigned long long>(64, (1ull << 26) / std::max<unsigned long long>(np3, 1));
-}
-
 template <typename T>
 Parament_ErrorCode equiprop_multi(Context *c, const T *carr, double dt, unsigned int pts, unsigned int amps, unsigned int batch, T *out,
                                   bool &handled) {
     handled = false;
     if (!c->have_hamiltonian || !carr || !out || (int)amps > c->amps || batch == 0 || c->Hnorm == 0.0) return PARAMENT_STATUS_SUCCESS;
     const unsigned long long N = effective_steps(c, pts);
-    const unsigned long long work = N * batch, share_min = min_steps_per_device(c);
-    unsigned int G = (unsigned int)std::min<unsigned long long>(c->peers.size() + 1, work / share_min);
-    if (batch > 1) G = std::min(G, batch);
+    const unsigned int G = devices_for_call((unsigned int)c->peers.size() + 1, batch, N, c->npad);   // plan.hpp
     if (G < 2) return PARAMENT_STATUS_SUCCESS;   // not worth sharing: the caller runs it on the first device
     handled = true;
     const int n = c->dim;

@@ -33,7 +33,6 @@ namespace pb {
 #define K1_T_PRINT
 #endif
 
-constexpr int K1_WARPS = 4;   // warps per CTA of the chain kernel
 
 // Ordered in-CTA product: afterwards warp 0 holds Q_0 Q_1 ... Q_{nwarps-1}.  smem: (nwarps/2) matrices.
 template <int NT>
@@ -464,61 +463,6 @@ static cudaError_t launch_chain_t(const SeriesParams &p, const IO *carr, const d
                     : launch_chain_tt<NT, IO, 0>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
 }
 
-int k3_warps_for(unsigned int partials_per_pulse);
-
-static int k1_ctas_per_sm(int npad, bool horner) {
-    static const int occ_env = getenv("PARAMENT_K1_OCC") ? atoi(getenv("PARAMENT_K1_OCC")) : 0;
-    return (npad == 8) ? 6 : (occ_env == 2 || occ_env == 3 ? occ_env : (horner ? 2 : 3));
-}
-
-unsigned int k1_warp_slots(int npad, int num_sms, bool horner) {
-    return (unsigned int)(num_sms * k1_ctas_per_sm(npad, horner) * K1_WARPS);
-}
-
-K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms, bool horner) {
-    K1Plan plan{};
-    const int ctas_per_sm = k1_ctas_per_sm(npad, horner);
-    plan.ctas_per_sm = ctas_per_sm;
-    const unsigned long long warps_total = (unsigned long long)num_sms * ctas_per_sm * K1_WARPS;
-    if (batch >= warps_total / 2 || nsteps < 2ull * K1_WARPS) {
-        // A warp owns a whole pulse -- or 1/k of it where that evens out the waves: all warps take equally long, so
-        // batch / warps_total = 2.8 costs three full waves with k = 1 but 17/6 = 2.83 with k = 6.
-        // The kernel is bound by the FP64 pipe of the SM, not by latency, so what matters is that every SM gets the same
-        // number of CTAs, and that CTAs are short: measured at dim 8 (3552 pulses of 1000 steps = exactly six CTAs per SM
-        // with k = 1): k = 1 2.654 ms, 2 2.532, 4 2.475, 8 2.450 -- about 0.91 + 0.09 / k.
-        unsigned int best_k = 1;
-        double best = 1e300;
-        for (unsigned int k = 1; k <= 8; ++k) {
-            if (k > 1 && nsteps / k < 64) break;
-            const double ctas = std::ceil((double)batch * k / K1_WARPS);
-            const double imbalance = std::ceil(ctas / num_sms) / (ctas / num_sms);
-            const double cost = imbalance * (0.91 + 0.09 / k);
-            if (cost < best * 0.999) { best = cost; best_k = k; }
-        }
-        static const int k_env = getenv("PARAMENT_K1_K") ? atoi(getenv("PARAMENT_K1_K")) : 0;   // A/B runs
-        if (k_env >= 1 && k_env <= 8 && nsteps / k_env >= 64) best_k = (unsigned int)k_env;
-        plan.chunks_per_pulse = best_k;
-        plan.reduce_in_cta = 0;
-        plan.partials_per_pulse = best_k;
-    } else {
-        static const int waves_env = getenv("PARAMENT_K1_WAVES") ? atoi(getenv("PARAMENT_K1_WAVES")) : 0;   // A/B runs
-        const unsigned long long rounds = waves_env >= 1 && waves_env <= 16 ? waves_env : 1;
-        unsigned long long ctas_per_pulse = (rounds * (warps_total / K1_WARPS) + batch - 1) / batch;
-        // keep at least ~8 steps per warp so the identity-start product stays a small fraction
-        const unsigned long long max_ctas = (nsteps / 8 + K1_WARPS - 1) / K1_WARPS;
-        if (ctas_per_pulse > max_ctas) ctas_per_pulse = max_ctas;
-        if (ctas_per_pulse < 1) ctas_per_pulse = 1;
-        plan.chunks_per_pulse = (unsigned int)(ctas_per_pulse * K1_WARPS);
-        plan.reduce_in_cta = 1;
-        plan.partials_per_pulse = (unsigned int)ctas_per_pulse;
-    }
-    const unsigned long long total_warps = (unsigned long long)batch * plan.chunks_per_pulse;
-    plan.grid = (unsigned int)((total_warps + K1_WARPS - 1) / K1_WARPS);
-    plan.k3_warps = k3_warps_for(plan.partials_per_pulse);
-    plan.partial_elems = (size_t)batch * plan.partials_per_pulse * npad * npad;
-    return plan;
-}
-
 cudaError_t launch_k1_chain(int npad, bool fp64_io, const SeriesParams &p, const void *carr, const double2 *Hfrag,
                             double2 *partials, unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
                             unsigned long long step_hi, cudaStream_t stream) {
@@ -555,13 +499,5 @@ cudaError_t launch_k3_reduce(int npad, bool fp64_io, const double2 *partials, un
     return fp64_io ? launch_k3_t<2, double2>(partials, partials_per_pulse, n, mid, (double2 *)out, batch, stream)
                    : launch_k3_t<2, float2>(partials, partials_per_pulse, n, mid, (float2 *)out, batch, stream);
 }
-
-size_t k3_mid_elems(int npad, unsigned int batch, unsigned int partials_per_pulse) {
-    return partials_per_pulse > 32 ? (size_t)batch * ((partials_per_pulse + 15) / 16) * npad * npad : 0;
-}
-
-int k3_launches(unsigned int partials_per_pulse) { return partials_per_pulse > 32 ? 2 : 1; }
-
-int k3_warps_for(unsigned int partials_per_pulse) { return partials_per_pulse >= 16 ? 8 : (partials_per_pulse >= 4 ? 4 : 1); }
 
 }  // namespace pb

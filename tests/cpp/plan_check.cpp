@@ -1,0 +1,47 @@
+// CPU checker for parament_b200/csrc/plan.hpp: prints the partitions as JSON lines for tests/test_plan.py.
+//   plan_check k1 npad batch nsteps num_sms horner
+//   plan_check egroups batch unit G
+//   plan_check tgroups nsteps G
+//   plan_check devices configured batch nsteps npad
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "plan.hpp"
+
+int main(int argc, char **argv) {
+    if (argc < 2) return 2;
+    using namespace pb;
+    if (!strcmp(argv[1], "k1") && argc == 7) {
+        const K1Plan p = plan_k1(atoi(argv[2]), (unsigned)atoll(argv[3]), strtoull(argv[4], nullptr, 10), atoi(argv[5]), atoi(argv[6]) != 0);
+        printf("{\"grid\": %u, \"chunks_per_pulse\": %u, \"partials_per_pulse\": %u, \"reduce_in_cta\": %d, \"k3_warps\": %d, "
+               "\"ctas_per_sm\": %d, \"partial_elems\": %zu, \"warp_slots\": %u, \"mid_elems\": %zu, \"k3_launches\": %d}\n",
+               p.grid, p.chunks_per_pulse, p.partials_per_pulse, p.reduce_in_cta, p.k3_warps, p.ctas_per_sm, p.partial_elems,
+               k1_warp_slots(atoi(argv[2]), atoi(argv[5]), atoi(argv[6]) != 0),
+               k3_mid_elems(atoi(argv[2]), (unsigned)atoll(argv[3]), p.partials_per_pulse), k3_launches(p.partials_per_pulse));
+        return 0;
+    }
+    if (!strcmp(argv[1], "egroups") && argc == 5) {
+        unsigned int gb[9];
+        const int ng = ensemble_copy_groups((unsigned)atoll(argv[2]), (unsigned)atoll(argv[3]), atoi(argv[4]), gb);
+        printf("[");
+        for (int g = 0; g <= ng; ++g) printf("%s%u", g ? ", " : "", gb[g]);
+        printf("]\n");
+        return 0;
+    }
+    if (!strcmp(argv[1], "tgroups") && argc == 4) {
+        unsigned long long b[9];
+        const int G = atoi(argv[3]);
+        time_copy_groups(strtoull(argv[2], nullptr, 10), G, b);
+        printf("[");
+        for (int g = 0; g <= (G < 1 ? 1 : G); ++g) printf("%s%llu", g ? ", " : "", b[g]);
+        printf("]\n");
+        return 0;
+    }
+    if (!strcmp(argv[1], "devices") && argc == 6) {
+        printf("{\"devices\": %u, \"min_steps\": %llu}\n",
+               devices_for_call((unsigned)atoll(argv[2]), (unsigned)atoll(argv[3]), strtoull(argv[4], nullptr, 10), atoi(argv[5])),
+               min_steps_per_device(atoi(argv[5])));
+        return 0;
+    }
+    return 2;
+}
