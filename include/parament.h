@@ -196,10 +196,12 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  *   9 series evaluation (0 Clenshaw recurrence, 1 Horner in Y^2, 2 Paterson-Stockmeyer blocks of four,
  *                        3 degree 8 in three products, 4 degree 12 in four products -- all the same polynomial family)
  *  10 complex matrix products executed per effective step (series + ordered product)
+ *  13 real matrix products per complex product in the kernel family used (4; 3 for the batched GEMM of dim > 64)
  * Environment switches read at Parament_create (development / A-B testing): PARAMENT_SERIES=clenshaw forces the reference's
  * recurrence, PARAMENT_SERIES=horner the Horner / Paterson-Stockmeyer forms; PARAMENT_NO_ONCHIP=1 selects the L2-scratch
  * chain kernel for dim 17..64; PARAMENT_DEVICE the default CUDA device; PARAMENT_F3_STREAMS=1..4 the chunks in flight for dim > 64
- * (default 4); PARAMENT_K4_FEED=tma the bulk-copy (TMA engine) operand feed of the batched GEMM (measured slower, default cp.async);
+ * (default 4); PARAMENT_K4_3M=0..3 the complex product of the batched GEMM (0: four real products on 64x64 tiles; 3, default: three real
+ * products on 64x32 tiles); PARAMENT_K4_FEED=tma the bulk-copy (TMA engine) operand feed of that GEMM in mode 0 (measured slower than cp.async);
  * PARAMENT_COPY_GROUPS=1..8 the copy/compute groups of the host-pointer pipeline. */
 PARAMENT_API double Parament_lastStat(void *handle, int key);
 

@@ -1400,6 +1400,7 @@ double Parament_lastStat(void *h, int key) {
             if (c->stat_horner == 1 && c->family == 2 && c->onchip && (M == 8 || M >= 10)) return 3.0 + M / 3;   // blocks of three
             return c->stat_horner ? 2.0 + (M >> 1) : (double)std::max(M, 1);
         }
+        case 13: return c->family == 3 ? k4_real_products(c->npad) : 4;   // real products per complex matrix product
         case 11: return c->stat_devices;
         case 12: return (double)c->peers.size() + 1.0;
         default: return -1.0;

@@ -52,14 +52,14 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem, const void *gmem, unsi
                  ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int BM, int BN>
+template <int BM, int BN, int STAGES = K4_STAGES>
 struct K4Smem {
     static constexpr int PA = K4_BK + 4;   // pitch of the A tile in double2: 8 lanes of an LDS.128 phase hit 8 bank groups
     static constexpr int PB = BN + 2;      // pitch of the B tile
     static constexpr int A_ELEMS = BM * PA;
     static constexpr int B_ELEMS = K4_BK * PB;
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-    static constexpr size_t BYTES = (size_t)K4_STAGES * STAGE_ELEMS * sizeof(double2);
+    static constexpr size_t BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double2);
 };
 
 struct TileArgs {
@@ -113,9 +113,13 @@ __device__ __forceinline__ void epilogue_pair(double (&vr)[2], double (&vi)[2], 
 // FEED = 0: every thread issues 16-byte cp.async copies (commit / wait groups).  FEED = 1: warp 0 issues one bulk copy per
 // tile row (TMA engine) that completes on the stage's mbarrier `bars[stage]` (initialised by the caller, count 1; this
 // variant is called once per CTA, so stage s is filled for the (ks / STAGES)-th time in iteration ks).
-template <int BM, int BN, int WM, int WN, int FEED = 0>
+// MUL3 = 1: the complex product from THREE real products per fragment pair instead of four (P1 = Ar Br, P2 = Ai Bi,
+// P3 = (Ar + Ai)(Br + Bi); Re = P1 - P2, Im = P3 - P1 - P2): a quarter fewer DMMAs for two additions per fragment and a
+// third accumulator set.  The imaginary part loses the component-wise error bound but keeps the norm-wise one, which is
+// what the tolerance of this path is stated in.
+template <int BM, int BN, int WM, int WN, int FEED = 0, int MUL3 = 0, int STAGES = K4_STAGES>
 __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int tile_m, int tile_n, unsigned long long *bars = nullptr) {
-    using SM = K4Smem<BM, BN>;
+    using SM = K4Smem<BM, BN, STAGES>;
     constexpr int NTHREADS = (BM / WM) * (BN / WN) * 32;
     constexpr int MT = WM / 8, NTL = WN / 8;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -137,11 +141,15 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
         }
     };
 
-    double cre[MT][NTL][2], cim[MT][NTL][2];
+    double cre[MT][NTL][2], cim[MT][NTL][2];          // MUL3: P1 and P2 until the main loop is over
+    double p3[MUL3 ? MT : 1][MUL3 ? NTL : 1][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NTL; ++nt) { cre[mt][nt][0] = cre[mt][nt][1] = 0.0; cim[mt][nt][0] = cim[mt][nt][1] = 0.0; }
+        for (int nt = 0; nt < NTL; ++nt) {
+            cre[mt][nt][0] = cre[mt][nt][1] = 0.0; cim[mt][nt][0] = cim[mt][nt][1] = 0.0;
+            if (MUL3) p3[MUL3 ? mt : 0][MUL3 ? nt : 0][0] = p3[MUL3 ? mt : 0][MUL3 ? nt : 0][1] = 0.0;
+        }
 
     const unsigned bar0 = FEED ? smem_u32(bars) : 0u;
     auto load_stage_bulk = [&](int stage, int k0) {   // warp 0, all lanes
@@ -157,29 +165,29 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
     const int nk = g.n / K4_BK;
     if (FEED) {
         if (warp == 0)
-            for (int s = 0; s < K4_STAGES - 1; ++s)
+            for (int s = 0; s < STAGES - 1; ++s)
                 if (s < nk) load_stage_bulk(s, s * K4_BK);
     } else {
 #pragma unroll
-        for (int s = 0; s < K4_STAGES - 1; ++s) {
+        for (int s = 0; s < STAGES - 1; ++s) {
             if (s < nk) load_stage(s, s * K4_BK);
             cp_async_commit();
         }
     }
     for (int ks = 0; ks < nk; ++ks) {
-        if (FEED) mbar_wait(bar0 + 8u * (ks % K4_STAGES), (unsigned)(ks / K4_STAGES) & 1u);
-        else cp_async_wait<K4_STAGES - 2>();
+        if (FEED) mbar_wait(bar0 + 8u * (ks % STAGES), (unsigned)(ks / STAGES) & 1u);
+        else cp_async_wait<STAGES - 2>();
         __syncthreads();
         {   // prefetch stage ks + STAGES - 1 into the buffer consumed in iteration ks - 1
-            const int nxt = ks + K4_STAGES - 1;
+            const int nxt = ks + STAGES - 1;
             if (FEED) {
-                if (warp == 0 && nxt < nk) load_stage_bulk(nxt % K4_STAGES, nxt * K4_BK);
+                if (warp == 0 && nxt < nk) load_stage_bulk(nxt % STAGES, nxt * K4_BK);
             } else {
-                if (nxt < nk) load_stage(nxt % K4_STAGES, nxt * K4_BK);
+                if (nxt < nk) load_stage(nxt % STAGES, nxt * K4_BK);
                 cp_async_commit();
             }
         }
-        const double2 *sA = smem + (ks % K4_STAGES) * SM::STAGE_ELEMS;
+        const double2 *sA = smem + (ks % STAGES) * SM::STAGE_ELEMS;
         const double2 *sB = sA + SM::A_ELEMS;
 #pragma unroll
         for (int kt = 0; kt < K4_BK / 4; ++kt) {
@@ -188,20 +196,48 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
             for (int mt = 0; mt < MT; ++mt) af[mt] = sA[(wm0 + 8 * mt + gq) * SM::PA + 4 * kt + q];
 #pragma unroll
             for (int nt = 0; nt < NTL; ++nt) bf[nt] = sB[(4 * kt + q) * SM::PB + wn0 + 8 * nt + gq];
+            if (MUL3) {
+                double as[MT], bs[NTL];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
+                for (int mt = 0; mt < MT; ++mt) as[mt] = af[mt].x + af[mt].y;
 #pragma unroll
-                for (int nt = 0; nt < NTL; ++nt) {
-                    dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].x, bf[nt].x);
-                    dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].x, bf[nt].y);
-                }
+                for (int nt = 0; nt < NTL; ++nt) bs[nt] = bf[nt].x + bf[nt].y;
 #pragma unroll
-                for (int nt = 0; nt < NTL; ++nt) {
-                    dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].y, -bf[nt].y);
-                    dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].y, bf[nt].x);
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NTL; ++nt) {
+                        dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].x, bf[nt].x);
+                        dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].y, bf[nt].y);
+                        dmma884(p3[MUL3 ? mt : 0][MUL3 ? nt : 0][0], p3[MUL3 ? mt : 0][MUL3 ? nt : 0][1], as[mt], bs[nt]);
+                    }
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                    for (int nt = 0; nt < NTL; ++nt) {
+                        dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].x, bf[nt].x);
+                        dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].x, bf[nt].y);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NTL; ++nt) {
+                        dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].y, -bf[nt].y);
+                        dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].y, bf[nt].x);
+                    }
                 }
             }
         }
+    }
+    if (MUL3) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double a = cre[mt][nt][i], b = cim[mt][nt][i];
+                    cre[mt][nt][i] = a - b;
+                    cim[mt][nt][i] = p3[MUL3 ? mt : 0][MUL3 ? nt : 0][i] - (a + b);
+                }
     }
     if (!FEED) cp_async_wait<0>();
     __syncthreads();   // every warp is done with the stage buffers: the next tile_gemm may refill them
@@ -251,7 +287,7 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
         }
 }
 
-template <int BM, int BN, int WM, int WN, int FEED = 0>
+template <int BM, int BN, int WM, int WN, int FEED = 0, int MUL3 = 0, int STAGES = K4_STAGES>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 k4_zgemm_kernel(const GemmArgs g) {
     extern __shared__ __align__(16) unsigned char k4_smem_raw[];
@@ -284,7 +320,7 @@ k4_zgemm_kernel(const GemmArgs g) {
     t.alpha = g.alpha; t.scaled = g.scaled;
     t.beta2 = g.beta2; t.gamma = g.gamma; t.gamma_lo = g.gamma_lo;
     t.n = g.n;
-    tile_gemm<BM, BN, WM, WN, FEED>(smem, t, blockIdx.x / tiles_n, blockIdx.x % tiles_n, bars);
+    tile_gemm<BM, BN, WM, WN, FEED, MUL3, STAGES>(smem, t, blockIdx.x / tiles_n, blockIdx.x % tiles_n, bars);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -591,10 +627,20 @@ static int k4_feed_mode() {
     return mode;
 }
 
-template <int BM, int BN, int WM, int WN>
-static cudaError_t launch_gemm_t(const GemmArgs &g, cudaStream_t stream) {
-    using SM = K4Smem<BM, BN>;
-    auto kern = k4_feed_mode() ? k4_zgemm_kernel<BM, BN, WM, WN, 1> : k4_zgemm_kernel<BM, BN, WM, WN, 0>;
+// Complex product of the batched GEMM ($PARAMENT_K4_3M, read once).  Measured at dim 256 (C4, 2e4 points, four chunk streams):
+//   0  four real products, 64x64 CTA tiles, 3 stages, 2 CTAs of 8 warps per SM                      4.50e4 steps/s
+//   1  three real products, 64x64 tiles, one CTA per SM (the third accumulator set: 156 registers)  4.37e4
+//   2  three real products, 64x32 tiles, 3 stages, 2 CTAs of 4 warps per SM                         4.75e4
+//   3  three real products, 64x32 tiles, 2 stages, 3 CTAs of 4 warps per SM (default)               5.45e4
+static int k4_mul3_mode() {
+    static const int mode = [] { const char *e = getenv("PARAMENT_K4_3M"); const int v = e ? atoi(e) : 3; return v >= 0 && v <= 3 ? v : 3; }();
+    return mode;
+}
+
+template <int BM, int BN, int WM, int WN, int FEED, int MUL3, int STAGES = K4_STAGES>
+static cudaError_t launch_gemm_tt(const GemmArgs &g, cudaStream_t stream) {
+    using SM = K4Smem<BM, BN, STAGES>;
+    auto kern = k4_zgemm_kernel<BM, BN, WM, WN, FEED, MUL3, STAGES>;
     cudaError_t e = opt_in_smem(kern, SM::BYTES);   // per-device function attribute; cheap, so set on every launch
     if (e != cudaSuccess) return e;
     // (programmatic dependent launch was measured here: 2.78e4 -> 2.50e4 steps/s at dim 256, so plain stream order is kept)
@@ -603,23 +649,47 @@ static cudaError_t launch_gemm_t(const GemmArgs &g, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// four real products per complex product (mode 0), with either operand feed
+template <int BM, int BN, int WM, int WN>
+static cudaError_t launch_gemm_t(const GemmArgs &g, cudaStream_t stream) {
+    return k4_feed_mode() ? launch_gemm_tt<BM, BN, WM, WN, 1, 0>(g, stream) : launch_gemm_tt<BM, BN, WM, WN, 0, 0>(g, stream);
+}
+
 cudaError_t k4_gemm(const GemmArgs &g, cudaStream_t stream) {
     if (g.batch <= 0) return cudaSuccess;
-    if (g.n % 64 == 0) return launch_gemm_t<64, 64, 32, 16>(g, stream);
+    if (g.n % 64 == 0) {
+        if (k4_mul3_mode() == 1) return launch_gemm_tt<64, 64, 32, 16, 0, 1>(g, stream);
+        if (k4_mul3_mode() == 2) return launch_gemm_tt<64, 32, 32, 16, 0, 1>(g, stream);
+        if (k4_mul3_mode() == 3) return launch_gemm_tt<64, 32, 32, 16, 0, 1, 2>(g, stream);
+        return launch_gemm_t<64, 64, 32, 16>(g, stream);
+    }
     return launch_gemm_t<32, 32, 16, 16>(g, stream);
 }
 
 int k4_pad(int n) { return n <= 32 ? 32 : ((n + 63) / 64) * 64; }
-int k4_tiles(int npad) { return npad % 64 == 0 ? (npad / 64) * (npad / 64) : 1; }
+int k4_real_products(int npad) { return (npad % 64 == 0 && k4_mul3_mode() != 0) ? 3 : 4; }
+int k4_tiles(int npad) {
+    if (npad % 64 != 0) return 1;
+    return (npad / 64) * (npad / (k4_mul3_mode() >= 2 ? 32 : 64));
+}
+
+template <typename K>
+static int k4_blocks_per_sm(K kern, int threads, size_t smem) {
+    int per_sm = 0;
+    opt_in_smem(kern, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    return per_sm;
+}
 
 int k4_wave_slots(int npad, int num_sms) {
     int per_sm = 0;
     if (npad % 64 == 0) {
-        opt_in_smem(k4_zgemm_kernel<64, 64, 32, 16>, K4Smem<64, 64>::BYTES);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_zgemm_kernel<64, 64, 32, 16>, 256, K4Smem<64, 64>::BYTES);
+        if (k4_mul3_mode() == 1) per_sm = k4_blocks_per_sm(k4_zgemm_kernel<64, 64, 32, 16, 0, 1>, 256, K4Smem<64, 64>::BYTES);
+        else if (k4_mul3_mode() == 2) per_sm = k4_blocks_per_sm(k4_zgemm_kernel<64, 32, 32, 16, 0, 1>, 128, K4Smem<64, 32>::BYTES);
+        else if (k4_mul3_mode() == 3) per_sm = k4_blocks_per_sm(k4_zgemm_kernel<64, 32, 32, 16, 0, 1, 2>, 128, K4Smem<64, 32, 2>::BYTES);
+        else per_sm = k4_blocks_per_sm(k4_zgemm_kernel<64, 64, 32, 16>, 256, K4Smem<64, 64>::BYTES);
     } else {
-        opt_in_smem(k4_zgemm_kernel<32, 32, 16, 16>, K4Smem<32, 32>::BYTES);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_zgemm_kernel<32, 32, 16, 16>, 128, K4Smem<32, 32>::BYTES);
+        per_sm = k4_blocks_per_sm(k4_zgemm_kernel<32, 32, 16, 16>, 128, K4Smem<32, 32>::BYTES);
     }
     if (per_sm < 1) per_sm = 1;
     return per_sm * num_sms;

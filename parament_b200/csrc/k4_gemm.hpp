@@ -52,6 +52,7 @@ SeriesProgram build_program(const SeriesParams &p);
 cudaError_t k4_gemm(const GemmArgs &g, cudaStream_t stream);
 int k4_pad(int n);                            // padded dimension used by this kernel family
 int k4_tiles(int npad);                       // CTA tiles per matrix
+int k4_real_products(int npad);               // real matrix products per complex product of the batched GEMM (4, or 3)
 int k4_wave_slots(int npad, int num_sms);     // co-resident CTAs of the batched GEMM kernel on the device
 int k4_chain_slots(int npad, int num_sms);    // co-resident CTAs of the persistent chain kernel (npad <= 64)
 

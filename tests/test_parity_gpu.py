@@ -486,9 +486,13 @@ def test_error_growth_is_not_linear_in_steps(pb):
     assert max(errs.values()) < 2e-6, errs
 
 
-def test_bulk_copy_operand_feed_variant(tmp_path):
-    """$PARAMENT_K4_FEED=tma: the batched GEMM fed by bulk copies (TMA engine) + mbarriers instead of cp.async (DESIGN.md 7.3:
-    measured slower, kept as the A/B alternative).  Read once per process, hence a subprocess; same results required."""
+@pytest.mark.parametrize("variant", [{"PARAMENT_K4_3M": "0", "PARAMENT_K4_FEED": "tma"}, {"PARAMENT_K4_3M": "0"}, {"PARAMENT_K4_3M": "1"},
+                                     {"PARAMENT_K4_3M": "2"}, {"PARAMENT_K4_3M": "3", "PARAMENT_F3_STREAMS": "1"}],
+                         ids=lambda v: "-".join(f"{k[9:]}={x}" for k, x in v.items()))
+def test_batched_gemm_variants(tmp_path, variant):
+    """The measured alternatives of the batched GEMM for dim > 64: four real products per complex product
+    with the cp.async or the bulk-copy (TMA engine) + mbarrier operand feed, three real products on 64x64 / 64x32 tiles, one
+    chunk stream.  The switches are read once per process, hence a subprocess; every variant must meet the tolerance."""
     import subprocess
     import sys
     import textwrap
@@ -513,7 +517,7 @@ def test_bulk_copy_operand_feed_variant(tmp_path):
             np.save({str(tmp_path)!r} + "/" + name + ".npy", U)
             np.savez({str(tmp_path)!r} + "/" + name + "_in.npz", H0=H0, H1=H1, carr=w.carr, dt=w.dt)
     """)
-    env = dict(os.environ, PARAMENT_K4_FEED="tma")
+    env = dict(os.environ, **variant)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     for name in ("C4", "C3"):
