@@ -153,7 +153,9 @@ PARAMENT_API Parament_ErrorCode Parament_equipropBatch_fp64(struct Parament_Cont
 
 /* Device-resident variant: carr_dev / out_dev are DEVICE pointers on the context's device; the work is
  * enqueued on `stream` (a cudaStream_t passed as void*, NULL = the context's own stream) and the call
- * returns without synchronising when `stream` is non-NULL.  Same layouts as Parament_equipropBatch. */
+ * returns without synchronising when `stream` is non-NULL.  Same layouts as Parament_equipropBatch.
+ * The context's scratch memory is ordered by that stream (and by internal streams joined to it): successive calls on one
+ * context must use the same stream or be separated by a synchronisation, as with a cuBLAS workspace. */
 PARAMENT_API Parament_ErrorCode Parament_equipropDevice(struct Parament_Context_f32 *handle, const Parament_c64 *carr_dev,
                                                         double dt, unsigned int pts, unsigned int amps, unsigned int batch,
                                                         Parament_c64 *out_dev, void *stream);
