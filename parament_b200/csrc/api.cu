@@ -56,15 +56,6 @@ bool ensure_dev(DeviceBuffer &b, size_t bytes) {
     return true;
 }
 
-bool ensure_pinned(void *&p, size_t &have, size_t bytes) {
-    if (have >= bytes && p) return true;
-    if (p) cudaFreeHost(p);
-    p = nullptr; have = 0;
-    if (!PB_CUDA_OK(cudaMallocHost(&p, bytes))) { p = nullptr; cudaGetLastError(); return false; }
-    have = bytes;
-    return true;
-}
-
 bool create_copy_events(Context *c) {
     for (int i = 0; i < kCopyEvents; ++i)
         if (!PB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming))) return false;
@@ -138,8 +129,6 @@ Parament_ErrorCode destroy_ctx(Context *c) {
     free_dev(c->d_gather);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
     free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->h_out) cudaFreeHost(c->h_out);
     cudaEventDestroy(c->ev_start);
     cudaEventDestroy(c->ev_stop);
     destroy_copy_events(c);

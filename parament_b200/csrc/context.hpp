@@ -107,8 +107,6 @@ struct Context {
     bool peer_store_ok = false;     // helper: its kernels may store into the first device's memory (same device or peer access)
     DeviceWorker *worker = nullptr; // helper: the host thread that drives this device
     int stat_devices = 1;           // devices that took part in the last equiprop
-    void *h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging for carr
-    void *h_out = nullptr;   size_t h_out_bytes = 0;    // pinned staging for results
 
     // statistics of the last equiprop (Parament_lastStat)
     double stat_ms = 0.0;
