@@ -91,7 +91,7 @@ def dist_env():
 def make_slices(name, world, rank):
     """Workload of this rank: slice `rank` of a pulse `world` times longer than the configuration's.  Ensembles
     (C5) shard pulses instead.  Every rank builds its slice from the same seeded generator."""
-    from parament_b200.workloads import make_workload, smooth_pulses
+    from workloads import make_workload, smooth_pulses
     w = make_workload(name)
     if world > 1 and w.batch == 1:
         rng = np.random.default_rng(20260000 + 100 * rank + 7)
@@ -358,7 +358,7 @@ def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
         return
-    from parament_b200.workloads import make_workload
+    from workloads import make_workload
     w = make_workload(args.config)
     n, fp64 = w.dim, w.precision == "fp64"
     sfx = "_fp64" if fp64 else ""

@@ -174,6 +174,18 @@ PARAMENT_API Parament_ErrorCode Parament_equipropSlice_fp64(struct Parament_Cont
                                                             unsigned long long step_lo, unsigned long long step_hi,
                                                             Parament_c128 *out);
 
+/* The same with the partial propagator left on the GPU: carr is a HOST pointer, out_dev a DEVICE pointer (dim x dim, context
+ * precision, on the context's device).  The last kernel writes the partial there and the call returns when it is complete --
+ * the hand-off point to an NCCL exchange of the partials in a one-process-per-GPU run (bench.py --gpus N). */
+PARAMENT_API Parament_ErrorCode Parament_equipropSliceToDevice(struct Parament_Context_f32 *handle, const Parament_c64 *carr,
+                                                               double dt, unsigned int pts, unsigned int amps,
+                                                               unsigned long long step_lo, unsigned long long step_hi,
+                                                               Parament_c64 *out_dev);
+PARAMENT_API Parament_ErrorCode Parament_equipropSliceToDevice_fp64(struct Parament_Context_f64 *handle, const Parament_c128 *carr,
+                                                                    double dt, unsigned int pts, unsigned int amps,
+                                                                    unsigned long long step_lo, unsigned long long step_hi,
+                                                                    Parament_c128 *out_dev);
+
 /* Ordered product of `count` dim x dim partial propagators (host pointers, parts[0] is the earliest slice):
  * out = parts[count-1] ... parts[1] parts[0], evaluated on the device in complex128. */
 PARAMENT_API Parament_ErrorCode Parament_combine(struct Parament_Context_f32 *handle, const Parament_c64 *parts,
@@ -194,7 +206,10 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  *   5 kernel family used (1 = register-resident DMMA warp kernel, 2 = persistent CTA chain kernel,
  *                         3 = batched GEMM pipeline over L2-resident time chunks)
  *   6 H2D bytes copied                    7 D2H bytes copied
- *   8 Hnorm of the loaded Hamiltonian
+ *   8 Hnorm of the loaded Hamiltonian (the reference's bound, parament.cpp:280-284: sum of max-row-abs-sums)
+ *  14 norm bound the series of the last call was built for: Hnorm for dim <= 16; for dim > 16 the spectral bound
+ *     1.05 (s(H0) + sum_k max_t|c_k(t)| s(H_k)) (largest singular values, amplitude maxima measured per call), never above Hnorm.
+ *     Key 3 (the reference table's degree) and error 70 always follow Hnorm; key 2 follows key 14.
  *   9 series evaluation (0 Clenshaw recurrence, 1 Horner in Y^2, 2 Paterson-Stockmeyer blocks of four,
  *                        3 degree 8 in three products, 4 degree 12 in four products -- all the same polynomial family)
  *  10 complex matrix products executed per effective step (series + ordered product)
@@ -204,7 +219,12 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  * chain kernel for dim 17..64; PARAMENT_DEVICE the default CUDA device; PARAMENT_F3_STREAMS=1..4 the chunks in flight for dim > 64
  * (default 4); PARAMENT_K4_3M=0..3 the complex product of the batched GEMM (0: four real products on 64x64 tiles; 3, default: three real
  * products on 64x32 tiles); PARAMENT_K4_FEED=tma the bulk-copy (TMA engine) operand feed of that GEMM in mode 0 (measured slower than cp.async);
- * PARAMENT_COPY_GROUPS=1..8 the copy/compute groups of the host-pointer pipeline. */
+ * PARAMENT_COPY_GROUPS=1..8 the copy/compute groups of the host-pointer pipeline; PARAMENT_NORM=reference builds the series for
+ * Hnorm at every dimension (A/B of the spectral bound).
+ * Limits: at most 64 effective control terms per step (controls + Magnus commutators: amps <= 64 without Magnus, amps <= 9
+ * with it); Parament_setHamiltonian returns PARAMENT_STATUS_INVALID_VALUE beyond that (the reference has no stated limit but
+ * its launch configurations break at amps > 16 with Magnus, control_expansion.cu:179).
+ * Every entry point selects the context's device for its own duration and restores the caller's current device on return. */
 PARAMENT_API double Parament_lastStat(void *handle, int key);
 
 /* Select the CUDA device a context lives on.  Must be called before setHamiltonian; default is device 0

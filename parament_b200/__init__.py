@@ -3,4 +3,4 @@
 Importing this package loads parament_b200/lib/libparament.so and fails loudly if it is missing.
 """
 from .parament import Parament, device_info, expm  # noqa: F401
-from . import constants, workloads  # noqa: F401
+from . import constants  # noqa: F401

@@ -45,6 +45,7 @@ for suffix, cp in (("", c64_p), ("_fp64", c128_p)):
     getattr(lib, "Parament_equipropBatch" + suffix).argtypes = [ctx_p, cp, f64, u32, u32, u32, cp]
     getattr(lib, "Parament_equipropDevice" + suffix).argtypes = [ctx_p, ctypes.c_void_p, f64, u32, u32, u32, ctypes.c_void_p, ctypes.c_void_p]
     getattr(lib, "Parament_equipropSlice" + suffix).argtypes = [ctx_p, cp, f64, u32, u32, u64, u64, cp]
+    getattr(lib, "Parament_equipropSliceToDevice" + suffix).argtypes = [ctx_p, cp, f64, u32, u32, u64, u64, ctypes.c_void_p]
     getattr(lib, "Parament_combine" + suffix).argtypes = [ctx_p, cp, u32, cp]
     getattr(lib, "Parament_setIterationCyclesManually" + suffix).argtypes = [ctx_p, u32]
     getattr(lib, "Parament_automaticIterationCycles" + suffix).argtypes = [ctx_p]
@@ -82,7 +83,8 @@ EXPORTED = [
     "Parament_selectIterationCycles_fp64", "OneNorm", "OneNorm_fp64", "device_info", "Parament_getLastError",
     # section 2: additive
     "Parament_equipropBatch", "Parament_equipropBatch_fp64", "Parament_equipropDevice",
-    "Parament_equipropDevice_fp64", "Parament_equipropSlice", "Parament_equipropSlice_fp64", "Parament_combine",
+    "Parament_equipropDevice_fp64", "Parament_equipropSlice", "Parament_equipropSlice_fp64", "Parament_equipropSliceToDevice",
+    "Parament_equipropSliceToDevice_fp64", "Parament_combine",
     "Parament_combine_fp64", "Parament_combineDevice", "Parament_lastStat", "Parament_setDevice", "Parament_setDevices",
     "Parament_setDeviceList", "Parament_measurePeak", "Parament_version",
 ]

@@ -15,7 +15,9 @@
 #include <chrono>
 #include <functional>
 #include <new>
+#include <mutex>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 #include "context.hpp"
@@ -30,10 +32,31 @@ namespace {
 
 #define PB_CUDA_OK(expr) ((expr) == cudaSuccess)
 
+// Handles are checked against the set of live contexts: a handle used after Parament_destroy (the wrapper's
+// use-after-destroy test) is rejected without touching freed memory.
+std::mutex g_live_mu;
+std::unordered_set<const void *> g_live;
+
 inline Context *as_ctx(void *h) {
-    Context *c = reinterpret_cast<Context *>(h);
-    return (c && c->magic == 0x50423230) ? c : nullptr;
+    if (!h) return nullptr;
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    return g_live.count(h) ? reinterpret_cast<Context *>(h) : nullptr;
 }
+
+// Every entry point works on the context's device and puts the caller's current device back on exit (the reference never
+// changes it; Parament_equipropDevice is meant for torch / cupy pointers, whose owner expects its device to stay current).
+struct DeviceGuard {
+    int prev = -1, dev;
+    explicit DeviceGuard(int device) : dev(device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 
 Parament_ErrorCode fail(Context *c, Parament_ErrorCode code) {
     if (c) c->lastError = code;
@@ -66,6 +89,28 @@ void destroy_copy_events(Context *c) {
         if (c->ev_copy[i]) { cudaEventDestroy(c->ev_copy[i]); c->ev_copy[i] = nullptr; }
 }
 
+// Streams, events and the pinned scalar buffer of a context on its (current) device.  destroy_device_objects nulls every handle
+// it destroys, so it is safe on a partially created set and cannot destroy a handle twice.
+bool create_device_objects(Context *c) {
+    return PB_CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device)) &&
+           PB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) &&
+           PB_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) && create_copy_events(c) &&
+           PB_CUDA_OK(cudaEventCreate(&c->ev_start)) && PB_CUDA_OK(cudaEventCreate(&c->ev_stop)) &&
+           PB_CUDA_OK(cudaMallocHost(&c->h_absmax, kMaxTerms * sizeof(double)));
+}
+void destroy_device_objects(Context *c) {
+    free_dev(c->d_gather); free_dev(c->d_absmax); free_dev(c->d_counters);
+    free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
+    free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
+    if (c->h_absmax) { cudaFreeHost(c->h_absmax); c->h_absmax = nullptr; }
+    if (c->ev_start) { cudaEventDestroy(c->ev_start); c->ev_start = nullptr; }
+    if (c->ev_stop) { cudaEventDestroy(c->ev_stop); c->ev_stop = nullptr; }
+    destroy_copy_events(c);
+    for (cudaStream_t &q : c->f3_streams) if (q) { cudaStreamDestroy(q); q = nullptr; }
+    if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); c->copy_stream = nullptr; }
+    if (c->stream) { cudaStreamDestroy(c->stream); c->stream = nullptr; }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // create / destroy                                                   (reference parament.cpp:51-205)
 // ---------------------------------------------------------------------------------------------------
@@ -89,17 +134,20 @@ Parament_ErrorCode create_ctx_on(Context **out, bool fp64, int dev) {
     }
     if (dev < 0 || dev >= ndev) dev = 0;
     c->device = dev;
-    if (!PB_CUDA_OK(cudaSetDevice(dev)) ||
-        !PB_CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, dev)) ||
-        !PB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
-        !PB_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) || !create_copy_events(c) ||
-        !PB_CUDA_OK(cudaEventCreate(&c->ev_start)) || !PB_CUDA_OK(cudaEventCreate(&c->ev_stop))) {
+    DeviceGuard guard(dev);
+    if (!create_device_objects(c)) {
+        destroy_device_objects(c);   // whatever was created before the failing call
         cudaGetLastError();
         delete c;
         return PARAMENT_STATUS_CUBLAS_INIT_FAILED;
     }
     if (const char *e = getenv("PARAMENT_SERIES")) c->series_mode = (strcmp(e, "clenshaw") == 0) ? 1 : (strcmp(e, "horner") == 0 ? 2 : 0);
+    if (const char *e = getenv("PARAMENT_NORM")) c->norm_mode = strcmp(e, "reference") == 0 ? 0 : 1;
     c->lastError = PARAMENT_STATUS_SUCCESS;
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live.insert(c);
+    }
     *out = c;
     return PARAMENT_STATUS_SUCCESS;
 }
@@ -124,20 +172,18 @@ Parament_ErrorCode destroy_ctx(Context *c) {
     if (!c) return PARAMENT_STATUS_SUCCESS;   // NULL is a no-op (parament.cpp:190-191)
     destroy_peers(c);
     if (c->worker) { c->worker->stop(); delete c->worker; c->worker = nullptr; }
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    free_dev(c->d_gather);
-    free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
-    free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
-    cudaEventDestroy(c->ev_start);
-    cudaEventDestroy(c->ev_stop);
-    destroy_copy_events(c);
-    for (cudaStream_t &q : c->f3_streams) if (q) { cudaStreamDestroy(q); q = nullptr; }
-    cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->stream);
+    {
+        DeviceGuard guard(c->device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        destroy_device_objects(c);
+        cudaGetLastError();
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live.erase(c);
+    }
     c->magic = 0;
     delete c;
-    cudaGetLastError();
     return PARAMENT_STATUS_SUCCESS;
 }
 
@@ -182,6 +228,47 @@ void commutator(const zc *A, const zc *B, zc *out, int n) {   // out = A B - B A
             for (int j = 0; j < n; ++j) ti[j] += a * Bk[j] - b * Ak[j];
         }
     std::copy(t.begin(), t.end(), out);
+}
+
+// Largest singular value of an n x n matrix: power iteration on A^H A from a fixed pseudo-random start (deterministic).
+// The Rayleigh quotient converges from below; the caller adds a safety margin.  Cost O(iters n^2) on the host, once per
+// Hamiltonian (the reference's norm, parament.cpp:280-284, is the looser max-row-abs-sum).
+double spectral_norm(const zc *A, int n, int iters = 80) {
+    std::vector<zc> v((size_t)n), w((size_t)n);
+    unsigned long long seed = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < n; ++i) {
+        seed = seed * 6364136223846793005ull + 1442695040888963407ull;
+        const double a = (double)(seed >> 11) / 9007199254740992.0 - 0.5;
+        seed = seed * 6364136223846793005ull + 1442695040888963407ull;
+        const double b = (double)(seed >> 11) / 9007199254740992.0 - 0.5;
+        v[i] = zc(a, b);
+    }
+    double sigma = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        double nv = 0.0;
+        for (int i = 0; i < n; ++i) nv += std::norm(v[i]);
+        nv = std::sqrt(nv);
+        if (!(nv > 0.0)) return 0.0;
+        for (int i = 0; i < n; ++i) v[i] /= nv;
+        double nw = 0.0;
+        for (int i = 0; i < n; ++i) {                 // w = A v
+            zc acc(0, 0);
+            const zc *Ai = A + (size_t)i * n;
+            for (int j = 0; j < n; ++j) acc += Ai[j] * v[j];
+            w[i] = acc;
+            nw += std::norm(acc);
+        }
+        const double s_new = std::sqrt(nw);           // ||A v|| <= sigma_max, increasing with the iteration
+        if (it > 8 && s_new <= sigma * (1.0 + 1e-7)) { sigma = std::max(sigma, s_new); break; }
+        sigma = std::max(sigma, s_new);
+        for (int j = 0; j < n; ++j) v[j] = zc(0, 0);  // v = A^H w
+        for (int i = 0; i < n; ++i) {
+            const zc *Ai = A + (size_t)i * n;
+            const zc wi = w[i];
+            for (int j = 0; j < n; ++j) v[j] += std::conj(Ai[j]) * wi;
+        }
+    }
+    return sigma;
 }
 
 inline int pair_index(int j, int k, int A) { return j * A - j * (j + 1) / 2 + (k - j - 1); }   // j < k
@@ -258,7 +345,7 @@ template <typename T>
 Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigned int dim, unsigned int amps,
                                    bool use_magnus, int quad) {
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     c->have_hamiltonian = false;   // a previous Hamiltonian is dropped first (parament.cpp:216)
     if (use_magnus && quad != PARAMENT_QUADRATURE_SIMPSON)
         return fail(c, PARAMENT_STATUS_INVALID_QUADRATURE_SELECTION);   // parament.cpp:220-226
@@ -272,8 +359,11 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     const size_t nn = (size_t)dim * dim;
     const int A = (int)amps;
     c->nmats = 1 + A + (use_magnus ? A + A * (A - 1) / 2 : 0);
+    // effective control terms per step are limited to kMaxTerms = 64 (include/parament.h): rejected here, not at equiprop time
+    if (c->nmats - 1 > kMaxTerms) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
     try {
         c->mats.assign((size_t)c->nmats * nn, zc(0, 0));
+        c->sigma_max.assign((size_t)1 + A, 0.0);
     } catch (const std::bad_alloc &) {
         return fail(c, PARAMENT_STATUS_HOST_ALLOC_FAILED);
     }
@@ -293,6 +383,10 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
         c->k4_slots = c->onchip ? oc : k4_chain_slots(c->npad, c->num_sms);
     }
     else                { c->family = 3; c->npad = k4_pad((int)dim); c->k4_slots = k4_wave_slots(c->npad, c->num_sms); }
+    c->series_cache.valid = false;
+    // spectral bound of the step Hamiltonians (dim > 16, where it saves a matrix product per step; series_norm_for_call)
+    if (c->family != 1 && c->norm_mode == 1)
+        for (int m = 0; m <= A; ++m) c->sigma_max[m] = spectral_norm(c->mats.data() + (size_t)m * nn, (int)dim);
 
     // physical commutators [H0,H_j] and [H_j,H_k], j<k (parament.cpp:289-359): on the host for the
     // register-resident family (tiny matrices), on the device GEMM kernel otherwise (upload_matrices)
@@ -309,9 +403,8 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     // single-process multi-GPU: every helper context gets the same Hamiltonian (constants are replicated)
     for (Context *p : c->peers) {
         const Parament_ErrorCode ec = set_hamiltonian<T>(p, H0, H1, dim, amps, use_magnus, quad);
-        if (ec != PARAMENT_STATUS_SUCCESS) { cudaSetDevice(c->device); return fail(c, ec); }
+        if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
     }
-    cudaSetDevice(c->device);
     c->have_hamiltonian = true;
     c->lastError = PARAMENT_STATUS_SUCCESS;
     return PARAMENT_STATUS_SUCCESS;
@@ -349,6 +442,7 @@ struct CallSpec {
     unsigned long long nsteps;      // effective steps per pulse to process; step 0 starts at raw point 0
     unsigned long long total_steps; // steps of the whole pulse (degree policy of sliced runs)
     double dt;
+    double series_norm;             // bound of ||H(t_j)||_2 the series is built for; 0: the reference's Hnorm
 };
 
 unsigned long long effective_steps(const Context *c, unsigned long long pts) {   // parament.cpp:820-831
@@ -365,25 +459,39 @@ int point_overlap(const Context *c) {   // extra raw points a slice needs beyond
     return 0;
 }
 
-// Degree policy.  M_ref is what the reference's table selects (parament.cpp:376-391); complex64 contexts
-// raise the degree until the accumulated truncation error N * 2|J_{M+1}(x)| is below 1e-6 (10 % of the
-// 1e-5 tolerance), because the fp32 table only bounds the error of ONE step (DESIGN.md "Numerics").
-Parament_ErrorCode choose_degree(Context *c, double h, unsigned long long total_steps, int &M_ref, int &M_used) {
+// Degree policy.  M_ref is what the reference's table selects for ITS norm bound Hnorm (parament.cpp:376-391); it decides
+// SELECT_SMALLER_DT and is what Parament_lastStat reports as the reference degree.  The degree actually evaluated:
+//   * series built for Hnorm (dim <= 16, or $PARAMENT_NORM=reference): complex128 contexts use the table; complex64 contexts
+//     raise the degree until the accumulated truncation error N * 2|J_{M+1}(x)| is below 1e-6 (10 % of the 1e-5 tolerance),
+//     because the fp32 table only bounds the error of ONE step (DESIGN.md "Numerics");
+//   * series built for the tighter spectral bound Hs < Hnorm (dim > 16): the table is read at Hs * h (same per-step
+//     semantics: the table is a function of norm bound x step), then raised until N * 2|J_{M+1}(Hs h)| is below 1e-6
+//     (complex64) / 1e-13 (complex128), and never above the reference's own choice for complex128.
+Parament_ErrorCode choose_degree(Context *c, double h, unsigned long long total_steps, double Hs, int &M_ref, int &M_used) {
     if (c->MMAX_manual) {
         M_ref = M_used = c->MMAX;
         if (M_used < 1 || M_used > kMaxDegree) return PARAMENT_STATUS_INVALID_VALUE;
         return PARAMENT_STATUS_SUCCESS;
     }
-    M_ref = c->fp64 ? select_cycles_fp64(c->Hnorm, h) : select_cycles_fp32(c->Hnorm, h);
+    const double ha = std::fabs(h);   // backward propagation (dt < 0) needs the degree of |dt|; the tables return 3 for x < 0
+    M_ref = c->fp64 ? select_cycles_fp64(c->Hnorm, ha) : select_cycles_fp32(c->Hnorm, ha);
     if (M_ref < 3) return PARAMENT_STATUS_SELECT_SMALLER_DT;   // parament.cpp:386-388
-    M_used = M_ref;
     c->MMAX = M_ref;
-    if (!c->fp64) {
-        const int cap = std::max(M_ref, select_cycles_fp64(c->Hnorm, h) > 0 ? select_cycles_fp64(c->Hnorm, h) : kMaxDegree);
+    const bool tight = Hs > 0.0 && Hs < c->Hnorm;
+    const double Hx = tight ? Hs : c->Hnorm;
+    M_used = M_ref;
+    if (tight) {
+        const int mt = c->fp64 ? select_cycles_fp64(Hx, ha) : select_cycles_fp32(Hx, ha);
+        if (mt >= 3 && mt < M_used) M_used = mt;
+    }
+    if (!c->fp64 || tight) {
+        const int m64 = select_cycles_fp64(c->Hnorm, ha);
+        const int cap = c->fp64 ? M_ref : std::max(M_ref, m64 > 0 ? m64 : kMaxDegree);
+        const double budget = c->fp64 ? 1e-13 : 1e-6;
         std::vector<long double> J; long double j0m1;
-        bessel_j_table((long double)(c->Hnorm * h), cap + 1, J, j0m1);
+        bessel_j_table((long double)(Hx * ha), cap + 1, J, j0m1);
         const double N = (double)std::max<unsigned long long>(total_steps, 1);
-        while (M_used < cap && N * 2.0 * std::fabs((double)J[M_used + 1]) > 1e-6) ++M_used;
+        while (M_used < cap && N * 2.0 * std::fabs((double)J[M_used + 1]) > budget) ++M_used;
     }
     return PARAMENT_STATUS_SUCCESS;
 }
@@ -454,16 +562,18 @@ bool solve_degree12(SeriesParams &p) {
 Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) {
     const double h = (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) ? 2.0 * s.dt : s.dt;   // parament.cpp:800-802
     int M_ref = 0, M_used = 0;
-    Parament_ErrorCode ec = choose_degree(c, h, s.total_steps, M_ref, M_used);
+    const double Hs = (s.series_norm > 0.0 && s.series_norm < c->Hnorm) ? s.series_norm : c->Hnorm;   // norm the series is built for
+    Parament_ErrorCode ec = choose_degree(c, h, s.total_steps, Hs, M_ref, M_used);
     if (ec != PARAMENT_STATUS_SUCCESS) return ec;
+    c->stat_series_norm = Hs;
     // Degrees 6..8 are evaluated as ONE degree-8 polynomial in three matrix products (below); the Y^2 Horner form needs four
     // for degree 6 or 7.  The register-resident family does so for complex64 contexts (its path has no compensated constants).
     const bool want_s8 = (c->family != 1 || !c->fp64) && !c->MMAX_manual && c->series_mode == 0 && M_used >= 6 && M_used <= 8 &&
-                         c->Hnorm * h <= 1.0;
+                         Hs * std::fabs(h) <= 1.0;
     if (want_s8) M_used = 8;
     // degrees 9..12 as ONE degree-12 polynomial in four matrix products
     const bool want_s12 = !c->MMAX_manual && c->series_mode == 0 && M_used >= 9 && M_used <= 12 &&
-                          c->Hnorm * h <= 1.0;
+                          Hs * std::fabs(h) <= 1.0;
     if (want_s12) M_used = 12;
     c->stat_M_ref = M_ref;
     c->stat_M_used = M_used;
@@ -480,7 +590,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     p.magfac = h / 12.0;
     const int cache_flags = (want_s8 ? 1 : 0) | (want_s12 ? 2 : 0) | (c->series_mode << 2) | (c->fp64 ? 32 : 0);
     Context::SeriesCache &sc = c->series_cache;
-    const bool cached = sc.valid && sc.h == h && sc.Hnorm == c->Hnorm && sc.M == M_used && sc.family == c->family &&
+    const bool cached = sc.valid && sc.h == h && sc.Hnorm == Hs && sc.M == M_used && sc.family == c->family &&
                         sc.onchip == (int)c->onchip && sc.flags == cache_flags;
     if (cached) {
         p.sigma = sc.sigma;
@@ -490,10 +600,12 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     } else {
     // sigma is rounded to double FIRST and x is derived from the rounded value in long double, so that
     // sigma * x == 2 h holds to 1e-19: a relative error in sigma alone would stretch the time axis coherently.
-    p.sigma = 2.0 / c->Hnorm;
+    p.sigma = 2.0 / Hs;
     const long double x = 2.0L * (long double)h / (long double)p.sigma;
     std::vector<long double> J; long double j0m1;
     bessel_j_table(x, M_used, J, j0m1);
+    if (x < 0)   // backward propagation: J_k(-x) = (-1)^k J_k(x)
+        for (int k = 1; k <= M_used; k += 2) J[k] = -J[k];
     p.a[0] = cplx{(double)j0m1, 0.0};
     p.a_lo[0] = cplx{(double)(j0m1 - (long double)p.a[0].re), 0.0};
     for (int k = 1; k <= M_used; ++k) {
@@ -511,7 +623,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     // converted in long double.  Restricted to x <= 1, where every term of the monomial sum is <= 1 (no cancellation).
     p.horner = 0;
     const double sigma0 = p.sigma;
-    if (c->series_mode != 1 && M_used >= 3 && M_used <= 24 && (double)x <= 1.0) {
+    if (c->series_mode != 1 && M_used >= 3 && M_used <= 24 && std::fabs((double)x) <= 1.0) {
         p.horner = 1;
         const int d = M_used;
         std::vector<std::vector<long double>> t(d + 1, std::vector<long double>(d + 1, 0.0L));
@@ -545,7 +657,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
         if (want_s8 && solve_degree8(p)) p.horner = 3;
         if (want_s12 && solve_degree12(p)) p.horner = 4;
     }
-    sc.valid = true; sc.h = h; sc.Hnorm = c->Hnorm; sc.M = M_used; sc.family = c->family; sc.onchip = (int)c->onchip; sc.flags = cache_flags;
+    sc.valid = true; sc.h = h; sc.Hnorm = Hs; sc.M = M_used; sc.family = c->family; sc.onchip = (int)c->onchip; sc.flags = cache_flags;
     sc.horner = p.horner; sc.sigma = p.sigma;
     memcpy(sc.a, p.a, sizeof(p.a));
     memcpy(sc.a_lo, p.a_lo, sizeof(p.a_lo));
@@ -608,7 +720,7 @@ Parament_ErrorCode tree_reduce_all(Context *c, double2 *buf, int count, double2 
     return PARAMENT_STATUS_SUCCESS;
 }
 
-struct F3Plan { int S; int cap; };
+struct F3Plan { int S; int cap; int NS; };   // chunk length, pending-list capacity, chunk streams (work sets) in flight
 constexpr int kF3Streams = 4;
 int f3_stream_count() {   // chunks in flight (one stream and one work set each); $PARAMENT_F3_STREAMS = 1..4 for A/B runs
     const char *env = getenv("PARAMENT_F3_STREAMS");
@@ -633,6 +745,7 @@ F3Plan plan_family3(const Context *c, const CallSpec &s) {
     // pending partial products: enough for the first tree levels to run in whole waves (16 chunks), bounded by 1.5 GiB
     const size_t want = std::min<size_t>(std::max<size_t>(64, (size_t)16 * f.S), std::max<size_t>(64, ((size_t)3 << 29) / (nn * sizeof(double2))));
     f.cap = (int)std::max<size_t>(2, std::min<size_t>(want, (size_t)std::min<unsigned long long>(s.nsteps, 1ull << 30)));
+    f.NS = (s.nsteps >= 4ull * f.S) ? f3_stream_count() : 1;   // short calls run on one stream and get one work set
     return f;
 }
 
@@ -642,7 +755,7 @@ int chain_grid(const Context *c, const CallSpec &s) {
 
 bool alloc_family3(Context *c, const F3Plan &f) {
     const size_t nn = (size_t)c->npad * c->npad;
-    return ensure_dev(c->d_Y, (size_t)f3_stream_count() * kSeriesSlots * f.S * nn * sizeof(double2)) &&   // one chunk work set per stream
+    return ensure_dev(c->d_Y, (size_t)f.NS * kSeriesSlots * f.S * nn * sizeof(double2)) &&   // one chunk work set per stream in use
            ensure_dev(c->d_pending, (size_t)2 * (f.cap + f.S) * nn * sizeof(double2)) &&   // two halves
            ensure_dev(c->d_tree, (size_t)((f.cap + f.S) / 2 + 1) * nn * sizeof(double2));
 }
@@ -690,7 +803,7 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
     const F3Plan f = plan_family3(c, s);
     const int S = f.S, cap = f.cap;
     const SeriesProgram prog = build_program(p);
-    const int NS = (s.nsteps >= 4ull * S) ? f3_stream_count() : 1;
+    const int NS = f.NS;
     cudaStream_t sx[kF3Streams] = {st, nullptr, nullptr, nullptr};
     if (NS > 1) {
         sx[0] = c->copy_stream;
@@ -798,10 +911,40 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
     return PARAMENT_STATUS_SUCCESS;
 }
 
+// Spectral bound of the step Hamiltonians of THIS call:  ||H0 + sum_k c_k(t) H_k||_2 <= s_0 + sum_k max_t|c_k(t)| s_k, with s_m the
+// largest singular values from setHamiltonian and the amplitude maxima measured on the device (one pass over the amplitude stream
+// and a 64-byte read-back; dim > 16 only, where a step costs >= 50 us of tensor work per SM).  The quadrature averages cannot
+// exceed the maxima; the Magnus commutator term adds at most (h/12) 2 rho^2.  5 % margin on the power-iteration estimates; never
+// above the reference's bound Hnorm (parament.cpp:280-284), which stays in charge of the error semantics.
+Parament_ErrorCode series_norm_for_call(Context *c, const void *carr_dev, const CallSpec &s, cudaStream_t st, double &Hs) {
+    Hs = c->Hnorm;
+    if (c->family == 1 || c->norm_mode != 1 || c->MMAX_manual || c->sigma_max.size() < (size_t)c->amps + 1) return PARAMENT_STATUS_SUCCESS;
+    double rho = c->sigma_max[0];
+    if (s.amps > 0) {
+        if (!ensure_dev(c->d_absmax, kMaxTerms * sizeof(unsigned long long))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+        const size_t pts = (size_t)points_per_step(c) * s.nsteps + point_overlap(c);
+        if (k4_absmax(c->fp64, carr_dev, s.batch, s.amps, s.stride, std::min(pts, s.stride), (unsigned long long *)c->d_absmax.ptr, st) != cudaSuccess ||
+            !PB_CUDA_OK(cudaMemcpyAsync(c->h_absmax, c->d_absmax.ptr, s.amps * sizeof(double), cudaMemcpyDeviceToHost, st)) ||
+            !PB_CUDA_OK(cudaStreamSynchronize(st)))
+            return PARAMENT_STATUS_CUBLAS_FAILED;
+        for (unsigned int k = 0; k < s.amps; ++k) rho += std::sqrt(c->h_absmax[k]) * c->sigma_max[1 + k];
+    }
+    if (c->enable_magnus) {
+        const double h = 2.0 * std::fabs(s.dt);
+        rho += (h / 6.0) * rho * rho;
+    }
+    rho *= 1.05;
+    if (rho > 0.0 && rho < c->Hnorm) Hs = rho;
+    return PARAMENT_STATUS_SUCCESS;
+}
+
 // Device-resident core shared by every equiprop entry point.
-Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const CallSpec &s, void *out_dev, cudaStream_t st) {
+Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const CallSpec &s_in, void *out_dev, cudaStream_t st) {
+    CallSpec s = s_in;
+    Parament_ErrorCode ec = series_norm_for_call(c, carr_dev, s, st, s.series_norm);
+    if (ec != PARAMENT_STATUS_SUCCESS) return ec;
     SeriesParams p;
-    Parament_ErrorCode ec = build_series(c, s, p);
+    ec = build_series(c, s, p);
     if (ec != PARAMENT_STATUS_SUCCESS) return ec;
     c->stat_steps = s.nsteps;
     c->stat_launches = 0;
@@ -922,6 +1065,22 @@ void write_identity(T *out, int n, unsigned int batch) {
             }
 }
 
+// Identity propagators to a host array or (out_is_device) to device memory through the context's stream.
+template <typename T>
+Parament_ErrorCode deliver_identity(Context *c, T *out, int n, unsigned int batch, bool out_is_device) {
+    if (!out_is_device) { write_identity(out, n, batch); return PARAMENT_STATUS_SUCCESS; }
+    try {
+        std::vector<T> id((size_t)batch * n * n);
+        write_identity(id.data(), n, batch);
+        if (!PB_CUDA_OK(cudaMemcpyAsync(out, id.data(), id.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream)) ||
+            !PB_CUDA_OK(cudaStreamSynchronize(c->stream)))
+            return PARAMENT_STATUS_CUBLAS_FAILED;
+    } catch (const std::bad_alloc &) {
+        return PARAMENT_STATUS_HOST_ALLOC_FAILED;
+    }
+    return PARAMENT_STATUS_SUCCESS;
+}
+
 // Host-pointer entry: stage the needed part of the amplitude stream, run, copy the result back.
 // step range [lo, hi) of each pulse; carr holds batch * amps arrays of pts points.
 template <typename T>
@@ -930,17 +1089,19 @@ Parament_ErrorCode equiprop_multi(Context *c, const T *carr, double dt, unsigned
 
 // gather_to != nullptr (single-process multi-GPU): the result is not copied to the host but to slot `slot` of
 // gather_to->d_gather by a peer copy (NVLink when the devices have peer access), and `out` is not written.
+// out_is_device: `out` is device memory on the context's device; the last kernel writes the result there (no D2H), and the
+// call returns once it is complete (Parament_equipropSliceToDevice: the partial stays on the GPU for the NCCL exchange).
 template <typename T>
 Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned int pts, unsigned int amps, unsigned int batch,
                                  unsigned long long lo, unsigned long long hi, bool whole, T *out, Context *gather_to = nullptr,
-                                 unsigned int slot = 0) {
+                                 unsigned int slot = 0, bool out_is_device = false) {
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
     if (whole && !gather_to && !c->peers.empty()) {
         bool handled = false;
         const Parament_ErrorCode mec = equiprop_multi<T>(c, carr, dt, pts, amps, batch, out, handled);
         if (handled) return mec;
     }
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     c->stat_devices = 1;
     if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);   // parament.cpp:795-798
     if (!out || (!carr && amps > 0 && pts > 0) || (int)amps > c->amps || batch == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
@@ -952,14 +1113,15 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
 
     CallSpec s{};
     s.amps = amps; s.batch = batch; s.dt = dt; s.nsteps = hi - lo; s.total_steps = N;
-    {   // the degree / dt check happens before any transfer, as in the reference (parament.cpp:804-807)
-        SeriesParams probe;
-        CallSpec s0 = s; s0.stride = 1;
-        Parament_ErrorCode ec = build_series(c, s0, probe);
+    {   // the degree / dt check happens before any transfer, as in the reference (parament.cpp:804-807); it builds no series
+        // (an all-zero Hamiltonian would give sigma = 2 / 0), so nothing is cached from here
+        int M_ref = 0, M_used = 0;
+        const double h = (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) ? 2.0 * dt : dt;
+        Parament_ErrorCode ec = choose_degree(c, h, s.total_steps, c->Hnorm, M_ref, M_used);
         if (ec != PARAMENT_STATUS_SUCCESS) return fail(c, ec);
     }
     if (s.nsteps == 0 || c->Hnorm == 0.0) {   // nothing to propagate: identity (reference returns stale memory, SURVEY A-7)
-        write_identity(out, n, batch);
+        if (Parament_ErrorCode ec = deliver_identity<T>(c, out, n, batch, out_is_device)) return fail(c, ec);
         c->lastError = PARAMENT_STATUS_SUCCESS;
         return PARAMENT_STATUS_SUCCESS;
     }
@@ -970,7 +1132,7 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
     const size_t arrays = (size_t)batch * amps;
     const size_t in_bytes = arrays * seg * sizeof(T);
     const size_t out_bytes = (size_t)batch * n * n * sizeof(T);
-    if (!ensure_dev(c->d_carr, in_bytes) || !ensure_dev(c->d_out, out_bytes)) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
+    if (!ensure_dev(c->d_carr, in_bytes) || (!out_is_device && !ensure_dev(c->d_out, out_bytes))) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
     // groups of >= 4 MB (and >= 16k steps along the time axis) for the copy / compute overlap of the register-resident family
     int G = (int)std::min<size_t>(8, in_bytes / ((size_t)4 << 20));
     if (const char *e = getenv("PARAMENT_COPY_GROUPS")) G = std::max(1, std::min(8, atoi(e)));   // A/B runs
@@ -981,7 +1143,7 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
     // shared call: the last kernel of this device stores its partial straight into the gather buffer on the first device
     // (plain stores over NVLink peer memory) when that memory is addressable from here, else a peer copy follows
     const bool direct_store = gather_to && (gather_to == c || c->peer_store_ok);
-    void *result_dev = direct_store ? (void *)((T *)gather_to->d_gather.ptr + (size_t)slot * n * n) : c->d_out.ptr;
+    void *result_dev = direct_store ? (void *)((T *)gather_to->d_gather.ptr + (size_t)slot * n * n) : (out_is_device ? (void *)out : c->d_out.ptr);
     if (c->family == 1 && G >= 2) {
         ec = pipelined_family1<T>(c, carr, pts, p_lo, seg, s, G, result_dev);
     } else {
@@ -1004,10 +1166,10 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
         c->lastError = PARAMENT_STATUS_SUCCESS;
         return PARAMENT_STATUS_SUCCESS;
     }
-    if (!PB_CUDA_OK(cudaMemcpyAsync(out, c->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, c->stream)) ||
+    if ((!out_is_device && !PB_CUDA_OK(cudaMemcpyAsync(out, c->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, c->stream))) ||
         !PB_CUDA_OK(cudaStreamSynchronize(c->stream)))
         return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
-    c->stat_d2h = (double)out_bytes;
+    c->stat_d2h = out_is_device ? 0.0 : (double)out_bytes;
     c->lastError = PARAMENT_STATUS_SUCCESS;
     return PARAMENT_STATUS_SUCCESS;
 }
@@ -1016,7 +1178,7 @@ template <typename T>
 Parament_ErrorCode equiprop_device(Context *c, const T *carr_dev, double dt, unsigned int pts, unsigned int amps,
                                    unsigned int batch, T *out_dev, void *stream) {
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);
     if (!out_dev || !carr_dev || (int)amps > c->amps || batch == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
     const unsigned long long N = effective_steps(c, pts);
@@ -1060,7 +1222,7 @@ Parament_ErrorCode combine_device_core(Context *c, const void *parts_dev, unsign
 template <typename T>
 Parament_ErrorCode combine_host(Context *c, const T *parts, unsigned int count, T *out) {
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);
     if (!parts || !out || count == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
     const size_t in_bytes = (size_t)count * c->dim * c->dim * sizeof(T), out_bytes = (size_t)c->dim * c->dim * sizeof(T);
@@ -1078,7 +1240,7 @@ Parament_ErrorCode combine_host(Context *c, const T *parts, unsigned int count, 
 
 Parament_ErrorCode combine_device(Context *c, const void *parts_dev, unsigned int count, void *out_dev, void *stream) {
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     if (!c->have_hamiltonian) return fail(c, PARAMENT_STATUS_NO_HAMILTONIAN);
     if (!parts_dev || !out_dev || count == 0) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
@@ -1106,6 +1268,7 @@ Parament_ErrorCode equiprop_multi(Context *c, const T *carr, double dt, unsigned
     const unsigned int G = devices_for_call((unsigned int)c->peers.size() + 1, batch, N, c->npad);   // plan.hpp
     if (G < 2) return PARAMENT_STATUS_SUCCESS;   // not worth sharing: the caller runs it on the first device
     handled = true;
+    DeviceGuard guard(c->device);
     const int n = c->dim;
     const size_t nn = (size_t)n * n;
     const auto t0 = std::chrono::steady_clock::now();
@@ -1113,22 +1276,28 @@ Parament_ErrorCode equiprop_multi(Context *c, const T *carr, double dt, unsigned
     auto ctx_of = [&](unsigned int g) { return g == 0 ? c : c->peers[g - 1]; };
     std::function<void(unsigned int)> run;
     if (batch == 1) {
-        cudaSetDevice(c->device);
         if (!ensure_dev(c->d_gather, (size_t)G * nn * sizeof(T))) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
-        run = [&](unsigned int g) {
-            ecs[g] = equiprop_host<T>(ctx_of(g), carr, dt, pts, amps, 1, N * g / G, N * (g + 1) / G, false, out, c, g);
+        run = [&](unsigned int g) {   // runs on a helper thread for g > 0: no exception may leave it (std::terminate)
+            try {
+                ecs[g] = equiprop_host<T>(ctx_of(g), carr, dt, pts, amps, 1, N * g / G, N * (g + 1) / G, false, out, c, g);
+            } catch (...) {
+                ecs[g] = PARAMENT_STATUS_HOST_ALLOC_FAILED;
+            }
         };
     } else {
         // whole = false with the full step range [0, N): neither this context nor a helper shares the work again
         run = [&](unsigned int g) {
             const size_t b0 = (size_t)batch * g / G, b1 = (size_t)batch * (g + 1) / G;
-            ecs[g] = equiprop_host<T>(ctx_of(g), carr + b0 * amps * pts, dt, pts, amps, (unsigned int)(b1 - b0), 0, N, false, out + b0 * nn);
+            try {
+                ecs[g] = equiprop_host<T>(ctx_of(g), carr + b0 * amps * pts, dt, pts, amps, (unsigned int)(b1 - b0), 0, N, false, out + b0 * nn);
+            } catch (...) {
+                ecs[g] = PARAMENT_STATUS_HOST_ALLOC_FAILED;
+            }
         };
     }
     for (unsigned int g = 1; g < G; ++g) ctx_of(g)->worker->submit([&run, g] { run(g); });   // fits std::function's inline storage
     run(0);
     for (unsigned int g = 1; g < G; ++g) ctx_of(g)->worker->wait();
-    cudaSetDevice(c->device);
     long long launches = 0;
     double h2d = 0;
     for (unsigned int g = 0; g < G; ++g) {
@@ -1167,8 +1336,10 @@ Parament_ErrorCode set_device_list(Context *c, const int *devices, int count) {
     if (!devices || count < 1 || cudaGetDeviceCount(&ndev) != cudaSuccess) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
     for (int i = 0; i < count; ++i)
         if (devices[i] < 0 || devices[i] >= ndev) return fail(c, PARAMENT_STATUS_INVALID_VALUE);
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    {
+        DeviceGuard guard(c->device);
+        cudaStreamSynchronize(c->stream);
+    }
     destroy_peers(c);
     if (devices[0] != c->device) {
         const Parament_ErrorCode ec = move_to_device(c, devices[0]);
@@ -1194,7 +1365,6 @@ Parament_ErrorCode set_device_list(Context *c, const int *devices, int count) {
         }
         if (ec != PARAMENT_STATUS_SUCCESS) {
             destroy_peers(c);
-            cudaSetDevice(c->device);
             return fail(c, ec);
         }
         c->peers.push_back(p);
@@ -1202,14 +1372,13 @@ Parament_ErrorCode set_device_list(Context *c, const int *devices, int count) {
         if (devices[i] != c->device) {   // direct NVLink path for the partials: the helper's kernels store into this device's memory
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, devices[i], c->device) == cudaSuccess && can) {
-                cudaSetDevice(devices[i]);
+                DeviceGuard guard(devices[i]);
                 const cudaError_t e = cudaDeviceEnablePeerAccess(c->device, 0);
                 p->peer_store_ok = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
             }
             cudaGetLastError();
         }
     }
-    cudaSetDevice(c->device);
     c->lastError = PARAMENT_STATUS_SUCCESS;
     return PARAMENT_STATUS_SUCCESS;
 }
@@ -1222,6 +1391,18 @@ Parament_ErrorCode set_device_count(Context *c, int ngpus) {
     std::vector<int> list(ngpus);
     for (int i = 0; i < ngpus; ++i) list[i] = (c->device + i) % ndev;
     return set_device_list(c, list.data(), ngpus);
+}
+
+// C++ exceptions must not cross the C ABI: every entry point that can allocate on the host runs through this.
+template <typename F>
+Parament_ErrorCode guarded(void *h, F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return fail(as_ctx(h), PARAMENT_STATUS_HOST_ALLOC_FAILED);
+    } catch (...) {
+        return fail(as_ctx(h), PARAMENT_FAIL);
+    }
 }
 
 }  // namespace
@@ -1238,54 +1419,64 @@ Parament_ErrorCode Parament_destroy_fp64(struct Parament_Context_f64 *h) { retur
 
 Parament_ErrorCode Parament_setHamiltonian(struct Parament_Context_f32 *h, const Parament_c64 *H0, const Parament_c64 *H1,
                                            unsigned int dim, unsigned int amps, bool use_magnus, enum Parament_QuadratureSpec q) {
-    return set_hamiltonian<Parament_c64>(as_ctx(h), H0, H1, dim, amps, use_magnus, (int)q);
+    return guarded(h, [&] { return set_hamiltonian<Parament_c64>(as_ctx(h), H0, H1, dim, amps, use_magnus, (int)q); });
 }
 Parament_ErrorCode Parament_setHamiltonian_fp64(struct Parament_Context_f64 *h, const Parament_c128 *H0, const Parament_c128 *H1,
                                                 unsigned int dim, unsigned int amps, bool use_magnus, Parament_QuadratureSpec q) {
-    return set_hamiltonian<Parament_c128>(as_ctx(h), H0, H1, dim, amps, use_magnus, (int)q);
+    return guarded(h, [&] { return set_hamiltonian<Parament_c128>(as_ctx(h), H0, H1, dim, amps, use_magnus, (int)q); });
 }
 
 Parament_ErrorCode Parament_equiprop(struct Parament_Context_f32 *h, const Parament_c64 *carr, double dt, unsigned int pts,
                                      unsigned int amps, Parament_c64 *out) {
-    return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, 1, 0, 0, true, out);
+    return guarded(h, [&] { return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, 1, 0, 0, true, out); });
 }
 Parament_ErrorCode Parament_equiprop_fp64(struct Parament_Context_f64 *h, const Parament_c128 *carr, double dt, unsigned int pts,
                                           unsigned int amps, Parament_c128 *out) {
-    return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, 1, 0, 0, true, out);
+    return guarded(h, [&] { return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, 1, 0, 0, true, out); });
 }
 
 Parament_ErrorCode Parament_equipropBatch(struct Parament_Context_f32 *h, const Parament_c64 *carr, double dt, unsigned int pts,
                                           unsigned int amps, unsigned int batch, Parament_c64 *out) {
-    return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, batch, 0, 0, true, out);
+    return guarded(h, [&] { return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, batch, 0, 0, true, out); });
 }
 Parament_ErrorCode Parament_equipropBatch_fp64(struct Parament_Context_f64 *h, const Parament_c128 *carr, double dt, unsigned int pts,
                                                unsigned int amps, unsigned int batch, Parament_c128 *out) {
-    return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, batch, 0, 0, true, out);
+    return guarded(h, [&] { return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, batch, 0, 0, true, out); });
 }
 
 Parament_ErrorCode Parament_equipropDevice(struct Parament_Context_f32 *h, const Parament_c64 *carr_dev, double dt, unsigned int pts,
                                            unsigned int amps, unsigned int batch, Parament_c64 *out_dev, void *stream) {
-    return equiprop_device<Parament_c64>(as_ctx(h), carr_dev, dt, pts, amps, batch, out_dev, stream);
+    return guarded(h, [&] { return equiprop_device<Parament_c64>(as_ctx(h), carr_dev, dt, pts, amps, batch, out_dev, stream); });
 }
 Parament_ErrorCode Parament_equipropDevice_fp64(struct Parament_Context_f64 *h, const Parament_c128 *carr_dev, double dt, unsigned int pts,
                                                 unsigned int amps, unsigned int batch, Parament_c128 *out_dev, void *stream) {
-    return equiprop_device<Parament_c128>(as_ctx(h), carr_dev, dt, pts, amps, batch, out_dev, stream);
+    return guarded(h, [&] { return equiprop_device<Parament_c128>(as_ctx(h), carr_dev, dt, pts, amps, batch, out_dev, stream); });
 }
 
 Parament_ErrorCode Parament_equipropSlice(struct Parament_Context_f32 *h, const Parament_c64 *carr, double dt, unsigned int pts,
                                           unsigned int amps, unsigned long long lo, unsigned long long hi, Parament_c64 *out) {
-    return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, 1, lo, hi, false, out);
+    return guarded(h, [&] { return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, 1, lo, hi, false, out); });
 }
 Parament_ErrorCode Parament_equipropSlice_fp64(struct Parament_Context_f64 *h, const Parament_c128 *carr, double dt, unsigned int pts,
                                                unsigned int amps, unsigned long long lo, unsigned long long hi, Parament_c128 *out) {
-    return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, 1, lo, hi, false, out);
+    return guarded(h, [&] { return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, 1, lo, hi, false, out); });
+}
+
+// host amplitudes in, partial propagator left on the device (include/parament.h section 2)
+Parament_ErrorCode Parament_equipropSliceToDevice(struct Parament_Context_f32 *h, const Parament_c64 *carr, double dt, unsigned int pts,
+                                                  unsigned int amps, unsigned long long lo, unsigned long long hi, Parament_c64 *out_dev) {
+    return guarded(h, [&] { return equiprop_host<Parament_c64>(as_ctx(h), carr, dt, pts, amps, 1, lo, hi, false, out_dev, nullptr, 0, true); });
+}
+Parament_ErrorCode Parament_equipropSliceToDevice_fp64(struct Parament_Context_f64 *h, const Parament_c128 *carr, double dt, unsigned int pts,
+                                                       unsigned int amps, unsigned long long lo, unsigned long long hi, Parament_c128 *out_dev) {
+    return guarded(h, [&] { return equiprop_host<Parament_c128>(as_ctx(h), carr, dt, pts, amps, 1, lo, hi, false, out_dev, nullptr, 0, true); });
 }
 
 Parament_ErrorCode Parament_combine(struct Parament_Context_f32 *h, const Parament_c64 *parts, unsigned int count, Parament_c64 *out) {
-    return combine_host<Parament_c64>(as_ctx(h), parts, count, out);
+    return guarded(h, [&] { return combine_host<Parament_c64>(as_ctx(h), parts, count, out); });
 }
 Parament_ErrorCode Parament_combine_fp64(struct Parament_Context_f64 *h, const Parament_c128 *parts, unsigned int count, Parament_c128 *out) {
-    return combine_host<Parament_c128>(as_ctx(h), parts, count, out);
+    return guarded(h, [&] { return combine_host<Parament_c128>(as_ctx(h), parts, count, out); });
 }
 
 Parament_ErrorCode Parament_combineDevice(void *h, const void *parts_dev, unsigned int count, void *out_dev, void *stream) {
@@ -1366,7 +1557,7 @@ double Parament_lastStat(void *h, int key) {
         case 0: {
             if (c->stat_devices > 1) return c->stat_ms;   // shared call: host wall clock around all devices and the combine
             float ms = 0;
-            cudaSetDevice(c->device);
+            DeviceGuard guard(c->device);
             if (cudaEventSynchronize(c->ev_stop) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop) == cudaSuccess) return ms;
             cudaGetLastError();
             return -1.0;
@@ -1390,6 +1581,7 @@ double Parament_lastStat(void *h, int key) {
             return c->stat_horner ? 2.0 + (M >> 1) : (double)std::max(M, 1);
         }
         case 13: return c->family == 3 ? k4_real_products(c->npad) : 4;   // real products per complex matrix product
+        case 14: return c->stat_series_norm;
         case 11: return c->stat_devices;
         case 12: return (double)c->peers.size() + 1.0;
         default: return -1.0;
@@ -1413,23 +1605,20 @@ Parament_ErrorCode Parament_setDeviceList(void *h, const int *devices, int count
 
 namespace {
 Parament_ErrorCode move_to_device(Context *c, int device) {
-    // move: drop everything that lives on the old device
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    free_dev(c->d_gather);
-    free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
-    free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
-    cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); destroy_copy_events(c);
-    for (cudaStream_t &q : c->f3_streams) if (q) { cudaStreamDestroy(q); q = nullptr; }
-    cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->stream);
+    // move: drop everything that lives on the old device (handles are nulled: a failed re-creation leaves nothing dangling)
+    {
+        DeviceGuard guard(c->device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        destroy_device_objects(c);
+    }
     c->device = device;
     c->have_hamiltonian = false;
-    if (cudaSetDevice(device) != cudaSuccess ||
-        cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess || !create_copy_events(c) ||
-        cudaEventCreate(&c->ev_start) != cudaSuccess || cudaEventCreate(&c->ev_stop) != cudaSuccess)
+    c->series_cache.valid = false;
+    DeviceGuard guard(device);
+    if (!create_device_objects(c)) {
+        destroy_device_objects(c);
         return fail(c, PARAMENT_STATUS_CUBLAS_INIT_FAILED);
+    }
     return PARAMENT_STATUS_SUCCESS;
 }
 }  // namespace

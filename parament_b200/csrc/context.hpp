@@ -85,7 +85,12 @@ struct Context {
     int dim = 0;
     int amps = 0;        // controls given to setHamiltonian
     int nmats = 0;       // 1 + amps (+ amps + amps(amps-1)/2 commutators with Magnus)
-    double Hnorm = 0.0;
+    double Hnorm = 0.0;      // the reference's norm bound (parament.cpp:280-284): error semantics and the reported table degree
+    std::vector<double> sigma_max;   // largest singular value of H0 and of every control matrix (power iteration, setHamiltonian)
+    int norm_mode = 1;       // 1: series domain from the spectral bound below (dim > 16); 0: the reference's Hnorm ($PARAMENT_NORM=reference)
+    double stat_series_norm = 0.0;   // norm the series of the last call was built for
+    DeviceBuffer d_absmax;   // per control: max |c_k|^2 of the last call's amplitude stream (bits of a double, atomicMax)
+    double *h_absmax = nullptr;      // pinned host copy
     std::vector<zc> mats;   // nmats * dim * dim, row-major
     int family = 0;      // 1 = register-resident warp kernels, 2 = persistent CTA chain kernel, 3 = batched GEMM pipeline
     int npad = 0;
@@ -97,6 +102,7 @@ struct Context {
     DeviceBuffer d_carr, d_out, d_partials;
     DeviceBuffer d_Y, d_pending, d_tree;   // families 2 / 3: series slots, pending partial products, tree scratch
     DeviceBuffer d_comb, d_comb2;   // combine of time-slice partials
+    DeviceBuffer d_counters;        // arrival counters of the fused ordered reduction (zero between launches)
     DeviceBuffer d_gather;          // single-process multi-GPU: partial propagators of all devices, slice order
 
     // Single-process multi-GPU (Parament_setDevices / $PARAMENT_NUM_GPUS): helper contexts on the other devices, owned

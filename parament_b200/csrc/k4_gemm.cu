@@ -12,6 +12,7 @@
 // k4_zgemm_kernel       dim > 64: the same tile code as a batched launch over the S steps of an L2-resident time chunk.
 // k4_assemble_kernel    batched assembly Y_s = sigma (H0 + sum_t c_t(s) H_t) + series start values (fuses the reference's
 //                       outer-product broadcast, quadrature kernels and rank-A' GEMM, parament.cpp:491-554).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include "coef.cuh"
@@ -478,6 +479,39 @@ __global__ void k4_eform_kernel(const IO *__restrict__ P, int n, int npad, int c
         v = make_double2((double)x.x - (r == c ? 1.0 : 0.0), (double)x.y);
     }
     E[e] = v;
+}
+
+// max_j |c_k(j)|^2 per control k over every pulse of the call (spectral bound of the step Hamiltonians, api.cu series_norm_for_call).
+// grid = (blocks, amps); out[k] holds the bits of a non-negative double, which order like unsigned integers.
+template <typename IO>
+__global__ void __launch_bounds__(256)
+k4_absmax_kernel(const IO *__restrict__ carr, unsigned int batch, unsigned int amps, size_t stride, size_t pts,
+                 unsigned long long *__restrict__ out) {
+    const unsigned int k = blockIdx.y;
+    double best = 0.0;
+    for (unsigned int b = 0; b < batch; ++b) {
+        const IO *c = carr + ((size_t)b * amps + k) * stride;
+        for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < pts; j += (size_t)gridDim.x * blockDim.x) {
+            const IO v = __ldg(c + j);
+            const double m = (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+            best = m > best ? m : best;   // a NaN amplitude never wins: the propagator will be NaN anyway
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { const double other = __shfl_xor_sync(0xffffffffu, best, o); best = other > best ? other : best; }
+    if ((threadIdx.x & 31) == 0 && best > 0.0) atomicMax(out + k, (unsigned long long)__double_as_longlong(best));
+}
+
+cudaError_t k4_absmax(bool fp64_io, const void *carr, unsigned int batch, unsigned int amps, size_t stride, size_t pts,
+                      unsigned long long *out_dev, cudaStream_t stream) {
+    if (amps == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(out_dev, 0, (size_t)amps * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    const size_t work = pts * batch;
+    const unsigned int bx = (unsigned int)std::max<size_t>(1, std::min<size_t>(592, (work + 2047) / 2048));
+    dim3 grid(bx, amps);
+    if (fp64_io) k4_absmax_kernel<double2><<<grid, 256, 0, stream>>>((const double2 *)carr, batch, amps, stride, pts, out_dev);
+    else         k4_absmax_kernel<float2><<<grid, 256, 0, stream>>>((const float2 *)carr, batch, amps, stride, pts, out_dev);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -62,6 +62,10 @@ cudaError_t k4_assemble(bool fp64_io, const SeriesParams &p, const SeriesProgram
 cudaError_t k4_eform(bool fp64_io, const void *P, int n, int npad, int count, double2 *E, cudaStream_t stream);   // E = P - I, padded
 cudaError_t k4_finish(bool fp64_io, const double2 *E, int n, int npad, void *out, bool add_identity, cudaStream_t stream);
 
+// out_dev[k] <- bits of max |c_k|^2 (double) over `batch` pulses of `pts` points; control arrays are `stride` points apart.
+cudaError_t k4_absmax(bool fp64_io, const void *carr, unsigned int batch, unsigned int amps, size_t stride, size_t pts,
+                      unsigned long long *out_dev, cudaStream_t stream);
+
 // Persistent single-tile chain kernel (npad == 32 or 64): `grid` CTAs each walk a contiguous range of the nsteps steps
 // with their matrices in a private L2-resident scratch (kSeriesSlots + 2 matrices per CTA) and leave one E-form partial each.
 cudaError_t k4_chain(bool fp64_io, const SeriesParams &p, const SeriesProgram &prog, const void *carr, const double2 *H,

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from oracle.equiprop_oracle import equiprop_oracle  # noqa: E402
-from parament_b200.workloads import make_workload  # noqa: E402
+from workloads import make_workload  # noqa: E402
 
 if __name__ == "__main__":
     cores = os.cpu_count()

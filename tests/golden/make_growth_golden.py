@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from oracle.equiprop_oracle import equiprop_oracle  # noqa: E402
-from parament_b200.workloads import make_workload  # noqa: E402
+from workloads import make_workload  # noqa: E402
 
 SIZES = {"C2": [1001, 10001, 100001, 400001], "C3": [1000, 10000, 100000, 300000], "C4": [100, 1000, 10000]}
 

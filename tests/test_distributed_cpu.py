@@ -39,7 +39,7 @@ def _worker(rank, world, port, name, pts, out_path):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from parament_b200.distributed import slice_bounds, time_sliced_equiprop
-    from parament_b200.workloads import make_workload
+    from workloads import make_workload
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     w = make_workload(name, pts=pts)
     U = time_sliced_equiprop(OracleContext(w), w.dt, w.carr)
@@ -56,7 +56,7 @@ def _worker(rank, world, port, name, pts, out_path):
 @pytest.mark.parametrize("name,pts,world", [("C2", 2001, 2), ("C1", 1000, 2), ("C2", 603, 3)])
 def test_time_sliced_equiprop_gloo(tmp_path, name, pts, world):
     from oracle.equiprop_oracle import equiprop_oracle, rel_frobenius
-    from parament_b200.workloads import make_workload
+    from workloads import make_workload
     out = str(tmp_path / "u.npy")
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, name, pts, out), nprocs=world, join=True)

@@ -15,7 +15,7 @@ import pytest
 
 from oracle.equiprop_oracle import equiprop_oracle, rel_frobenius
 from parament_b200 import constants as K
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -166,7 +166,7 @@ def test_unchanged_reference_wrapper_with_num_gpus_env(tmp_path, gpu_count):
         np.float = float
         sys.path.insert(0, {wrapper!r}); sys.path.insert(0, {ROOT!r})
         import parament
-        from parament_b200.workloads import make_workload
+        from workloads import make_workload
         w = make_workload("C3", pts=3000)
         ctx = parament.Parament(precision="fp64")
         ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=False, quadrature_mode="none")

@@ -104,7 +104,7 @@ def test_ordered_product_order():
 
 
 def test_parallel_slices_match_serial():
-    from parament_b200.workloads import make_workload
+    from workloads import make_workload
     w = make_workload("C2", pts=4001)
     a = equiprop_oracle(w.H0, w.H1, w.carr, w.dt, w.quadrature, w.use_magnus, w.precision, workers=1)
     b = equiprop_oracle(w.H0, w.H1, w.carr, w.dt, w.quadrature, w.use_magnus, w.precision, workers=3, block=97)

@@ -17,7 +17,7 @@ import pytest
 
 from cases import extended_cases, reference_test_cases
 from oracle.equiprop_oracle import effective_steps, equiprop_oracle, rel_frobenius
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 
 pytestmark = pytest.mark.gpu
 
@@ -501,13 +501,13 @@ def test_batched_gemm_variants(tmp_path, variant):
         import sys, numpy as np
         sys.path.insert(0, {root!r})
         import parament_b200 as pb
-        from parament_b200.workloads import make_workload
+        from workloads import make_workload
         for name, pts in (("C4", 150), ("C3", 300)):
             w = make_workload(name, pts=pts)
             H0, H1 = w.H0, w.H1
             if name == "C3":                      # C3's pulse on a dim-96 system: zero-padded to 128 in the batched pipeline
                 rng = np.random.default_rng(5)
-                from parament_b200.workloads import rand_herm
+                from workloads import rand_herm
                 H0 = (0.5 * rand_herm(rng, 96)).astype(np.complex128)
                 H1 = np.stack([(0.125 * rand_herm(rng, 96)).astype(np.complex128) for _ in range(4)])
             with pb.Parament("fp64") as ctx:

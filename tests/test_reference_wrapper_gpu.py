@@ -33,7 +33,7 @@ def test_unchanged_wrapper_in_process_matches_mirror(tmp_path):
     code = """
 import numpy as np; np.float = float
 import parament, parament_b200
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 w = make_workload("C2", pts=4001)
 with parament.Parament() as ctx:
     ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=False, quadrature_mode="simpson")

@@ -2,7 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import parament_b200 as pb
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 for name in sys.argv[1:]:
     w = make_workload(name)
     carr = torch.from_numpy(np.ascontiguousarray(w.carr)).cuda()

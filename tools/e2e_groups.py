@@ -3,7 +3,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import parament_b200 as pb
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 name = sys.argv[1] if len(sys.argv) > 1 else "C5"
 w = make_workload(name)
 carr = torch.from_numpy(np.ascontiguousarray(w.carr.reshape(w.batch, w.amps, w.pts))).pin_memory().numpy()

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import parament_b200 as pb
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 
 QUAD = {"none": 0, "midpoint": 0x01000000, "simpson": 0x02000000}
 growth = np.load(os.path.join(ROOT, "tests", "golden", "growth.npz"))

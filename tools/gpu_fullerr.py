@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import parament_b200 as pb
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 from oracle.equiprop_oracle import rel_frobenius
 for name in sys.argv[1:] or ["C1", "C2", "C3", "C4"]:
     gold = np.load(os.path.join("tests", "golden", f"full_{name}.npz"))["U"]

@@ -25,7 +25,7 @@ def main():
     import torch
     import parament_b200 as pb
     from parament_b200 import constants as K
-    from parament_b200.workloads import make_workload
+    from workloads import make_workload
     ndev = torch.cuda.device_count()
     counts = [g for g in (1, 2, 4, 8) if g <= ndev]
     rows = []

@@ -3,7 +3,7 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import parament_b200 as pb
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 
 def sweep(name, sizes, reps=3, **kw):
     for pts in sizes:

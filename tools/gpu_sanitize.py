@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import parament_b200 as pb
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 from oracle.equiprop_oracle import equiprop_oracle, rel_frobenius
 
 # C4 pts=700: the four-stream chunk pipeline with both halves of the pending list in use (cap + carry)

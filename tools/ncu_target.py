@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import parament_b200 as pb
-from parament_b200.workloads import make_workload
+from workloads import make_workload
 name, pts = sys.argv[1], int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 kw = {"batch": int(sys.argv[4])} if len(sys.argv) > 4 else {}

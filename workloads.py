@@ -4,7 +4,9 @@ Shapes and normalisation follow SURVEY.md section 8(d): every matrix is Hermitia
 reference's norm bound (`parament.cpp:280-284`, max-row-abs-sum of H0 plus that of every H_k) is
 exactly 1, pulses are smooth, real and bounded by 1, and dt is chosen so that Hnorm*h = 0.2, which makes
 the reference pick MMAX = 5 (complex64) / 11 (complex128) (`parament.cpp:726,750`).  numpy only: the
-same generator feeds the GPU library, the CPU oracle and the reference build.
+same generator feeds the GPU library, the CPU oracle and the reference build.  This module is bench / test
+infrastructure and deliberately lives outside the parament_b200 package: importing it must not load libparament.so
+(bench.py --impl reference runs the reference's library only).
 """
 from __future__ import annotations
 
@@ -78,6 +80,10 @@ _SPECS = {
     "C3": (3, 64, 4, 1_000_000, "fp64", "none", False, 1),
     "C4": (4, 256, 8, 100_000, "fp64", "none", False, 1),
     "C5": (5, 8, 2, 1_000, "fp32", "none", False, 10_000),
+    # variants of C2 the north_star names but BASELINE.json has no line for: the Magnus commutator terms (A' = 5 effective
+    # terms per step) and complex amplitudes (the full-cost branch of the assembly)
+    "C2_magnus": (2, 16, 2, 1_000_000, "fp32", "simpson", True, 1),
+    "C2_complex": (2, 16, 2, 1_000_000, "fp32", "simpson", False, 1),
 }
 
 DESCRIPTIONS = {
@@ -86,11 +92,13 @@ DESCRIPTIONS = {
     "C3": "6-qubit system dim=64, 4 controls, 1e6 points, complex128",
     "C4": "8-qubit transmon chain dim=256, 8 controls, 1e5 points, complex128",
     "C5": "GRAPE ensemble: 1e4 independent dim=8 pulses x 1e3 points, complex64",
+    "C2_magnus": "C2 with use_magnus=True: dim=16, 2 controls (5 effective terms), 1e6 points, complex64, SIMPSON + Magnus commutators",
+    "C2_complex": "C2 with complex-valued amplitudes: dim=16, 2 controls, 1e6 points, complex64, SIMPSON",
 }
 
 
 def make_workload(name: str, pts: int | None = None, batch: int | None = None, x: float = 0.2) -> Workload:
-    """Build configuration `name` (C1..C5); `pts` / `batch` override the size (reduced-N parity cases)."""
+    """Build configuration `name` (C1..C5, C2_magnus, C2_complex); `pts` / `batch` override the size (reduced-N parity cases)."""
     cfg, n, A, P, prec, quad, mag, B = _SPECS[name]
     P = P if pts is None else int(pts)
     B = B if batch is None else int(batch)
@@ -105,6 +113,8 @@ def make_workload(name: str, pts: int | None = None, batch: int | None = None, x
         H1 = np.stack([(0.5 / A) * rand_herm(rng, n) for _ in range(A)])
         carr = smooth_pulses(rng, A, P, batch=B if B > 1 else None,
                              dtype=np.float32 if prec == "fp32" else np.float64)
+        if name == "C2_complex":     # |c_k| <= 1 still holds: both parts are bounded by 1 / sqrt(2)
+            carr = (carr + 1j * smooth_pulses(rng, A, P, dtype=np.float32)) / np.sqrt(2.0)
     ct = np.complex64 if prec == "fp32" else np.complex128
     H0 = H0.astype(ct)
     H1 = H1.astype(ct)
