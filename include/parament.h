@@ -248,7 +248,8 @@ PARAMENT_API Parament_ErrorCode Parament_setDevices(void *handle, int ngpus);
 PARAMENT_API Parament_ErrorCode Parament_setDeviceList(void *handle, const int *devices, int count);
 
 /* Pipe-peak microbenchmark on the current CUDA device, used as roofline denominator by bench.py.
- * kind: 0 FP32 FFMA TFLOP/s, 1 FP64 DFMA TFLOP/s, 2 FP64 tensor-pipe DMMA TFLOP/s, 3 HBM copy GB/s. */
+ * kind: 0 FP32 FFMA TFLOP/s, 1 FP64 DFMA TFLOP/s, 2 FP64 tensor-pipe DMMA TFLOP/s, 3 HBM copy GB/s,
+ * 4 TF32 warp-level tensor path (mma.sync.m16n8k8) TFLOP/s. */
 PARAMENT_API double Parament_measurePeak(int kind);
 
 /* Library identification string, e.g. "parament-b200 0.1 (sm_100a)". */

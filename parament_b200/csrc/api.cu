@@ -1206,6 +1206,11 @@ Parament_ErrorCode equiprop_device(Context *c, const T *carr_dev, double dt, uns
 // Device-resident core: parts_dev / out_dev in the IO precision, scratch from the context (grow-only), no synchronisation.
 Parament_ErrorCode combine_device_core(Context *c, const void *parts_dev, unsigned int count, void *out_dev, cudaStream_t st) {
     const int n = c->dim;
+    c->stat_launches = 0;
+    if (c->family == 1) {   // register-resident family: one launch of one CTA
+        PB_LAUNCH(launch_k3_combine(c->npad, c->fp64, parts_dev, count, n, out_dev, st));
+        return PARAMENT_STATUS_SUCCESS;
+    }
     const int gp = k4_pad(n);
     const size_t gnn = (size_t)gp * gp;
     if (!ensure_dev(c->d_comb, (size_t)count * gnn * sizeof(double2)) ||

@@ -364,6 +364,85 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
     }
 }
 
+// out (n x n row-major, IO precision) = Q^T: the running products are kept transposed (frag.cuh).
+template <int NT, typename IO>
+__device__ __forceinline__ void store_propagator(const AccFrag<NT> &Q, IO *__restrict__ o, int n, int lane) {
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = acc_row(lane, mt), cidx = acc_col(lane, nt, i);
+                if (r < n && cidx < n) {
+                    IO v;
+                    v.x = Q.re[mt][nt][i];
+                    v.y = Q.im[mt][nt][i];
+                    o[(size_t)cidx * n + r] = v;
+                }
+            }
+}
+
+// Fragments of P^T from a propagator P stored n x n row-major in the IO precision (identity in the padding).
+template <int NT, typename IO>
+__device__ __forceinline__ void load_acc_of_transpose(AccFrag<NT> &Q, const IO *__restrict__ P, int n, int lane) {
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = acc_row(lane, mt), c = acc_col(lane, nt, i);
+                double re = (r == c) ? 1.0 : 0.0, im = 0.0;
+                if (r < n && c < n) { const IO v = P[(size_t)c * n + r]; re = v.x; im = v.y; }
+                Q.re[mt][nt][i] = re;
+                Q.im[mt][nt][i] = im;
+            }
+}
+template <int NT, typename IO>
+__device__ __forceinline__ void load_bfrag_of_transpose(BFrag<NT> &B, const IO *__restrict__ P, int n, int lane) {
+#pragma unroll
+    for (int kt = 0; kt < 2 * NT; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int r = bf_row(lane, kt), c = bf_col(lane, nt);
+            double re = (r == c) ? 1.0 : 0.0, im = 0.0;
+            if (r < n && c < n) { const IO v = P[(size_t)c * n + r]; re = v.x; im = v.y; }
+            B.re[kt][nt] = re;
+            B.im[kt][nt] = im;
+            B.nim[kt][nt] = neg(im);
+        }
+}
+
+// Ordered product of `count` propagators of time slices (multi-GPU combine, dim <= 16): out = parts[count-1] ... parts[0].
+// ONE launch of one CTA: each warp multiplies a contiguous sub-range, then the in-CTA tree (kernel 2's) finishes.
+// Replaces the padded E-form tree on the GEMM kernel (five launches for eight 16 x 16 partials in round 1).
+template <int NT, typename IO>
+__global__ void __launch_bounds__(256)
+k3_combine_kernel(const IO *__restrict__ parts, unsigned int count, int n, IO *__restrict__ out) {
+    constexpr int NP = 8 * NT;
+    __shared__ double2 smem[4 * NP * NP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const unsigned int b0 = (unsigned int)((unsigned long long)count * warp / nwarps);
+    const unsigned int b1 = (unsigned int)((unsigned long long)count * (warp + 1) / nwarps);
+    AccFrag<NT> Q;
+    if (b0 < b1) {
+        load_acc_of_transpose<NT, IO>(Q, parts + (size_t)b0 * n * n, n, lane);
+        for (unsigned int b = b0 + 1; b < b1; ++b) {
+            BFrag<NT> B;
+            load_bfrag_of_transpose<NT, IO>(B, parts + (size_t)b * n * n, n, lane);
+            AccFrag<NT> R;
+            set_zero<NT>(R);
+            cmma<NT>(R, Q, B);
+            Q = R;
+        }
+    } else {
+        set_identity<NT>(Q, lane);
+    }
+    cta_ordered_product<NT>(Q, smem, warp, nwarps, lane);
+    if (warp == 0) store_propagator<NT, IO>(Q, out, n, lane);
+}
+
 // Ordered reduction of the partial products of each pulse.  grid = (pulses, groups): CTA (pulse, g) multiplies the
 // contiguous group g of that pulse's nb partials (each warp a contiguous sub-range, the next partial prefetched while the
 // current product runs, then the in-CTA tree).  With mid != nullptr the group product is written back as a partial
@@ -407,21 +486,7 @@ k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, unsigned
         if (mid) {
             store_acc<NT>(Q, mid + ((size_t)pulse * gridDim.y + g) * NP * NP, NP, lane);
         } else {
-            IO *o = out + (size_t)pulse * n * n;
-#pragma unroll
-            for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int r = acc_row(lane, mt), cidx = acc_col(lane, nt, i);
-                        if (r < n && cidx < n) {
-                            IO v;
-                            v.x = Q.re[mt][nt][i];
-                            v.y = Q.im[mt][nt][i];
-                            o[(size_t)cidx * n + r] = v;   // transpose back: P = Q^T
-                        }
-                    }
+            store_propagator<NT, IO>(Q, out + (size_t)pulse * n * n, n, lane);   // transpose back: P = Q^T
         }
     }
 }
@@ -498,6 +563,20 @@ cudaError_t launch_k3_reduce(int npad, bool fp64_io, const double2 *partials, un
                        : launch_k3_t<1, float2>(partials, partials_per_pulse, n, mid, (float2 *)out, batch, stream);
     return fp64_io ? launch_k3_t<2, double2>(partials, partials_per_pulse, n, mid, (double2 *)out, batch, stream)
                    : launch_k3_t<2, float2>(partials, partials_per_pulse, n, mid, (float2 *)out, batch, stream);
+}
+
+template <int NT, typename IO>
+static cudaError_t launch_combine_t(const IO *parts, unsigned int count, int n, IO *out, cudaStream_t stream) {
+    k3_combine_kernel<NT, IO><<<1, 32 * k3_warps_for(count), 0, stream>>>(parts, count, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k3_combine(int npad, bool fp64_io, const void *parts, unsigned int count, int n, void *out, cudaStream_t stream) {
+    if (npad == 8)
+        return fp64_io ? launch_combine_t<1, double2>((const double2 *)parts, count, n, (double2 *)out, stream)
+                       : launch_combine_t<1, float2>((const float2 *)parts, count, n, (float2 *)out, stream);
+    return fp64_io ? launch_combine_t<2, double2>((const double2 *)parts, count, n, (double2 *)out, stream)
+                   : launch_combine_t<2, float2>((const float2 *)parts, count, n, (float2 *)out, stream);
 }
 
 }  // namespace pb

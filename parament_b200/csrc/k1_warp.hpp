@@ -16,4 +16,8 @@ cudaError_t launch_k1_chain(int npad, bool fp64_io, const SeriesParams &p, const
 cudaError_t launch_k3_reduce(int npad, bool fp64_io, const double2 *partials, unsigned int partials_per_pulse, int n,
                              void *out, unsigned int batch, double2 *mid, cudaStream_t stream);
 
+// Multi-GPU combine for dim <= 16 in one launch: out = parts[count-1] ... parts[0]; parts / out are dim x dim propagators in the
+// context precision on the device.
+cudaError_t launch_k3_combine(int npad, bool fp64_io, const void *parts, unsigned int count, int n, void *out, cudaStream_t stream);
+
 }  // namespace pb

@@ -50,7 +50,7 @@ __device__ __forceinline__ void cp_async16_keep(unsigned dst, const void *src, u
 // Geometry for padded dimension N (64: 8 warps of 32x16 tiles; 32: 4 warps of 16x16 tiles).
 template <int N>
 struct Oc {
-    static constexpr int P = N + 4;                 // pitch in double2: rows 8 apart fall into different bank groups (A fragments)
+    static constexpr int P = N;                     // pitch in double2: no padding, the 16-byte column index is XOR-swizzled (at())
     static constexpr int BUF = N * P;               // elements per buffer
     static constexpr int WM = N / 2, WN = N / 4 < 16 ? 16 : N / 4;   // warp tile
     static constexpr int WARPS_N = N / WN, WARPS = (N / WM) * WARPS_N;
@@ -59,8 +59,19 @@ struct Oc {
     static constexpr int NN = N * N;
     static constexpr int EPT = NN / THREADS;        // matrix elements per thread in elementwise phases
     static constexpr int COEF = 3 * BUF;             // offset of the coefficient block of the fused assembly (OC_BLOCK x kMaxTerms)
-    static constexpr size_t SMEM = (3 * (size_t)BUF + 4 * kMaxTerms) * sizeof(double2);
+    static constexpr size_t SMEM = (3 * (size_t)BUF + 4 * kMaxTerms) * sizeof(double2);   // 196 KB + 4 KB at N = 64
     static_assert(EPT == N / 4, "one assembled element per k-tile");
+    // Element (r, c) of a buffer.  The row pitch is a multiple of 128 bytes, so the bank group (16-byte unit within a 128-byte
+    // line) of an element is c & 7; XOR-ing it with s(r) = 0, 5, 2, 7 for r mod 4 = 0..3 makes every access pattern of this
+    // kernel conflict-free per 8-lane LDS.128 / STS.128 phase (lane = 4 g + q):
+    //   A fragments  rows R + g, cols 4 kt + q       : g = 2m, 2m + 1 differ in bit 2 of s -> the two rows use different halves
+    //   B fragments  rows 4 kt + q, cols C + g       : s takes four values with distinct bits (2, 1) -> four disjoint unit pairs
+    //   epilogue     rows R + g, cols C + 2 q (+ 1)  : bit 0 of s separates the even units of row 2m from those of row 2m + 1
+    //   row-wise elementwise passes and cp.async     : eight consecutive units of one row stay a permutation of the line
+    // (the padded pitch N + 4 of round 1 left the B-fragment loads and the epilogue two-way conflicted: 34 % of all
+    // shared-memory wavefronts, profiles/ncu_prof_onchip_C3_r1.txt).
+    __device__ static __forceinline__ int swz(int r) { return ((r & 1) * 5) | (r & 2); }
+    __device__ static __forceinline__ int at(int r, int c) { return r * N + (c ^ swz(r)); }
 };
 constexpr int OC_MAXT = 8;                          // control terms the fused assembly keeps in registers
 constexpr int OC_BLOCK = 4;                         // time steps assembled per pass over the Hamiltonian table
@@ -107,7 +118,7 @@ struct OcAssemble {
     const Term *terms;
     int nterms;
     double sigma;
-    int y_smem;                 // destination buffer of the NEXT step's Y (offset into oc_smem, pitch OC_P)
+    int y_smem;                 // destination buffer of the NEXT step's Y (offset into oc_smem, layout Oc<N>::at)
     int nblock;                 // steps assembled per pass of the table (1..OC_BLOCK)
     double2 *y_glob;            // row-major destinations of the later steps of the block: y_glob[(b - 1) * N*N + e], b >= 1
     uint64_t keep;              // L2 evict-last policy for y_glob
@@ -138,7 +149,7 @@ __device__ __forceinline__ double2 oc_combine(const OcAssemble &as, int b, doubl
     return make_double2(x.x * as.sigma, x.y * as.sigma);
 }
 
-// D = A * B (+ epilogue), A and B in shared memory (pitch OC_P).  All 256 threads; no barrier inside.
+// D = A * B (+ epilogue), A and B in shared memory (layout Oc<N>::at).  All 256 threads; no barrier inside.
 // a thread's own elements of a matrix, in epilogue order (sized for the larger geometry)
 typedef double2 OcOwn[4][2][2];
 
@@ -154,8 +165,8 @@ __device__ __forceinline__ void oc_load_own(OcOwn &y, int m) {
 #pragma unroll
         for (int nt = 0; nt < G::NTL; ++nt) {
             const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q;
-            y[mt][nt][0] = oc_smem[m + r * G::P + c];
-            y[mt][nt][1] = oc_smem[m + r * G::P + c + 1];
+            y[mt][nt][0] = oc_smem[m + G::at(r, c)];
+            y[mt][nt][1] = oc_smem[m + G::at(r, c + 1)];
         }
 }
 
@@ -177,6 +188,11 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
 #pragma unroll
         for (int nt = 0; nt < NTL; ++nt) { cre[mt][nt][0] = cre[mt][nt][1] = 0.0; cim[mt][nt][0] = cim[mt][nt][1] = 0.0; }
 
+    // swizzled column offsets (Oc<N>::at): the rows of this lane's A fragments are congruent to g mod 8, those of its B
+    // fragments to q mod 4, so the XOR masks are per-thread constants
+    const int a_col[2] = {q ^ G::swz(gq), (4 + q) ^ G::swz(gq)};
+    const int b_col = gq ^ G::swz(q);
+
     double2 h0, h[OC_MAXT];
     if (ASSEMBLE) oc_issue_loads<N>(as, tid, h0, h);
 
@@ -184,13 +200,13 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
     for (int kt = 0; kt < OC_N / 4; ++kt) {
         double2 af[MT], bf[NTL];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) af[mt] = sA[(wm0 + 8 * mt + gq) * OC_P + 4 * kt + q];
+        for (int mt = 0; mt < MT; ++mt) af[mt] = sA[(wm0 + 8 * mt + gq) * OC_P + 8 * (kt >> 1) + a_col[kt & 1]];
 #pragma unroll
-        for (int nt = 0; nt < NTL; ++nt) bf[nt] = sB[(4 * kt + q) * OC_P + wn0 + 8 * nt + gq];
+        for (int nt = 0; nt < NTL; ++nt) bf[nt] = sB[(4 * kt + q) * OC_P + wn0 + 8 * nt + b_col];
         if (ASSEMBLE) {
             // element e = tid + 256 kt of the next step's Y: consume the loads issued one k-tile ago, issue the next ones
             const int e = tid + kt * OC_THREADS;
-            oc_smem[as.y_smem + (e / OC_N) * OC_P + (e % OC_N)] = oc_combine(as, 0, h0, h);
+            oc_smem[as.y_smem + G::at(e / OC_N, e % OC_N)] = oc_combine(as, 0, h0, h);
             for (int b = 1; b < as.nblock; ++b) st_keep(as.y_glob + (size_t)(b - 1) * (OC_N * OC_N) + e, oc_combine(as, b, h0, h), as.keep);
             if (kt + 1 < OC_N / 4) oc_issue_loads<N>(as, e + OC_THREADS, h0, h);
         }
@@ -217,7 +233,7 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
             const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q;
             double vr[2] = {cre[mt][nt][0], cre[mt][nt][1]}, vi[2] = {cim[mt][nt][0], cim[mt][nt][1]};
             if (EPI == EPI_FIRST) {
-                const double2 w0 = oc_smem[g.c_smem + r * OC_P + c], w1 = oc_smem[g.c_smem + r * OC_P + c + 1];
+                const double2 w0 = oc_smem[g.c_smem + G::at(r, c)], w1 = oc_smem[g.c_smem + G::at(r, c + 1)];
                 const double2 ws[2] = {w0, w1};
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
@@ -243,7 +259,7 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                     vi[i] = fma(g.ci, yr, vi[i]);
                 }
             } else if (EPI == EPI_CLENSHAW) {
-                const double2 w0 = oc_smem[g.c_smem + r * OC_P + c], w1 = oc_smem[g.c_smem + r * OC_P + c + 1];
+                const double2 w0 = oc_smem[g.c_smem + G::at(r, c)], w1 = oc_smem[g.c_smem + G::at(r, c + 1)];
                 vr[0] = fma(g.beta, w0.x, vr[0]); vi[0] = fma(g.beta, w0.y, vi[0]);
                 vr[1] = fma(g.beta, w1.x, vr[1]); vi[1] = fma(g.beta, w1.y, vi[1]);
 #pragma unroll
@@ -269,7 +285,7 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                     vi[i] = fma(g.by.re, a1.y, fma(g.by.im, a1.x, vi[i]));
                 }
             } else if (EPI == EPI_S12_LR || EPI == EPI_S12_E) {
-                const double2 vs[2] = {oc_smem[g.v_smem + r * OC_P + c], oc_smem[g.v_smem + r * OC_P + c + 1]};
+                const double2 vs[2] = {oc_smem[g.v_smem + G::at(r, c)], oc_smem[g.v_smem + G::at(r, c + 1)]};
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const double2 a1 = y[mt][nt][i], a2 = y2[mt][nt][i];
@@ -288,8 +304,8 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                     vi[i] = fma(g.kY, a1.x, vi[i]);
                 }
             } else if (EPI == EPI_CHAIN) {
-                const double2 e0 = oc_smem[g.c_smem + r * OC_P + c], e1 = oc_smem[g.c_smem + r * OC_P + c + 1];
-                const double2 f0 = oc_smem[g.c_smem2 + r * OC_P + c], f1 = oc_smem[g.c_smem2 + r * OC_P + c + 1];
+                const double2 e0 = oc_smem[g.c_smem + G::at(r, c)], e1 = oc_smem[g.c_smem + G::at(r, c + 1)];
+                const double2 f0 = oc_smem[g.c_smem2 + G::at(r, c)], f1 = oc_smem[g.c_smem2 + G::at(r, c + 1)];
                 vr[0] += e0.x + f0.x; vi[0] += e0.y + f0.y;
                 vr[1] += e1.x + f1.x; vi[1] += e1.y + f1.y;
             }
@@ -297,8 +313,8 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                 st_keep(g.d_glob + r * OC_N + c, make_double2(vr[0], vi[0]), g.keep);
                 st_keep(g.d_glob + r * OC_N + c + 1, make_double2(vr[1], vi[1]), g.keep);
             } else {
-                oc_smem[g.d_smem + r * OC_P + c] = make_double2(vr[0], vi[0]);
-                oc_smem[g.d_smem + r * OC_P + c + 1] = make_double2(vr[1], vi[1]);
+                oc_smem[g.d_smem + G::at(r, c)] = make_double2(vr[0], vi[0]);
+                oc_smem[g.d_smem + G::at(r, c + 1)] = make_double2(vr[1], vi[1]);
             }
         }
     if (EPI == EPI_S12_LR) {
@@ -310,8 +326,8 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                 const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const double2 v = oc_smem[g.v_smem + r * OC_P + c + i], a2 = y2[mt][nt][i];
-                    oc_smem[g.d_smem2 + r * OC_P + c + i] =
+                    const double2 v = oc_smem[g.v_smem + G::at(r, c + i)], a2 = y2[mt][nt][i];
+                    oc_smem[g.d_smem2 + G::at(r, c + i)] =
                         make_double2(fma(g.k2W, a2.x, fma(-g.k2V, v.y, cre[mt][nt][i])), fma(g.k2W, a2.y, fma(g.k2V, v.x, cim[mt][nt][i])));
                 }
             }
@@ -370,7 +386,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                     x.y += ct.re * hh.y + ct.im * hh.x;
                 }
                 const double2 v = make_double2(x.x * p.sigma, x.y * p.sigma);
-                oc_smem[iy * OC_BUF + (e / OC_N) * OC_P + (e % OC_N)] = v;
+                oc_smem[iy * OC_BUF + G::at(e / OC_N, e % OC_N)] = v;
             }
             __syncthreads();
         }
@@ -401,7 +417,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                             const int lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
                             const int r = (warp / G::WARPS_N) * G::WM + 8 * mt + gq, c = (warp % G::WARPS_N) * G::WN + 8 * nt + 2 * q + i;
                             const double2 a1 = y[mt][nt][i], a2 = y2[mt][nt][i];
-                            oc_smem[PB + r * OC_P + c] = make_double2(fma(-c3, a1.y, c4 * a2.x), fma(c3, a1.x, c4 * a2.y));
+                            oc_smem[PB + G::at(r, c)] = make_double2(fma(-c3, a1.y, c4 * a2.x), fma(c3, a1.x, c4 * a2.y));
                         }
             }
             __syncthreads();
@@ -449,8 +465,8 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
                             const int r = wm0 + 8 * mt + gq, c = wn0 + 8 * nt + 2 * q + i;
-                            const double2 v = oc_smem[PB + r * OC_P + c], a1 = y[mt][nt][i], a2 = y2[mt][nt][i];
-                            oc_smem[PA + r * OC_P + c] = make_double2(fma(tY, a1.x, fma(-tW, a2.y, tV * v.x)), fma(tY, a1.y, fma(tW, a2.x, tV * v.y)));
+                            const double2 v = oc_smem[PB + G::at(r, c)], a1 = y[mt][nt][i], a2 = y2[mt][nt][i];
+                            oc_smem[PA + G::at(r, c)] = make_double2(fma(tY, a1.x, fma(-tW, a2.y, tV * v.x)), fma(tY, a1.y, fma(tW, a2.x, tV * v.y)));
                         }
             }
             __syncthreads();
@@ -505,7 +521,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                             double vr = t2.re * a2.x - t2.im * a2.y + (t1.re * a1.x - t1.im * a1.y);
                             double vi = t2.re * a2.y + t2.im * a2.x + (t1.re * a1.y + t1.im * a1.x);
                             if (r == c) { vr += t0.re; vi += t0.im; }
-                            oc_smem[PY + r * OC_P + c] = make_double2(vr, vi);
+                            oc_smem[PY + G::at(r, c)] = make_double2(vr, vi);
                         }
             }
             __syncthreads();
@@ -555,10 +571,10 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                 const int e = tid + it * OC_THREADS;
                 const int r = e / OC_N, c = e % OC_N;
                 const bool diag = (r == c);
-                const double2 v = oc_smem[PY + r * OC_P + c];
-                oc_smem[PA + r * OC_P + c] = make_double2(((prog.u.re * v.x - prog.u.im * v.y) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
+                const double2 v = oc_smem[PY + G::at(r, c)];
+                oc_smem[PA + G::at(r, c)] = make_double2(((prog.u.re * v.x - prog.u.im * v.y) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
                                                 ((prog.u.re * v.y + prog.u.im * v.x) + (diag ? prog.v_lo.im : 0.0)) + (diag ? prog.v.im : 0.0));
-                oc_smem[PB + r * OC_P + c] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
+                oc_smem[PB + G::at(r, c)] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
             }
             __syncthreads();
             int cur = PA, oth = PB;
@@ -594,7 +610,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 #pragma unroll
             for (int it = 0; it < OC_EPT; ++it) {
                 const int e = tid + it * OC_THREADS;
-                st_keep(Fg[f_cur] + e, oc_smem[E + (e / OC_N) * OC_P + (e % OC_N)], keep);
+                st_keep(Fg[f_cur] + e, oc_smem[E + G::at(e / OC_N, e % OC_N)], keep);
             }
             have_f = true;
             __syncthreads();
@@ -606,7 +622,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 #pragma unroll
                 for (int it = 0; it < OC_EPT; ++it) {
                     const int e = tid + it * OC_THREADS;
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Fb + (e / OC_N) * OC_P + (e % OC_N));
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Fb + G::at(e / OC_N, e % OC_N));
                     cp_async16_keep(dst, fsrc + e, keep);
                 }
                 asm volatile("cp.async.commit_group;\n" ::);
@@ -626,7 +642,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
 #pragma unroll
                     for (int it = 0; it < OC_EPT; ++it) {
                         const int e = tid + it * OC_THREADS;
-                        const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Yn + (e / OC_N) * OC_P + (e % OC_N));
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(oc_smem + Yn + G::at(e / OC_N, e % OC_N));
                         cp_async16_keep(dst, ysrc + e, keep);
                     }
                     asm volatile("cp.async.commit_group;\n" ::);

@@ -32,6 +32,18 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_never_loads_this_library():
+    """The reference arm must time the reference's library only: no module of parament_b200 (whose import dlopens
+    parament_b200/lib/libparament.so) may be imported by it."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    r = subprocess.run([sys.executable, "-X", "importtime", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C1",
+                        "--steps", "1", "--warmup", "0", "--configs", "none"], env=env, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "parament_b200" not in r.stderr
+    assert "workloads" in r.stderr        # the generator it does import lives outside the package
+
+
 def test_reference_arm_other_ranks_stay_silent():
     r = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, "--gpus", "2")
     assert r.returncode == 0 and r.stdout.strip() == ""

@@ -122,7 +122,10 @@ def test_degree8_three_product_path(pb, n, A, quad, mag, complex_amps, prec, mon
     """Table degrees 6..8 are evaluated as one degree-8 polynomial in three matrix products (api.cu solve_degree8;
     k1_warp.cu for complex64 contexts of dim <= 16, k4_onchip.cu / k4_gemm.cu build_program above that).  It must be
     active, agree with the oracle, and agree with the Horner-in-Y^2 evaluation of the table degree -- for Hermitian and
-    non-Hermitian generators (complex amplitudes), every quadrature, and Magnus terms beyond the software-pipelined ones."""
+    non-Hermitian generators (complex amplitudes), every quadrature, and Magnus terms beyond the software-pipelined ones.
+    The series is built for the reference's norm bound here (PARAMENT_NORM=reference, read at Parament_create) so that the
+    degree under test is the table's at every dimension; the spectral bound of dim > 16 is covered in test_round2_gpu.py."""
+    monkeypatch.setenv("PARAMENT_NORM", "reference")
     rng = np.random.default_rng(100 * n + A)
     herm = lambda: (lambda g: (g + g.conj().T) / 2)(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
     norm1 = lambda m: m / np.max(np.sum(np.abs(m), axis=1))
@@ -163,7 +166,9 @@ def test_degree8_three_product_path(pb, n, A, quad, mag, complex_amps, prec, mon
 def test_degree12_four_product_path(pb, n, A, quad, mag, prec, dt, onchip, monkeypatch):
     """Table degrees 9..12 are evaluated as one degree-12 polynomial in four matrix products in every kernel family
     (api.cu solve_degree12; k1_warp.cu, k4_onchip.cu, k4_gemm.cu build_program).  It must be active,
-    meet the north_star tolerance against the oracle and agree with the Paterson-Stockmeyer / Horner evaluation."""
+    meet the north_star tolerance against the oracle and agree with the Paterson-Stockmeyer / Horner evaluation.
+    (PARAMENT_NORM=reference: see test_degree8_three_product_path.)"""
+    monkeypatch.setenv("PARAMENT_NORM", "reference")
     rng = np.random.default_rng(1000 * n + A)
     herm = lambda: (lambda g: (g + g.conj().T) / 2)(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
     norm1 = lambda m: m / np.max(np.sum(np.abs(m), axis=1))
@@ -430,14 +435,17 @@ def test_odd_dimensions_and_many_controls(pb, n, A, pts, quad, mag):
 
 
 def test_too_many_effective_terms_is_an_error(pb):
-    """Magnus with 11 controls needs 77 effective terms; the kernels take at most 64 -> code 50 (invalid value), not garbage."""
+    """Magnus with 11 controls needs 77 effective terms; the kernels take at most 64 (include/parament.h): setHamiltonian
+    rejects it with code 50 (invalid value) and leaves the context without a Hamiltonian."""
     n, A = 4, 11
     rng = np.random.default_rng(0)
     H = [rng.standard_normal((n, n)) for _ in range(A + 1)]
     with pb.Parament("fp64") as ctx:
-        ctx.set_hamiltonian(H[0], *H[1:], use_magnus=True, quadrature_mode="simpson")
         with pytest.raises(ValueError, match="Invalid value"):
-            ctx.equiprop(0.001, *rng.uniform(-1, 1, (A, 9)))
+            ctx.set_hamiltonian(H[0], *H[1:], use_magnus=True, quadrature_mode="simpson")
+        out = np.zeros(n * n, dtype=np.complex128)
+        carr = np.ascontiguousarray(rng.uniform(-1, 1, (A, 9)).astype(np.complex128).ravel())
+        assert pb._lib.lib.Parament_equiprop_fp64(ctx._handle, carr, 0.001, 9, A, out) == 80      # no Hamiltonian set
 
 
 def test_device_resident_operands(pb):

@@ -1,0 +1,194 @@
+"""GPU tests added in round 2 (run with -m gpu on the B200 box), all through the C-ABI:
+  * the device-resident entry points (Parament_equipropDevice, Parament_combineDevice, Parament_equipropSliceToDevice)
+    against the float64 oracle, not against the host entry of the same library;
+  * the spectral series norm of dim > 16 (fewer matrix products per step): parity, reported statistics, clamp to the
+    reference's bound, A/B against PARAMENT_NORM=reference;
+  * backward propagation (dt < 0), handles used after destroy, the caller's current device left alone.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from oracle.equiprop_oracle import equiprop_oracle, rel_frobenius
+from workloads import make_workload, rand_herm
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = {"fp32": 1e-5, "fp64": 1e-12}
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import parament_b200
+    return parament_b200
+
+
+@pytest.mark.parametrize("name,pts", [("C2", 50001), ("C1", 4001), ("C3", 300), ("C4", 40), ("C5", 1000)])
+def test_device_entry_vs_oracle(pb, name, pts):
+    torch = pytest.importorskip("torch")
+    w = make_workload(name, pts=pts, batch=3 if name == "C5" else None)
+    tdt = torch.complex64 if w.precision == "fp32" else torch.complex128
+    carr = torch.from_numpy(np.ascontiguousarray(w.carr)).cuda()
+    out = torch.zeros(w.batch, w.dim, w.dim, dtype=tdt, device="cuda")
+    with pb.Parament(w.precision) as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=w.use_magnus, quadrature_mode=w.quadrature)
+        ctx.equiprop_device(w.dt, carr.data_ptr(), w.pts, w.amps, out.data_ptr(), batch=w.batch)
+        torch.cuda.synchronize()
+        assert ctx.stat(1) >= 1
+    got = out.cpu().numpy()
+    pulses = w.carr.reshape(w.batch, w.amps, w.pts)
+    for b in range(w.batch):
+        Uo = equiprop_oracle(w.H0, w.H1, pulses[b], w.dt, w.quadrature, w.use_magnus, w.precision)
+        assert rel_frobenius(got[b], Uo) < TOL[w.precision], (name, b)
+
+
+@pytest.mark.parametrize("name,pts,count", [("C2", 8001, 8), ("C2", 8001, 3), ("C3", 96, 8), ("C4", 16, 4), ("C1", 801, 5)])
+def test_combine_device_vs_numpy(pb, name, pts, count):
+    """Parament_combineDevice on device-resident partials = the ordered product parts[count-1] ... parts[0]."""
+    torch = pytest.importorskip("torch")
+    w = make_workload(name, pts=pts)
+    rng = np.random.default_rng(7)
+    n = w.dim
+    parts = []
+    for g in range(count):   # unitary-ish partial propagators: oracle propagators of short random pulses
+        c = rng.uniform(-1, 1, (w.amps, 9)).astype(w.ctype)
+        parts.append(equiprop_oracle(w.H0, w.H1, c, w.dt, "none", False, w.precision).astype(w.ctype))
+    parts = np.stack(parts)
+    exp = np.eye(n, dtype=np.complex128)
+    for g in range(count):
+        exp = parts[g].astype(np.complex128) @ exp
+    tdt = torch.complex64 if w.precision == "fp32" else torch.complex128
+    dparts = torch.from_numpy(parts).cuda()
+    dout = torch.zeros(n, n, dtype=tdt, device="cuda")
+    with pb.Parament(w.precision) as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=w.use_magnus, quadrature_mode=w.quadrature)
+        ctx.combine_device(dparts.data_ptr(), count, dout.data_ptr())
+        torch.cuda.synchronize()
+        launches = ctx.stat(1)
+        host = ctx.combine(parts)
+    assert rel_frobenius(dout.cpu().numpy(), exp) < (2e-7 if w.precision == "fp32" else 1e-14)
+    assert rel_frobenius(host, exp) < (2e-7 if w.precision == "fp32" else 1e-14)
+    if n <= 16:
+        assert launches == 1          # one launch for the register-resident family (round 1: five)
+
+
+@pytest.mark.parametrize("name,pts", [("C2", 20001), ("C3", 200), ("C1", 2001)])
+def test_slice_to_device_vs_oracle(pb, name, pts):
+    """Host amplitudes in, partial propagator left on the GPU; slices compose to the whole pulse."""
+    torch = pytest.importorskip("torch")
+    w = make_workload(name, pts=pts)
+    tdt = torch.complex64 if w.precision == "fp32" else torch.complex128
+    sfx = "_fp64" if w.precision == "fp64" else ""
+    N = w.steps
+    bounds = [0, N // 3, N // 3, (2 * N) // 3 + 1, N]       # includes an empty slice
+    parts = torch.zeros(len(bounds) - 1, w.dim, w.dim, dtype=tdt, device="cuda")
+    flat = np.ascontiguousarray(w.carr.reshape(-1))
+    with pb.Parament(w.precision) as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=w.use_magnus, quadrature_mode=w.quadrature)
+        fn = getattr(pb._lib.lib, "Parament_equipropSliceToDevice" + sfx)
+        for g in range(len(bounds) - 1):
+            assert fn(ctx._handle, flat, float(w.dt), w.pts, w.amps, bounds[g], bounds[g + 1], ctypes.c_void_p(parts[g].data_ptr())) == 0
+        out = torch.zeros(w.dim, w.dim, dtype=tdt, device="cuda")
+        ctx.combine_device(parts.data_ptr(), len(bounds) - 1, out.data_ptr())
+        torch.cuda.synchronize()
+    assert np.allclose(parts[1].cpu().numpy(), np.eye(w.dim))               # empty slice -> identity, on the device
+    Uo = equiprop_oracle(w.H0, w.H1, w.carr, w.dt, w.quadrature, w.use_magnus, w.precision)
+    assert rel_frobenius(out.cpu().numpy(), Uo) < TOL[w.precision]
+
+
+@pytest.mark.parametrize("dim,prec,quad", [(4, "fp64", "midpoint"), (16, "fp32", "simpson"), (32, "fp64", "none"), (64, "fp64", "simpson"),
+                                           (96, "fp64", "none")])
+def test_backward_propagation(pb, dim, prec, quad):
+    """dt < 0: exp(+i |dt| H) per step, in every kernel family (J_k(-x) = (-1)^k J_k(x); the degree follows |dt|)."""
+    rng = np.random.default_rng(11)
+    ct = np.complex64 if prec == "fp32" else np.complex128
+    H0 = (0.5 * rand_herm(rng, dim)).astype(ct)
+    H1 = np.stack([(0.25 * rand_herm(rng, dim)).astype(ct) for _ in range(2)])
+    carr = rng.uniform(-1, 1, (2, 41)).astype(ct)
+    dt = -0.3
+    with pb.Parament(prec) as ctx:
+        ctx.set_hamiltonian(H0, *H1, quadrature_mode=quad)
+        U = ctx.equiprop(dt, *carr)
+        Uf = ctx.equiprop(-dt, *carr)
+        assert ctx.stat(2) >= 3
+    assert rel_frobenius(U, equiprop_oracle(H0, H1, carr, dt, quad, False, prec)) < TOL[prec]
+    assert rel_frobenius(Uf, equiprop_oracle(H0, H1, carr, -dt, quad, False, prec)) < TOL[prec]
+
+
+def test_spectral_norm_saves_a_product(pb):
+    """dim > 16: the series is built for the spectral bound (stat 14) instead of the reference's row-sum bound (stat 8): at the
+    BASELINE workloads that lowers the degree from 12 (four products) to 8 (three), at unchanged accuracy."""
+    for name, pts in (("C3", 400), ("C4", 24)):
+        w = make_workload(name, pts=pts)
+        with pb.Parament("fp64") as ctx:
+            ctx.set_hamiltonian(w.H0, *w.H1, quadrature_mode="none")
+            U = ctx.equiprop(w.dt, *w.carr)
+            hn, hs, m_used, m_ref, products = ctx.stat(8), ctx.stat(14), ctx.stat(2), ctx.stat(3), ctx.stat(10)
+        assert abs(hn - 1.0) < 1e-12 and 0.05 < hs < 0.5 * hn
+        sig = np.linalg.norm(w.H0, 2) + sum(np.linalg.norm(h, 2) for h in w.H1)
+        assert sig <= hs <= 1.06 * sig                       # a true bound with at most the 5 % margin (|c_k| <= 1 here)
+        assert m_ref == 11 and m_used == 8 and products == 4.0
+        assert rel_frobenius(U, equiprop_oracle(w.H0, w.H1, w.carr, w.dt, "none", False, "fp64")) < 1e-13
+
+
+def test_spectral_norm_never_exceeds_reference_bound(pb):
+    """Amplitudes above 1 leave the reference's series domain; the spectral bound is then clamped to Hnorm,
+    so the degree is never lower than what the reference semantics give, and small amplitudes lower it further."""
+    w = make_workload("C3", pts=50)
+    with pb.Parament("fp64") as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, quadrature_mode="none")
+        ctx.equiprop(w.dt, *(40.0 * w.carr))
+        assert ctx.stat(14) == ctx.stat(8) and ctx.stat(2) == 12
+        ctx.equiprop(w.dt, *(1e-3 * w.carr))
+        hs_small = ctx.stat(14)
+        U = ctx.equiprop(w.dt, *w.carr)
+        assert hs_small < ctx.stat(14) < ctx.stat(8)
+    assert rel_frobenius(U, equiprop_oracle(w.H0, w.H1, w.carr, w.dt, "none", False, "fp64")) < 1e-13
+
+
+def test_reference_norm_switch(tmp_path):
+    """PARAMENT_NORM=reference (read at Parament_create) builds the series for Hnorm at every dimension: degree 12 again."""
+    code = textwrap.dedent(f"""
+        import sys, numpy as np
+        sys.path.insert(0, {ROOT!r})
+        import parament_b200 as pb
+        from workloads import make_workload
+        w = make_workload("C3", pts=200)
+        with pb.Parament("fp64") as ctx:
+            ctx.set_hamiltonian(w.H0, *w.H1, quadrature_mode="none")
+            U = ctx.equiprop(w.dt, *w.carr)
+            assert ctx.stat(2) == 12 and ctx.stat(14) == ctx.stat(8), (ctx.stat(2), ctx.stat(14))
+        np.save({str(tmp_path)!r} + "/u.npy", U)
+    """)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PARAMENT_NORM="reference"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    w = make_workload("C3", pts=200)
+    assert rel_frobenius(np.load(tmp_path / "u.npy"), equiprop_oracle(w.H0, w.H1, w.carr, w.dt, "none", False, "fp64")) < 1e-13
+
+
+def test_handle_used_after_destroy_is_rejected(pb):
+    lib = pb._lib.lib
+    h = ctypes.c_void_p()
+    assert lib.Parament_create(ctypes.byref(h)) == 0
+    assert lib.Parament_destroy(h) == 0
+    out = np.zeros(4, dtype=np.complex64)
+    assert lib.Parament_equiprop(h, np.zeros(1, dtype=np.complex64), 0.1, 1, 1, out) == 50     # not a crash, not stale memory
+    assert lib.Parament_peekAtLastError(h) == 50
+    assert lib.Parament_destroy(h) == 0                                                        # idempotent
+
+
+def test_callers_current_device_is_left_alone(pb, gpu_count):
+    torch = pytest.importorskip("torch")
+    torch.cuda.set_device(0)
+    other = 1 if gpu_count > 1 else 0
+    w = make_workload("C2", pts=2001)
+    with pb.Parament("fp32", device=other) as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, quadrature_mode="simpson")
+        U = ctx.equiprop(w.dt, *w.carr)
+        assert torch.cuda.current_device() == 0
+    assert rel_frobenius(U, equiprop_oracle(w.H0, w.H1, w.carr, w.dt, "simpson", False, "fp32")) < 1e-5
