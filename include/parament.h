@@ -214,13 +214,18 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  *                        3 degree 8 in three products, 4 degree 12 in four products -- all the same polynomial family)
  *  10 complex matrix products executed per effective step (series + ordered product)
  *  13 real matrix products per complex product in the kernel family used (4; 3 for the batched GEMM of dim > 64)
+ *  15 arithmetic of the last call: 0 = double precision on the FP64 tensor pipe (DMMA); 1 = single precision as 3xTF32 split
+ *     products on the warp-level tensor path (complex64 contexts, dim <= 8, accumulated phase N h (s(H0) + sum_k s(H_k)) <= 128:
+ *     the range in which the measured error stays below half the 1e-5 tolerance, profiles/error_growth_tf32_r2.md)
  * Environment switches read at Parament_create (development / A-B testing): PARAMENT_SERIES=clenshaw forces the reference's
  * recurrence, PARAMENT_SERIES=horner the Horner / Paterson-Stockmeyer forms; PARAMENT_NO_ONCHIP=1 selects the L2-scratch
  * chain kernel for dim 17..64; PARAMENT_DEVICE the default CUDA device; PARAMENT_F3_STREAMS=1..4 the chunks in flight for dim > 64
  * (default 4); PARAMENT_K4_3M=0..3 the complex product of the batched GEMM (0: four real products on 64x64 tiles; 3, default: three real
  * products on 64x32 tiles); PARAMENT_K4_FEED=tma the bulk-copy (TMA engine) operand feed of that GEMM in mode 0 (measured slower than cp.async);
  * PARAMENT_COPY_GROUPS=1..8 the copy/compute groups of the host-pointer pipeline; PARAMENT_NORM=reference builds the series for
- * Hnorm at every dimension (A/B of the spectral bound).
+ * Hnorm at every dimension (A/B of the spectral bound); PARAMENT_C64_MATH=f64|tf32 forces the arithmetic of complex64 contexts with
+ * dim <= 8 (default: by step count, key 15), PARAMENT_TF32_MAX_PHASE moves that bound (both read per call), PARAMENT_TF32_COMP=1
+ * switches the compensated running product of the TF32 kernel on (read once per process; measured without effect).
  * Limits: at most 64 effective control terms per step (controls + Magnus commutators: amps <= 64 without Magnus, amps <= 9
  * with it); Parament_setHamiltonian returns PARAMENT_STATUS_INVALID_VALUE beyond that (the reference has no stated limit but
  * its launch configurations break at amps > 16 with Magnus, control_expansion.cu:179).

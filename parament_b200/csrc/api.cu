@@ -20,6 +20,8 @@
 #include <unordered_set>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler injects its library
+
 #include "context.hpp"
 #include "k1_warp.hpp"
 #include "k4_gemm.hpp"
@@ -56,6 +58,15 @@ struct DeviceGuard {
     }
     DeviceGuard(const DeviceGuard &) = delete;
     DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
+// NVTX range for the phases of the path (visible in Nsight Systems / `ncu --nvtx`): the reference only has a commented-out
+// nvtxMarkA (parament.cpp:361).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
 };
 
 Parament_ErrorCode fail(Context *c, Parament_ErrorCode code) {
@@ -345,6 +356,7 @@ template <typename T>
 Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigned int dim, unsigned int amps,
                                    bool use_magnus, int quad) {
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    NvtxRange range("Parament_setHamiltonian");
     DeviceGuard guard(c->device);
     c->have_hamiltonian = false;   // a previous Hamiltonian is dropped first (parament.cpp:216)
     if (use_magnus && quad != PARAMENT_QUADRATURE_SIMPSON)
@@ -385,7 +397,8 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     else                { c->family = 3; c->npad = k4_pad((int)dim); c->k4_slots = k4_wave_slots(c->npad, c->num_sms); }
     c->series_cache.valid = false;
     // spectral bound of the step Hamiltonians (dim > 16, where it saves a matrix product per step; series_norm_for_call)
-    if (c->family != 1 && c->norm_mode == 1)
+    // (also for complex64 contexts of dim <= 8: the accumulated phase decides between FP64 and TF32 arithmetic, tf32_candidate)
+    if ((c->family != 1 && c->norm_mode == 1) || (!c->fp64 && c->npad == 8 && c->family == 1))
         for (int m = 0; m <= A; ++m) c->sigma_max[m] = spectral_norm(c->mats.data() + (size_t)m * nn, (int)dim);
 
     // physical commutators [H0,H_j] and [H_j,H_k], j<k (parament.cpp:289-359): on the host for the
@@ -559,6 +572,30 @@ bool solve_degree12(SeriesParams &p) {
     return true;
 }
 
+// complex64 contexts, dim <= 8, degree-8 form, short pulses: FP32 arithmetic on the TF32 tensor path (k1_tf32.cu) instead of FP64.
+// The tensor core accumulates with truncation, which acts as a coherent rescaling of the time axis: the measured error of that
+// kernel is beta * (accumulated phase), accumulated phase = N h (s(H0) + sum_k s(H_k)) for amplitudes bounded by 1, with
+// beta <= 4e-8 over the sweep of profiles/error_growth_tf32_r2.md.  The path is taken while that stays below half the 1e-5
+// tolerance: kTf32MaxPhase = 128 (C5: 1e3 steps x 0.11 = 110).  $PARAMENT_C64_MATH = f64 | tf32 forces either path,
+// $PARAMENT_TF32_MAX_PHASE moves the bound (A/B runs and the error sweep).
+constexpr double kTf32MaxPhase = 128.0;
+bool tf32_candidate(const Context *c, unsigned long long total_steps, double h) {
+    if (c->fp64 || c->family != 1 || c->npad != 8) return false;
+    const char *em = getenv("PARAMENT_C64_MATH"), *ep = getenv("PARAMENT_TF32_MAX_PHASE");   // read per call: tests toggle them
+    const int mode = !em ? 0 : (strcmp(em, "f64") == 0 ? 1 : (strcmp(em, "tf32") == 0 ? 2 : 0));
+    const double max_phase = ep ? atof(ep) : kTf32MaxPhase;
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    double rho = 0.0;
+    for (double sg : c->sigma_max) rho += sg;
+    if (!(rho > 0.0) || rho > c->Hnorm) rho = c->Hnorm;
+    return (double)total_steps * std::fabs(h) * rho <= max_phase;
+}
+bool use_tf32_path(const Context *c, const SeriesParams &p, const CallSpec &s) {
+    const double h = (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) ? 2.0 * s.dt : s.dt;
+    return p.horner == 3 && tf32_candidate(c, s.total_steps, h);   // the kernel implements the three-product degree-8 form only
+}
+
 Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) {
     const double h = (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) ? 2.0 * s.dt : s.dt;   // parament.cpp:800-802
     int M_ref = 0, M_used = 0;
@@ -568,8 +605,9 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     c->stat_series_norm = Hs;
     // Degrees 6..8 are evaluated as ONE degree-8 polynomial in three matrix products (below); the Y^2 Horner form needs four
     // for degree 6 or 7.  The register-resident family does so for complex64 contexts (its path has no compensated constants).
-    const bool want_s8 = (c->family != 1 || !c->fp64) && !c->MMAX_manual && c->series_mode == 0 && M_used >= 6 && M_used <= 8 &&
-                         Hs * std::fabs(h) <= 1.0;
+    // (The TF32 kernel of short complex64 pulses implements that form only; degrees 4 and 5 cost three products as well.)
+    const bool want_s8 = (c->family != 1 || !c->fp64) && !c->MMAX_manual && c->series_mode == 0 &&
+                         M_used >= (tf32_candidate(c, s.total_steps, h) ? 4 : 6) && M_used <= 8 && Hs * std::fabs(h) <= 1.0;
     if (want_s8) M_used = 8;
     // degrees 9..12 as ONE degree-12 polynomial in four matrix products
     const bool want_s12 = !c->MMAX_manual && c->series_mode == 0 && M_used >= 9 && M_used <= 12 &&
@@ -911,6 +949,28 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
     return PARAMENT_STATUS_SUCCESS;
 }
 
+// Chain launch of the register-resident family in either arithmetic.
+cudaError_t launch_family1_chain(const Context *c, const SeriesParams &p, bool tf32, const void *carr, double2 *partials, unsigned int batch,
+                                 const K1Plan &plan, unsigned long long lo, unsigned long long hi, const K1Final &fz, cudaStream_t st) {
+    if (tf32) return launch_k1_tf32_chain(p, carr, (const double2 *)c->d_H.ptr, partials, batch, plan, lo, hi, fz, st);
+    return launch_k1_chain(c->npad, c->fp64, p, carr, (const double2 *)c->d_H.ptr, partials, batch, plan, lo, hi, fz, st);
+}
+
+// Scratch of a fused chain launch (plan_k1 with fuse = true): the CTA partials, the group products behind them, and the arrival
+// counters (zeroed when the buffer grows; every launch leaves them at zero).  Returns the final-stage arguments.
+bool prepare_fused(Context *c, const K1Plan &plan, unsigned int batch, void *out_dev, cudaStream_t st, K1Final &fz) {
+    const size_t np2 = (size_t)c->npad * c->npad;
+    const size_t mid_elems = (size_t)batch * plan.groups_per_pulse * np2;
+    const size_t cnt_bytes = ((size_t)batch * (plan.groups_per_pulse + 1) + 1) * sizeof(unsigned int);
+    if (!ensure_dev(c->d_partials, (plan.partial_elems + mid_elems) * sizeof(double2))) return false;
+    if (c->d_counters.bytes < cnt_bytes || !c->d_counters.ptr) {
+        if (!ensure_dev(c->d_counters, cnt_bytes) || !PB_CUDA_OK(cudaMemsetAsync(c->d_counters.ptr, 0, c->d_counters.bytes, st))) return false;
+    }
+    fz.out = out_dev; fz.n = c->dim; fz.counters = (unsigned int *)c->d_counters.ptr;
+    fz.mid = (double2 *)c->d_partials.ptr + plan.partial_elems; fz.groups = plan.groups_per_pulse;
+    return true;
+}
+
 // Spectral bound of the step Hamiltonians of THIS call:  ||H0 + sum_k c_k(t) H_k||_2 <= s_0 + sum_k max_t|c_k(t)| s_k, with s_m the
 // largest singular values from setHamiltonian and the amplitude maxima measured on the device (one pass over the amplitude stream
 // and a 64-byte read-back; dim > 16 only, where a step costs >= 50 us of tensor work per SM).  The quadrature averages cannot
@@ -940,6 +1000,7 @@ Parament_ErrorCode series_norm_for_call(Context *c, const void *carr_dev, const 
 
 // Device-resident core shared by every equiprop entry point.
 Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const CallSpec &s_in, void *out_dev, cudaStream_t st) {
+    NvtxRange range("parament: propagate (device-resident core)");
     CallSpec s = s_in;
     Parament_ErrorCode ec = series_norm_for_call(c, carr_dev, s, st, s.series_norm);
     if (ec != PARAMENT_STATUS_SUCCESS) return ec;
@@ -950,10 +1011,12 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
     c->stat_launches = 0;
     // all allocations happen before the timed region (grow-only scratch, nothing is allocated in steady state)
     K1Plan plan{};
+    const bool tf32 = use_tf32_path(c, p, s);
+    c->stat_math = tf32 ? 1 : 0;
+    K1Final fz{};
     if (c->family == 1) {
-        plan = plan_k1(c->npad, s.batch, s.nsteps, c->num_sms, p.horner != 0);
-        if (!ensure_dev(c->d_partials, (plan.partial_elems + k3_mid_elems(c->npad, s.batch, plan.partials_per_pulse)) * sizeof(double2)))
-            return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+        plan = plan_k1(c->npad, s.batch, s.nsteps, c->num_sms, p.horner != 0, true);
+        if (!prepare_fused(c, plan, s.batch, out_dev, st, fz)) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
     } else if (c->family == 2) {
         if (!alloc_family2(c, chain_grid(c, s))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
     } else if (!alloc_family3(c, plan_family3(c, s))) {
@@ -961,11 +1024,8 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
     }
     if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, st))) return PARAMENT_STATUS_CUBLAS_FAILED;
     if (c->family == 1) {
-        PB_LAUNCH(launch_k1_chain(c->npad, c->fp64, p, carr_dev, (const double2 *)c->d_H.ptr, (double2 *)c->d_partials.ptr,
-                                  s.batch, plan, 0, s.nsteps, st));
-        PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, plan.partials_per_pulse, c->dim,
-                                   out_dev, s.batch, (double2 *)c->d_partials.ptr + plan.partial_elems, st));
-        c->stat_launches += k3_launches(plan.partials_per_pulse) - 1;
+        // ONE launch: the chain kernel's last CTAs reduce the partials and write the propagators (k1_common.cuh)
+        PB_LAUNCH(launch_family1_chain(c, p, tf32, carr_dev, (double2 *)c->d_partials.ptr, s.batch, plan, 0, s.nsteps, fz, st));
     } else {
         ec = c->family == 2 ? run_family2(c, p, carr_dev, s, out_dev, st) : run_family3(c, p, carr_dev, s, out_dev, st);
         if (ec != PARAMENT_STATUS_SUCCESS) return ec;
@@ -981,6 +1041,7 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
 template <typename T>
 Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts, size_t p_lo, size_t seg, const CallSpec &s,
                                      int G, void *out_dev) {
+    NvtxRange range("parament: copy / compute pipeline (dim <= 16)");
     SeriesParams p;
     Parament_ErrorCode ec = build_series(c, s, p);
     if (ec != PARAMENT_STATUS_SUCCESS) return ec;
@@ -989,6 +1050,8 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
     const int n = c->dim, NP2 = c->npad * c->npad;
     T *dcarr = (T *)c->d_carr.ptr;
     const bool horner = p.horner != 0;
+    const bool tf32 = use_tf32_path(c, p, s);
+    c->stat_math = tf32 ? 1 : 0;
     if (G > 8) G = 8;
     auto copy_arrays = [&](size_t a0, size_t a1, size_t pt0, size_t npts) -> bool {
         // arrays [a0, a1) of the device buffer (stride seg) <- host arrays (stride pts), points [pt0, pt0 + npts) of the slice
@@ -1004,25 +1067,31 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
         // is the only one no kernel hides, later groups are long enough to hide theirs behind the group before.
         unsigned int gb[9];
         const int ng = ensemble_copy_groups(s.batch, std::max(1u, k1_warp_slots(c->npad, c->num_sms, horner) / 8), G, gb);   // plan.hpp
-        size_t part_cap = 0, mid_cap = 0;
-        for (int g = 0; g < ng; ++g) {
-            const K1Plan pg = plan_k1(c->npad, gb[g + 1] - gb[g], s.nsteps, c->num_sms, horner);
-            part_cap = std::max(part_cap, pg.partial_elems);
-            mid_cap = std::max(mid_cap, k3_mid_elems(c->npad, gb[g + 1] - gb[g], pg.partials_per_pulse));
+        // every group is one fused launch that writes its pulses' propagators; scratch sized for the largest group up front
+        {
+            K1Plan big{};
+            size_t need = 0;
+            unsigned int bmax = 0;
+            for (int g = 0; g < ng; ++g) {
+                const K1Plan pg = plan_k1(c->npad, gb[g + 1] - gb[g], s.nsteps, c->num_sms, horner, true);
+                const size_t e = pg.partial_elems + (size_t)(gb[g + 1] - gb[g]) * pg.groups_per_pulse * NP2;
+                if (e >= need) { need = e; big = pg; bmax = gb[g + 1] - gb[g]; }
+            }
+            K1Final probe{};
+            if (!ensure_dev(c->d_partials, need * sizeof(double2)) || !prepare_fused(c, big, std::max(bmax, s.batch), out_dev, c->stream, probe))
+                return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
         }
-        if (!ensure_dev(c->d_partials, (part_cap + mid_cap) * sizeof(double2))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
         if (!PB_CUDA_OK(cudaEventRecord(c->ev_start, c->stream))) return PARAMENT_STATUS_CUBLAS_FAILED;
         for (int g = 0; g < ng; ++g) {
             const unsigned int b0 = gb[g], b1 = gb[g + 1];
             if (!copy_arrays((size_t)b0 * s.amps, (size_t)b1 * s.amps, 0, seg) ||
                 !PB_CUDA_OK(cudaEventRecord(c->ev_copy[g], c->copy_stream)) || !PB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0)))
                 return PARAMENT_STATUS_CUBLAS_FAILED;
-            const K1Plan plan = plan_k1(c->npad, b1 - b0, s.nsteps, c->num_sms, horner);
-            PB_LAUNCH(launch_k1_chain(c->npad, c->fp64, p, dcarr + (size_t)b0 * s.amps * seg, (const double2 *)c->d_H.ptr,
-                                      (double2 *)c->d_partials.ptr, b1 - b0, plan, 0, s.nsteps, c->stream));
-            PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, plan.partials_per_pulse, n,
-                                       (T *)out_dev + (size_t)b0 * n * n, b1 - b0, (double2 *)c->d_partials.ptr + part_cap, c->stream));
-            c->stat_launches += k3_launches(plan.partials_per_pulse) - 1;
+            const K1Plan plan = plan_k1(c->npad, b1 - b0, s.nsteps, c->num_sms, horner, true);
+            K1Final fz{};
+            if (!prepare_fused(c, plan, b1 - b0, (T *)out_dev + (size_t)b0 * n * n, c->stream, fz)) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+            PB_LAUNCH(launch_family1_chain(c, p, tf32, dcarr + (size_t)b0 * s.amps * seg, (double2 *)c->d_partials.ptr, b1 - b0, plan, 0,
+                                           s.nsteps, fz, c->stream));
         }
     } else {
         const int r = points_per_step(c), ov = point_overlap(c);
@@ -1044,8 +1113,8 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
             if (!copy_arrays(0, s.amps, pt0, pt1 - pt0) ||
                 !PB_CUDA_OK(cudaEventRecord(c->ev_copy[g], c->copy_stream)) || !PB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copy[g], 0)))
                 return PARAMENT_STATUS_CUBLAS_FAILED;
-            PB_LAUNCH(launch_k1_chain(c->npad, c->fp64, p, dcarr, (const double2 *)c->d_H.ptr, (double2 *)c->d_partials.ptr + off[g] * NP2,
-                                      1, plans[g], bound[g], bound[g + 1], c->stream));
+            PB_LAUNCH(launch_family1_chain(c, p, tf32, dcarr, (double2 *)c->d_partials.ptr + off[g] * NP2, 1, plans[g], bound[g], bound[g + 1],
+                                           K1Final{}, c->stream));   // partials only: the groups' partials are reduced together below
         }
         PB_LAUNCH(launch_k3_reduce(c->npad, c->fp64, (const double2 *)c->d_partials.ptr, (unsigned int)off[G], n, out_dev, 1,
                                    (double2 *)c->d_partials.ptr + off[G] * NP2, c->stream));
@@ -1096,6 +1165,7 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
                                  unsigned long long lo, unsigned long long hi, bool whole, T *out, Context *gather_to = nullptr,
                                  unsigned int slot = 0, bool out_is_device = false) {
     if (!c) return PARAMENT_STATUS_INVALID_VALUE;
+    NvtxRange range(gather_to ? "parament: equiprop slice (helper device)" : "Parament_equiprop (host pointers)");
     if (whole && !gather_to && !c->peers.empty()) {
         bool handled = false;
         const Parament_ErrorCode mec = equiprop_multi<T>(c, carr, dt, pts, amps, batch, out, handled);
@@ -1205,6 +1275,7 @@ Parament_ErrorCode equiprop_device(Context *c, const T *carr_dev, double dt, uns
 // out = parts[count-1] ... parts[0]: ordered E-form tree on the GEMM kernel (multi-GPU combine of time slices).
 // Device-resident core: parts_dev / out_dev in the IO precision, scratch from the context (grow-only), no synchronisation.
 Parament_ErrorCode combine_device_core(Context *c, const void *parts_dev, unsigned int count, void *out_dev, cudaStream_t st) {
+    NvtxRange range("parament: ordered combine of slice partials");
     const int n = c->dim;
     c->stat_launches = 0;
     if (c->family == 1) {   // register-resident family: one launch of one CTA
@@ -1273,6 +1344,7 @@ Parament_ErrorCode equiprop_multi(Context *c, const T *carr, double dt, unsigned
     const unsigned int G = devices_for_call((unsigned int)c->peers.size() + 1, batch, N, c->npad);   // plan.hpp
     if (G < 2) return PARAMENT_STATUS_SUCCESS;   // not worth sharing: the caller runs it on the first device
     handled = true;
+    NvtxRange range("parament: single-process multi-GPU call");
     DeviceGuard guard(c->device);
     const int n = c->dim;
     const size_t nn = (size_t)n * n;
@@ -1587,6 +1659,7 @@ double Parament_lastStat(void *h, int key) {
         }
         case 13: return c->family == 3 ? k4_real_products(c->npad) : 4;   // real products per complex matrix product
         case 14: return c->stat_series_norm;
+        case 15: return c->stat_math;
         case 11: return c->stat_devices;
         case 12: return (double)c->peers.size() + 1.0;
         default: return -1.0;

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdlib>
 #include "k1_warp.hpp"
+#include "k1_common.cuh"
 
 namespace pb {
 
@@ -34,34 +35,13 @@ namespace pb {
 #endif
 
 
-// Ordered in-CTA product: afterwards warp 0 holds Q_0 Q_1 ... Q_{nwarps-1}.  smem: (nwarps/2) matrices.
-template <int NT>
-__device__ __forceinline__ void cta_ordered_product(AccFrag<NT> &Q, double2 *smem, int warp, int nwarps, int lane) {
-    constexpr int NP = 8 * NT;
-    for (int stride = 1; stride < nwarps; stride <<= 1) {
-        const int mask = 2 * stride - 1;
-        const int slot = warp / (2 * stride);
-        if ((warp & mask) == stride) store_acc<NT>(Q, smem + slot * NP * NP, NP, lane);
-        __syncthreads();
-        if ((warp & mask) == 0 && warp + stride < nwarps) {
-            BFrag<NT> B;
-            load_bfrag<NT>(B, smem + slot * NP * NP, NP, lane);
-            AccFrag<NT> R;
-            set_zero<NT>(R);
-            cmma<NT>(R, Q, B);
-            Q = R;
-        }
-        __syncthreads();
-    }
-}
-
 // Hfrag layout: [matrix][layout 0 = AccFrag order, 1 = BFrag order][element e < 2*NT*NT][lane] as double2.
 // OCC: CTAs per SM the register allocation is bounded for (NT == 2: 2 -> 255 registers, 3 -> 168 registers with spills)
 template <int NT, typename IO, int HORNER, int OCC>
 __global__ void __launch_bounds__(32 * K1_WARPS, OCC)
 k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ Hfrag,
                 double2 *__restrict__ partials, unsigned int batch, unsigned int chunks_per_pulse,
-                unsigned long long step_lo, unsigned long long step_hi, int reduce_in_cta) {
+                unsigned long long step_lo, unsigned long long step_hi, int reduce_in_cta, const K1Final fz) {
     constexpr int NP = 8 * NT;
     constexpr int NE = 2 * NT * NT;   // fragment elements per lane and layout
     __shared__ double2 smem[(K1_WARPS / 2) * NP * NP];
@@ -353,65 +333,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
         K1_T_PRINT
     }
 
-    if (reduce_in_cta) {
-        cta_ordered_product<NT>(Q, smem, warp, K1_WARPS, lane);
-        if (warp == 0 && active) {
-            const unsigned int nb = chunks_per_pulse / K1_WARPS;
-            store_acc<NT>(Q, partials + ((size_t)pulse * nb + chunk / K1_WARPS) * NP * NP, NP, lane);
-        }
-    } else if (active) {
-        store_acc<NT>(Q, partials + ((size_t)pulse * chunks_per_pulse + chunk) * NP * NP, NP, lane);
-    }
-}
-
-// out (n x n row-major, IO precision) = Q^T: the running products are kept transposed (frag.cuh).
-template <int NT, typename IO>
-__device__ __forceinline__ void store_propagator(const AccFrag<NT> &Q, IO *__restrict__ o, int n, int lane) {
-#pragma unroll
-    for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int r = acc_row(lane, mt), cidx = acc_col(lane, nt, i);
-                if (r < n && cidx < n) {
-                    IO v;
-                    v.x = Q.re[mt][nt][i];
-                    v.y = Q.im[mt][nt][i];
-                    o[(size_t)cidx * n + r] = v;
-                }
-            }
-}
-
-// Fragments of P^T from a propagator P stored n x n row-major in the IO precision (identity in the padding).
-template <int NT, typename IO>
-__device__ __forceinline__ void load_acc_of_transpose(AccFrag<NT> &Q, const IO *__restrict__ P, int n, int lane) {
-#pragma unroll
-    for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int r = acc_row(lane, mt), c = acc_col(lane, nt, i);
-                double re = (r == c) ? 1.0 : 0.0, im = 0.0;
-                if (r < n && c < n) { const IO v = P[(size_t)c * n + r]; re = v.x; im = v.y; }
-                Q.re[mt][nt][i] = re;
-                Q.im[mt][nt][i] = im;
-            }
-}
-template <int NT, typename IO>
-__device__ __forceinline__ void load_bfrag_of_transpose(BFrag<NT> &B, const IO *__restrict__ P, int n, int lane) {
-#pragma unroll
-    for (int kt = 0; kt < 2 * NT; ++kt)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int r = bf_row(lane, kt), c = bf_col(lane, nt);
-            double re = (r == c) ? 1.0 : 0.0, im = 0.0;
-            if (r < n && c < n) { const IO v = P[(size_t)c * n + r]; re = v.x; im = v.y; }
-            B.re[kt][nt] = re;
-            B.im[kt][nt] = im;
-            B.nim[kt][nt] = neg(im);
-        }
+    k1_tail<NT, IO>(Q, active, pulse, chunk, chunks_per_pulse, reduce_in_cta, partials, fz, smem, warp, lane);
 }
 
 // Ordered product of `count` propagators of time slices (multi-GPU combine, dim <= 16): out = parts[count-1] ... parts[0].
@@ -462,26 +384,8 @@ k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, unsigned
     const double2 *P = partials + ((size_t)pulse * nb + g0) * NP * NP;
     const unsigned int cnt = g1 - g0;
 
-    const unsigned int b0 = (unsigned int)((unsigned long long)cnt * warp / nwarps);
-    const unsigned int b1 = (unsigned int)((unsigned long long)cnt * (warp + 1) / nwarps);
     AccFrag<NT> Q;
-    if (b0 < b1) {
-        load_acc<NT>(Q, P + (size_t)b0 * NP * NP, NP, lane);
-        BFrag<NT> B;
-        if (b0 + 1 < b1) load_bfrag<NT>(B, P + (size_t)(b0 + 1) * NP * NP, NP, lane);
-        for (unsigned int b = b0 + 1; b < b1; ++b) {
-            BFrag<NT> Bn;
-            if (b + 1 < b1) load_bfrag<NT>(Bn, P + (size_t)(b + 1) * NP * NP, NP, lane);   // prefetch
-            AccFrag<NT> R;
-            set_zero<NT>(R);
-            cmma<NT>(R, Q, B);
-            Q = R;
-            if (b + 1 < b1) B = Bn;
-        }
-    } else {
-        set_identity<NT>(Q, lane);
-    }
-    cta_ordered_product<NT>(Q, smem, warp, nwarps, lane);
+    cta_reduce_range<NT>(Q, P, cnt, smem, warp, nwarps, lane);
     if (warp == 0) {
         if (mid) {
             store_acc<NT>(Q, mid + ((size_t)pulse * gridDim.y + g) * NP * NP, NP, lane);
@@ -497,46 +401,46 @@ k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, unsigned
 template <int NT, typename IO, int HORNER, int OCC>
 static cudaError_t launch_chain_ttt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                    unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
-                                   unsigned long long step_hi, cudaStream_t stream) {
+                                   unsigned long long step_hi, const K1Final &fz, cudaStream_t stream) {
     k1_chain_kernel<NT, IO, HORNER, OCC><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
                                                                                    plan.chunks_per_pulse, step_lo, step_hi,
-                                                                                   plan.reduce_in_cta);
+                                                                                   plan.reduce_in_cta, fz);
     return cudaGetLastError();
 }
 
 template <int NT, typename IO, int HORNER>
 static cudaError_t launch_chain_tt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                    unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
-                                   unsigned long long step_hi, cudaStream_t stream) {
-    if (NT == 1) return launch_chain_ttt<NT, IO, HORNER, 6>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
-    if (plan.ctas_per_sm == 3) return launch_chain_ttt<NT, IO, HORNER, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
-    return launch_chain_ttt<NT, IO, HORNER, 2>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
+                                   unsigned long long step_hi, const K1Final &fz, cudaStream_t stream) {
+    if (NT == 1) return launch_chain_ttt<NT, IO, HORNER, 6>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+    if (plan.ctas_per_sm == 3) return launch_chain_ttt<NT, IO, HORNER, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+    return launch_chain_ttt<NT, IO, HORNER, 2>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
 }
 
 template <int NT, typename IO>
 static cudaError_t launch_chain_t(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                   unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
-                                  unsigned long long step_hi, cudaStream_t stream) {
-    if (p.horner == 4) return launch_chain_tt<NT, IO, 4>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
+                                  unsigned long long step_hi, const K1Final &fz, cudaStream_t stream) {
+    if (p.horner == 4) return launch_chain_tt<NT, IO, 4>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     if (p.horner == 3) {   // complex64 contexts only (api.cu build_series)
         if constexpr (sizeof(IO) == sizeof(float2))
-            return launch_chain_tt<NT, IO, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
+            return launch_chain_tt<NT, IO, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
         else
             return cudaErrorInvalidValue;
     }
-    return p.horner ? launch_chain_tt<NT, IO, 1>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream)
-                    : launch_chain_tt<NT, IO, 0>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
+    return p.horner ? launch_chain_tt<NT, IO, 1>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream)
+                    : launch_chain_tt<NT, IO, 0>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
 }
 
 cudaError_t launch_k1_chain(int npad, bool fp64_io, const SeriesParams &p, const void *carr, const double2 *Hfrag,
                             double2 *partials, unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
-                            unsigned long long step_hi, cudaStream_t stream) {
+                            unsigned long long step_hi, const K1Final &fz, cudaStream_t stream) {
     if (npad == 8) {
-        return fp64_io ? launch_chain_t<1, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream)
-                       : launch_chain_t<1, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
+        return fp64_io ? launch_chain_t<1, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream)
+                       : launch_chain_t<1, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     }
-    return fp64_io ? launch_chain_t<2, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream)
-                   : launch_chain_t<2, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, stream);
+    return fp64_io ? launch_chain_t<2, double2>(p, (const double2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream)
+                   : launch_chain_t<2, float2>(p, (const float2 *)carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
 }
 
 template <int NT, typename IO>

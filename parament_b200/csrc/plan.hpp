@@ -18,6 +18,7 @@ struct K1Plan {
     int k3_warps;                      // warps per CTA of the reduce kernel
     int ctas_per_sm;                   // occupancy the chain kernel variant is compiled for
     size_t partial_elems;              // double2 elements of the partial buffer
+    unsigned int groups_per_pulse;     // fused final stage: groups of 16 CTA partials per pulse (few-long-pulses mode), else 0
 };
 
 inline int k3_warps_for(unsigned int partials_per_pulse) { return partials_per_pulse >= 16 ? 8 : (partials_per_pulse >= 4 ? 4 : 1); }
@@ -37,7 +38,9 @@ inline unsigned int k1_warp_slots(int npad, int num_sms, bool horner) {
 }
 
 // How `batch` pulses of `nsteps` effective steps are spread over warps and CTAs.
-inline K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms, bool horner) {
+// fuse: the chain launch writes the propagators itself (k1_common.cuh); the warps of an ensemble pulse must then share a CTA,
+// i.e. a pulse is cut into 1, 2 or 4 chunks.
+inline K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, int num_sms, bool horner, bool fuse = false) {
     K1Plan plan{};
     const int ctas_per_sm = k1_ctas_per_sm(npad, horner);
     plan.ctas_per_sm = ctas_per_sm;
@@ -48,15 +51,16 @@ inline K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, i
         // of 1000 steps = exactly six CTAs per SM with k = 1): k = 1 2.654 ms, 2 2.532, 4 2.475, 8 2.450 -- about 0.91 + 0.09 / k.
         unsigned int best_k = 1;
         double best = 1e300;
-        for (unsigned int k = 1; k <= 8; ++k) {
+        for (unsigned int k = 1; k <= (fuse ? 4u : 8u); ++k) {
             if (k > 1 && nsteps / k < 64) break;
+            if (fuse && k == 3) continue;
             const double ctas = std::ceil((double)batch * k / K1_WARPS);
             const double imbalance = std::ceil(ctas / num_sms) / (ctas / num_sms);
             const double cost = imbalance * (0.91 + 0.09 / k);
             if (cost < best * 0.999) { best = cost; best_k = k; }
         }
         static const int k_env = getenv("PARAMENT_K1_K") ? atoi(getenv("PARAMENT_K1_K")) : 0;   // A/B runs
-        if (k_env >= 1 && k_env <= 8 && nsteps / k_env >= 64) best_k = (unsigned int)k_env;
+        if (k_env >= 1 && k_env <= 8 && nsteps / k_env >= 64 && (!fuse || k_env == 1 || k_env == 2 || k_env == 4)) best_k = (unsigned int)k_env;
         plan.chunks_per_pulse = best_k;
         plan.reduce_in_cta = 0;
         plan.partials_per_pulse = best_k;
@@ -78,6 +82,7 @@ inline K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, i
     plan.grid = (unsigned int)((total_warps + K1_WARPS - 1) / K1_WARPS);
     plan.k3_warps = k3_warps_for(plan.partials_per_pulse);
     plan.partial_elems = (size_t)batch * plan.partials_per_pulse * npad * npad;
+    plan.groups_per_pulse = (fuse && plan.reduce_in_cta) ? (plan.partials_per_pulse + 15) / 16 : 0;
     return plan;
 }
 

@@ -50,7 +50,7 @@ def test_time_axis_is_shared_between_listed_devices(pb, name, pts, devices, tol)
         U = ctx.equiprop(w.dt, *w.carr)
         assert ctx.stat(K.STAT_DEVICES_USED) == len(devices)
         assert ctx.stat(K.STAT_STEPS) == w.steps
-        assert ctx.stat(K.STAT_LAUNCHES) >= 2 * len(devices)
+        assert ctx.stat(K.STAT_LAUNCHES) >= len(devices) + 1       # one fused chain launch per device + the one-launch combine
         assert ctx.stat(K.STAT_DEVICE_MS) > 0
         U2 = ctx.equiprop(w.dt, *w.carr)            # scratch is reused; same slices, same result
     assert np.array_equal(U, U2)

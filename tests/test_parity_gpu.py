@@ -126,6 +126,7 @@ def test_degree8_three_product_path(pb, n, A, quad, mag, complex_amps, prec, mon
     The series is built for the reference's norm bound here (PARAMENT_NORM=reference, read at Parament_create) so that the
     degree under test is the table's at every dimension; the spectral bound of dim > 16 is covered in test_round2_gpu.py."""
     monkeypatch.setenv("PARAMENT_NORM", "reference")
+    monkeypatch.setenv("PARAMENT_C64_MATH", "f64")     # the FP64 kernels are under test (the TF32 path of dim <= 8: test_round2_gpu.py)
     rng = np.random.default_rng(100 * n + A)
     herm = lambda: (lambda g: (g + g.conj().T) / 2)(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
     norm1 = lambda m: m / np.max(np.sum(np.abs(m), axis=1))
@@ -281,7 +282,7 @@ def test_ensemble_full_size(pb):
     for b in (0, 777, 5000, 9999):
         Uo = equiprop_oracle(w.H0, w.H1, w.carr[b], w.dt, "none", False, "fp32")
         assert rel_frobenius(U[b], Uo) < TOL["fp32"]
-    assert rel_frobenius(U[1234], single) < 1e-6
+    assert rel_frobenius(U[1234], single) < 5e-6      # ensemble and single call chunk the pulse differently (fp32 / TF32 arithmetic)
     Ud = U.astype(np.complex128)
     dev = np.linalg.norm(np.einsum("bji,bjk->bik", Ud.conj(), Ud) - np.eye(8), axis=(1, 2)).max()
     assert dev < 1e-5
@@ -459,7 +460,7 @@ def test_device_resident_operands(pb):
         host = ctx.equiprop(w.dt, *w.carr)
         ctx.equiprop_device(w.dt, carr.data_ptr(), w.pts, w.amps, out.data_ptr())
         torch.cuda.synchronize()
-        assert ctx.stat(1) >= 2 and ctx.stat(0) > 0
+        assert ctx.stat(1) >= 1 and ctx.stat(0) > 0       # one fused launch (chain + ordered reduction) since round 2
     assert rel_frobenius(out.cpu().numpy(), host) < 1e-7
 
 

@@ -130,8 +130,11 @@ def test_spectral_norm_saves_a_product(pb):
             U = ctx.equiprop(w.dt, *w.carr)
             hn, hs, m_used, m_ref, products = ctx.stat(8), ctx.stat(14), ctx.stat(2), ctx.stat(3), ctx.stat(10)
         assert abs(hn - 1.0) < 1e-12 and 0.05 < hs < 0.5 * hn
-        sig = np.linalg.norm(w.H0, 2) + sum(np.linalg.norm(h, 2) for h in w.H1)
-        assert sig <= hs <= 1.06 * sig                       # a true bound with at most the 5 % margin (|c_k| <= 1 here)
+        # s(H0) + sum_k max_t |c_k(t)| s(H_k) with the amplitude maxima of THIS pulse, times the 5 % margin
+        sig = np.linalg.norm(w.H0, 2) + sum(np.abs(c).max() * np.linalg.norm(h, 2) for c, h in zip(w.carr, w.H1))
+        assert 1.04 * sig <= hs <= 1.0501 * sig
+        worst = max(np.linalg.norm(w.H0 + np.tensordot(w.carr[:, j], w.H1, axes=1), 2) for j in range(0, pts, max(1, pts // 16)))
+        assert worst <= hs                                   # a true bound of the sampled step Hamiltonians
         assert m_ref == 11 and m_used == 8 and products == 4.0
         assert rel_frobenius(U, equiprop_oracle(w.H0, w.H1, w.carr, w.dt, "none", False, "fp64")) < 1e-13
 
@@ -192,3 +195,85 @@ def test_callers_current_device_is_left_alone(pb, gpu_count):
         U = ctx.equiprop(w.dt, *w.carr)
         assert torch.cuda.current_device() == 0
     assert rel_frobenius(U, equiprop_oracle(w.H0, w.H1, w.carr, w.dt, "simpson", False, "fp32")) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# complex64, dim <= 8: FP32 arithmetic as 3xTF32 on the warp-level tensor path (k1_tf32.cu)
+# ---------------------------------------------------------------------------------------------------------
+def _run_sub(code, env, tmp_path):
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return r.stdout
+
+
+TF32_CASES = textwrap.dedent("""
+    import sys, numpy as np
+    sys.path.insert(0, ROOT)
+    import parament_b200 as pb
+    from workloads import make_workload, rand_herm
+    from oracle.equiprop_oracle import equiprop_oracle, rel_frobenius
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    # dims 2..8, every quadrature, Magnus (more terms than stay in registers), complex amplitudes, ragged lengths, chunked pulses
+    for n, A, quad, mag, cplx_amp, pts in [(8, 2, "none", False, False, 1000), (8, 2, "simpson", False, True, 2001), (5, 1, "midpoint", False, False, 333),
+                                            (2, 1, "none", False, False, 4000), (7, 3, "simpson", True, False, 801), (8, 4, "none", False, True, 64),
+                                            (3, 2, "simpson", True, True, 5), (8, 2, "none", False, False, 1), (6, 2, "midpoint", False, False, 2)]:
+        H0 = (0.5 * rand_herm(rng, n)).astype(np.complex64)
+        H1 = np.stack([(0.5 / A * rand_herm(rng, n)).astype(np.complex64) for _ in range(A)])
+        carr = rng.uniform(-1, 1, (A, pts)) + (1j * rng.uniform(-1, 1, (A, pts)) if cplx_amp else 0)
+        carr = carr.astype(np.complex64)
+        dt = 0.2 if quad in ("none", "midpoint") else 0.1
+        with pb.Parament("fp32") as ctx:
+            ctx.set_hamiltonian(H0, *H1, use_magnus=mag, quadrature_mode=quad)
+            U = ctx.equiprop(dt, *carr)
+            assert ctx.stat(15) == EXPECT_MATH, (n, quad, ctx.stat(15), ctx.stat(9))
+        err = rel_frobenius(U, equiprop_oracle(H0, H1, carr, dt, quad, mag, "fp32"))
+        assert err < 1e-5, (n, A, quad, mag, pts, err)
+        worst = max(worst, err)
+    # the C5 ensemble at full size: host-pointer batch call (copy groups) and the first 16 golden pulses + 4 oracle pulses
+    w = make_workload("C5")
+    with pb.Parament("fp32") as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1)
+        U = ctx.equiprop_batch(w.dt, w.carr)
+        assert ctx.stat(15) == EXPECT_MATH
+        one = ctx.equiprop(w.dt, *w.carr[4321])
+    for b in (0, 15, 4321, 9999):
+        err = rel_frobenius(U[b], equiprop_oracle(w.H0, w.H1, w.carr[b], w.dt, "none", False, "fp32"))
+        assert err < 1e-5, (b, err)
+        worst = max(worst, err)
+    assert rel_frobenius(U[4321], one) < 2e-6
+    print("worst", worst)
+""")
+
+
+@pytest.mark.parametrize("mode,expect", [("tf32", 1), ("f64", 0)])
+def test_complex64_small_dim_arithmetic_paths(tmp_path, mode, expect):
+    """Both arithmetic paths of complex64 contexts with dim <= 8 meet the 1e-5 tolerance on the same cases; the TF32 path
+    must really be the one that ran when selected (Parament_lastStat key 15)."""
+    code = TF32_CASES.replace("ROOT", repr(ROOT)).replace("EXPECT_MATH", str(expect))
+    out = _run_sub(code, {"PARAMENT_C64_MATH": mode}, tmp_path)
+    assert "worst" in out
+
+
+def test_tf32_path_is_selected_by_step_count(pb):
+    """Automatic choice by accumulated phase N h rho <= 128: C5's 1e3 steps run on the TF32 path, long pulses in FP64; dim 16 and
+    complex128 contexts always in FP64."""
+    w = make_workload("C5", pts=1000, batch=8)
+    wl = make_workload("C5", pts=20000, batch=1)
+    with pb.Parament("fp32") as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1)
+        ctx.equiprop_batch(w.dt, w.carr)
+        assert ctx.stat(15) == 1
+        U = ctx.equiprop(wl.dt, *wl.carr)
+        assert ctx.stat(15) == 0
+    assert rel_frobenius(U, equiprop_oracle(wl.H0, wl.H1, wl.carr, wl.dt, "none", False, "fp32")) < 1e-5
+    w2 = make_workload("C2", pts=2001)
+    with pb.Parament("fp32") as ctx:
+        ctx.set_hamiltonian(w2.H0, *w2.H1, quadrature_mode="simpson")
+        ctx.equiprop(w2.dt, *w2.carr)
+        assert ctx.stat(15) == 0
+    w1 = make_workload("C1", pts=1001)
+    with pb.Parament("fp64") as ctx:
+        ctx.set_hamiltonian(w1.H0, *w1.H1, quadrature_mode="midpoint")
+        ctx.equiprop(w1.dt, *w1.carr)
+        assert ctx.stat(15) == 0
