@@ -310,7 +310,7 @@ class Ours:
         stats = {"M_used": int(ctx.stat(K.STAT_DEGREE_USED)), "M_ref": int(ctx.stat(K.STAT_DEGREE_REFERENCE)),
                  "products": ctx.stat(K.STAT_PRODUCTS), "horner": int(ctx.stat(K.STAT_HORNER)), "family": int(ctx.stat(K.STAT_FAMILY)),
                  "real_products": int(ctx.stat(K.STAT_REAL_PRODUCTS)), "hnorm": ctx.stat(K.STAT_HNORM),
-                 "series_norm": ctx.stat(K.STAT_SERIES_NORM)}
+                 "series_norm": ctx.stat(K.STAT_SERIES_NORM), "math": int(ctx.stat(K.STAT_MATH))}
         gpu_launches = launches[0]
 
         # ---- timed region 2: end to end through the host-pointer C-ABI ----
@@ -373,15 +373,22 @@ class Ours:
                     traffic = json.load(f).get(name)
             except OSError:
                 pass
-            pk = self.peak_dmma
+            # Denominator: the FP64 tensor pipe (DMMA) -- except where the complex64 kernel of dim <= 8 ran in FP32 arithmetic as
+            # 3xTF32 split products: SURVEY 8(d) asks for that fraction against the FP32 ceiling the path replaces (FFMA peak),
+            # with the tensor-pipe utilisation (three TF32 MACs per fp32-grade MAC) reported beside it.
+            tf32 = stats["math"] == 1
+            pk = self.peak_ffma if tf32 else self.peak_dmma
+            pipe = ("FP32-grade products as 3xTF32 on the warp-level tensor path (HMMA.1688.F32.TF32); peak = measured FFMA rate, the FP32 ceiling it replaces"
+                    if tf32 else "FP64 tensor pipe (DMMA.8x8x4)")
             rec = {
                 "value": job_steps * steps / (dev_ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": dev_ms / steps, "scaling": mode, "dtype": "f64",
+                "ms_per_step": dev_ms / steps, "scaling": mode, "dtype": "f32 (3xTF32)" if tf32 else "f64",
                 "config": workload_config(name, w, world, mode, l2),
                 "implementation": {"degree_reference": stats["M_ref"], "degree_used": stats["M_used"],
                                    "series_evaluation": SERIES_NAMES.get(stats["horner"], str(stats["horner"])),
                                    "matrix_products_per_step": stats["products"],
                                    "real_products_per_complex_product": stats["real_products"], "kernel_family": stats["family"],
+                                   "arithmetic": "fp32 as 3xTF32 (mma.sync.m16n8k8.tf32)" if tf32 else "fp64 (mma.sync.m8n8k4.f64)",
                                    "norm_reference": stats["hnorm"], "norm_series": stats["series_norm"],
                                    "effective_steps_per_gpu": local_steps},
                 "clocks": self.sampler.window(t0, t1),
@@ -396,10 +403,14 @@ class Ours:
                 # `achieved` = algorithmic flops of the reference's recurrence / time.  The product-saving
                 # evaluation executes fewer products than that recurrence, so `frac` is computed from the EXECUTED flops and
                 # stays a pipe utilisation (<= 1); the algorithmic figure is kept in `algorithmic_frac`.
-                "roofline": {"bound": "tensor", "pipe": "FP64 tensor pipe (DMMA.8x8x4)", "achieved": achieved, "peak": pk, "unit": "TFLOP/s",
+                "roofline": {"bound": "tensor", "pipe": pipe, "achieved": achieved, "peak": pk, "unit": "TFLOP/s",
                              "frac": min(achieved, executed) / pk if pk > 0 else None,
                              "algorithmic_frac": achieved / pk if pk > 0 else None, "traffic": traffic,
-                             "peak_source": "Parament_measurePeak(DMMA mma.sync.m8n8k4.f64) in this process; MEASURED_PEAKS.json has no FP64 figure",
+                             "peak_source": ("Parament_measurePeak(FFMA) in this process" if tf32 else
+                                             "Parament_measurePeak(DMMA mma.sync.m8n8k4.f64) in this process") + "; MEASURED_PEAKS.json has no FP32 / FP64 figure",
+                             "tensor_pipe": ({"executed_tf32_tflops": 3.0 * executed, "peak_tflops": self.peak_tf32,
+                                              "frac": 3.0 * executed / self.peak_tf32 if self.peak_tf32 > 0 else None} if tf32 else None),
+                             "fp64_dmma_peak_tflops": self.peak_dmma,
                              "kernel": KERNEL_NAMES.get(stats["family"]), "kernel_ms_per_launch": kernel_ms,
                              "flops_per_step_algorithmic": F_alg, "flops_per_step_executed": F_exe,
                              "executed_tflops": executed, "executed_frac": executed / pk if pk > 0 else None,
@@ -443,7 +454,7 @@ def run_ours(args):
     if top is not None:
         line = {"metric": "propagator steps/sec", "value": top["value"], "unit": "steps/s", "n_gpus": o.world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+                "vs_baseline": None, "dtype": top["dtype"], "data": "synthetic"}
         for k in ("config", "implementation", "clocks", "gpu_launches", "e2e", "roofline", "cpu_baseline"):
             if k in top:
                 line[k] = top[k]
