@@ -309,7 +309,7 @@ class Ours:
         kernel_ms = dev_ms / steps if world == 1 else ctx.stat(K.STAT_DEVICE_MS)   # N = 1: nothing but the path's kernels in the region
         stats = {"M_used": int(ctx.stat(K.STAT_DEGREE_USED)), "M_ref": int(ctx.stat(K.STAT_DEGREE_REFERENCE)),
                  "products": ctx.stat(K.STAT_PRODUCTS), "horner": int(ctx.stat(K.STAT_HORNER)), "family": int(ctx.stat(K.STAT_FAMILY)),
-                 "real_products": int(ctx.stat(K.STAT_REAL_PRODUCTS)), "hnorm": ctx.stat(K.STAT_HNORM),
+                 "real_products": ctx.stat(K.STAT_REAL_PRODUCTS), "hnorm": ctx.stat(K.STAT_HNORM),
                  "series_norm": ctx.stat(K.STAT_SERIES_NORM), "math": int(ctx.stat(K.STAT_MATH))}
         gpu_launches = launches[0]
 

@@ -213,7 +213,8 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  *   9 series evaluation (0 Clenshaw recurrence, 1 Horner in Y^2, 2 Paterson-Stockmeyer blocks of four,
  *                        3 degree 8 in three products, 4 degree 12 in four products -- all the same polynomial family)
  *  10 complex matrix products executed per effective step (series + ordered product)
- *  13 real matrix products per complex product in the kernel family used (4; 3 for the batched GEMM of dim > 64)
+ *  13 real matrix products per complex product in the kernel family used, averaged over the products of a step (4; 3 for the
+ *     batched GEMM of dim > 64; 3.25 / 3.4 for the shared-memory-resident kernel of dim 17..64 in its degree-8 / degree-12 form)
  *  15 arithmetic of the last call: 0 = double precision on the FP64 tensor pipe (DMMA); 1 = single precision as 3xTF32 split
  *     products on the warp-level tensor path (complex64 contexts, dim <= 8, accumulated phase N h (s(H0) + sum_k s(H_k)) <= 128:
  *     the range in which the measured error stays below half the 1e-5 tolerance, profiles/error_growth_tf32_r2.md)

@@ -1657,7 +1657,17 @@ double Parament_lastStat(void *h, int key) {
             if (c->stat_horner == 1 && c->family == 2 && c->onchip && (M == 8 || M >= 10)) return 3.0 + M / 3;   // blocks of three
             return c->stat_horner ? 2.0 + (M >> 1) : (double)std::max(M, 1);
         }
-        case 13: return c->family == 3 ? k4_real_products(c->npad) : 4;   // real products per complex matrix product
+        case 13:   // real matrix products per complex matrix product, averaged over the products of a step
+            if (c->family == 3) return k4_real_products(c->npad);
+            // shared-memory-resident kernel: three real products wherever the own elements of Y and W are not both live in
+            // registers -- all but the L/R product of the degree-8 form, all but two products of the degree-12 form
+            if (c->family == 2 && c->onchip && c->stat_horner == 3) return 13.0 / 4.0;
+            if (c->family == 2 && c->onchip && c->stat_horner == 4) return 17.0 / 5.0;
+            if (c->family == 2 && c->onchip) {   // other forms: only the running-product update
+                const double np_ = Parament_lastStat(h, 10);
+                return np_ > 0 ? (4.0 * (np_ - 1.0) + 3.0) / np_ : 4.0;
+            }
+            return 4;
         case 14: return c->stat_series_norm;
         case 15: return c->stat_math;
         case 11: return c->stat_devices;

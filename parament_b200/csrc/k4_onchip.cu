@@ -86,7 +86,8 @@ enum OcEpi : int {
     EPI_PS3 = 6,       // D_smem = A B + b2 * Y2own(regs) + b1 * Yown(regs) + gamma I        (+ sub-ulp remainders if LO)
     EPI_S12_LR = 7,    // D_smem = A B + i kV Vown(smem) + kW Wown(regs) + i kY Yown(regs) + kI I, then (after a barrier: the
                        // second destination is the A operand) D_smem2 = A B + i k2V Vown + k2W Wown     (degree 12, L and R)
-    EPI_S12_E = 8      // D_smem = A B + i kV Vown(smem) + kW Wown(regs) + i kY Yown(regs) + kI I   (+ sub-ulp remainders if LO)
+    EPI_S12_E = 8,     // D_smem = A B + i kV Vown(smem) + kW Wown(regs) + i kY Yown(regs) + kI I   (+ sub-ulp remainders if LO)
+    EPI_ADD = 9        // D_smem = A B + Sown(smem, == D): the addend of the last series product, precomputed by EPI_S12_LR (want_s)
 };
 
 // Shared-memory buffers are named by their element OFFSET into the dynamic shared array, never by pointer: a pointer that
@@ -108,6 +109,11 @@ struct OcArgs {
     cplx gamma, gamma_lo;
     int v_smem, d_smem2;        // EPI_S12_*: own elements of V = Y^3; second destination
     double kV, kW, kY, kI, kV_lo, kW_lo, kY_lo, kI_lo, k2V, k2W;
+    // EPI_S12_LR with want_s: after the barrier the thread also writes S = i sV Vown + sW Wown + i sY Yown + sI I (+ sub-ulp
+    // remainders if LO), the addend of the NEXT product (EPI_ADD), over its own elements of s_smem -- the last use of the own
+    // elements of Y and W in registers, so the products after this one run with 128 registers less.
+    int want_s, s_smem;
+    double sV, sW, sY, sI, sV_lo, sW_lo, sY_lo, sI_lo;
 };
 
 // Fused assembly of the next step's Y (one element per thread and k-tile).
@@ -171,7 +177,10 @@ __device__ __forceinline__ void oc_load_own(OcOwn &y, int m) {
 }
 
 // `y`: the thread's own elements of Y (EPI_FIRST / EPI_HORNER), loaded once per step by oc_load_own.
-template <int N, int EPI, bool LO, bool ASSEMBLE>
+// MUL3: the complex product from THREE real products per fragment pair (P1 = Ar Br, P2 = Ai Bi, P3 = (Ar + Ai)(Br + Bi);
+// Re = P1 - P2, Im = P3 - P1 - P2): 24 instead of 32 DMMAs per k-tile for six DADDs and a third accumulator set.  Used where
+// the thread's own elements of Y and W are not both live in registers (k4_gemm.cu tile_gemm has the norm-wise error argument).
+template <int N, int EPI, bool LO, bool ASSEMBLE, bool MUL3 = false>
 __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, const OcOwn &y, OcOwn &y2) {
     using G = Oc<N>;
     constexpr int OC_P = G::P, OC_N = N, OC_THREADS = G::THREADS;
@@ -182,11 +191,15 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
     const double2 *sA = oc_smem + g.sA;
     const double2 *sB = oc_smem + g.sB;
 
-    double cre[MT][NTL][2], cim[MT][NTL][2];
+    double cre[MT][NTL][2], cim[MT][NTL][2];          // MUL3: P1 and P2 until the main loop is over
+    double p3[MUL3 ? MT : 1][MUL3 ? NTL : 1][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NTL; ++nt) { cre[mt][nt][0] = cre[mt][nt][1] = 0.0; cim[mt][nt][0] = cim[mt][nt][1] = 0.0; }
+        for (int nt = 0; nt < NTL; ++nt) {
+            cre[mt][nt][0] = cre[mt][nt][1] = 0.0; cim[mt][nt][0] = cim[mt][nt][1] = 0.0;
+            if (MUL3) p3[MUL3 ? mt : 0][MUL3 ? nt : 0][0] = p3[MUL3 ? mt : 0][MUL3 ? nt : 0][1] = 0.0;
+        }
 
     // swizzled column offsets (Oc<N>::at): the rows of this lane's A fragments are congruent to g mod 8, those of its B
     // fragments to q mod 4, so the XOR masks are per-thread constants
@@ -196,6 +209,8 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
     double2 h0, h[OC_MAXT];
     if (ASSEMBLE) oc_issue_loads<N>(as, tid, h0, h);
 
+    // (Double-buffering the fragments in registers -- k-tile kt + 1 requested before the DMMAs of k-tile kt -- was measured
+    // without effect at dim 64: 278.5 vs 278.7 ms per 1e6 steps; the second warp of the scheduler already covers the LDS latency.)
 #pragma unroll 2
     for (int kt = 0; kt < OC_N / 4; ++kt) {
         double2 af[MT], bf[NTL];
@@ -210,19 +225,47 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
             for (int b = 1; b < as.nblock; ++b) st_keep(as.y_glob + (size_t)(b - 1) * (OC_N * OC_N) + e, oc_combine(as, b, h0, h), as.keep);
             if (kt + 1 < OC_N / 4) oc_issue_loads<N>(as, e + OC_THREADS, h0, h);
         }
+        if (MUL3) {
+            double as_[MT], bs_[NTL];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) as_[mt] = af[mt].x + af[mt].y;
 #pragma unroll
-            for (int nt = 0; nt < NTL; ++nt) {
-                dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].x, bf[nt].x);
-                dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].x, bf[nt].y);
-            }
+            for (int nt = 0; nt < NTL; ++nt) bs_[nt] = bf[nt].x + bf[nt].y;
 #pragma unroll
-            for (int nt = 0; nt < NTL; ++nt) {
-                dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].y, neg(bf[nt].y));
-                dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].y, bf[nt].x);
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].x, bf[nt].x);
+                    dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].y, bf[nt].y);
+                    dmma884(p3[MUL3 ? mt : 0][MUL3 ? nt : 0][0], p3[MUL3 ? mt : 0][MUL3 ? nt : 0][1], as_[mt], bs_[nt]);
+                }
+        } else {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].x, bf[nt].x);
+                    dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].x, bf[nt].y);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    dmma884(cre[mt][nt][0], cre[mt][nt][1], af[mt].y, neg(bf[nt].y));
+                    dmma884(cim[mt][nt][0], cim[mt][nt][1], af[mt].y, bf[nt].x);
+                }
             }
         }
+    }
+    if (MUL3) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const double a = cre[mt][nt][i], b = cim[mt][nt][i];
+                    cre[mt][nt][i] = a - b;
+                    cim[mt][nt][i] = p3[MUL3 ? mt : 0][MUL3 ? nt : 0][i] - (a + b);
+                }
     }
 
     // ---- epilogue (small terms first, dominant term last with one FMA rounding: DESIGN.md "Numerics") ----
@@ -303,6 +346,10 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                     vr[i] = fma(-g.kY, a1.y, vr[i]);                             // the Y term dominates: last
                     vi[i] = fma(g.kY, a1.x, vi[i]);
                 }
+            } else if (EPI == EPI_ADD) {
+                const double2 s0 = oc_smem[g.d_smem + G::at(r, c)], s1 = oc_smem[g.d_smem + G::at(r, c + 1)];
+                vr[0] += s0.x; vi[0] += s0.y;
+                vr[1] += s1.x; vi[1] += s1.y;
             } else if (EPI == EPI_CHAIN) {
                 const double2 e0 = oc_smem[g.c_smem + G::at(r, c)], e1 = oc_smem[g.c_smem + G::at(r, c + 1)];
                 const double2 f0 = oc_smem[g.c_smem2 + G::at(r, c)], f1 = oc_smem[g.c_smem2 + G::at(r, c + 1)];
@@ -329,6 +376,21 @@ __device__ __forceinline__ void oc_gemm(const OcArgs &g, const OcAssemble &as, c
                     const double2 v = oc_smem[g.v_smem + G::at(r, c + i)], a2 = y2[mt][nt][i];
                     oc_smem[g.d_smem2 + G::at(r, c + i)] =
                         make_double2(fma(g.k2W, a2.x, fma(-g.k2V, v.y, cre[mt][nt][i])), fma(g.k2W, a2.y, fma(g.k2V, v.x, cim[mt][nt][i])));
+                    if (g.want_s) {   // the next product's addend (small terms first, the dominant Y term last)
+                        const double2 a1 = y[mt][nt][i];
+                        double sr = 0.0, si = 0.0;
+                        if (LO) {
+                            sr = (g.sW_lo * a2.x - g.sV_lo * v.y) - g.sY_lo * a1.y;
+                            si = (g.sW_lo * a2.y + g.sV_lo * v.x) + g.sY_lo * a1.x;
+                            if (r == c + i) sr = (sr + g.sI_lo) + g.sI;
+                        } else if (r == c + i) {
+                            sr = g.sI;
+                        }
+                        sr = fma(-g.sV, v.y, sr); si = fma(g.sV, v.x, si);
+                        sr = fma(g.sW, a2.x, sr); si = fma(g.sW, a2.y, si);
+                        sr = fma(-g.sY, a1.y, sr); si = fma(g.sY, a1.x, si);
+                        oc_smem[g.s_smem + G::at(r, c + i)] = make_double2(sr, si);
+                    }
                 }
             }
     }
@@ -404,7 +466,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             oc_load_own<N>(y, PY);
             OcArgs a{};
             a.sA = PY; a.sB = PY; a.d_smem = PA;
-            oc_gemm<N, EPI_KEEP, false, false>(a, none, y, y2);         // W -> PA, own elements -> y2
+            oc_gemm<N, EPI_KEEP, false, false, true>(a, none, y, y2);   // W -> PA, own elements -> y2
             PB_T(1)
             {   // T -> PB (free)
                 const double c4 = p.a[0].re, c3 = p.a[1].re;
@@ -426,14 +488,16 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             lr.sA = PB; lr.sB = PA; lr.d_smem = PY; lr.d_smem2 = PB; lr.v_smem = PA;
             lr.kV = 0.0; lr.kW = -p.a[2].re; lr.kY = -p.a[3].re; lr.kI = p.a[5].re;
             lr.k2V = 0.0; lr.k2W = -p.a[4].re;
-            oc_gemm<N, EPI_S12_LR, false, false>(lr, none, y, y2);      // L -> PY (Y is dead as an operand), R -> PB
+            // ... and the addend S = -r2' W - i r1 Y + r0 I of the last product over the own elements of W (dead as an operand)
+            lr.want_s = 1; lr.s_smem = PA;
+            lr.sV = 0.0; lr.sW = -p.a[6].re; lr.sY = -p.a[7].re; lr.sI = p.a[8].re;
+            lr.sV_lo = 0.0; lr.sW_lo = -p.a_lo[6].re; lr.sY_lo = -p.a_lo[7].re; lr.sI_lo = p.a_lo[8].re;
+            if (LO) oc_gemm<N, EPI_S12_LR, true, false>(lr, none, y, y2);   // L -> PY (Y is dead as an operand), R -> PB, S -> PA
+            else    oc_gemm<N, EPI_S12_LR, false, false>(lr, none, y, y2);
             __syncthreads();
             OcArgs ee{};
-            ee.sA = PY; ee.sB = PB; ee.d_smem = PA; ee.v_smem = PA;     // W is dead as an operand
-            ee.kV = 0.0; ee.kW = -p.a[6].re; ee.kY = -p.a[7].re; ee.kI = p.a[8].re;
-            ee.kV_lo = 0.0; ee.kW_lo = -p.a_lo[6].re; ee.kY_lo = -p.a_lo[7].re; ee.kI_lo = p.a_lo[8].re;
-            if (LO) oc_gemm<N, EPI_S12_E, true, false>(ee, none, y, y2);
-            else    oc_gemm<N, EPI_S12_E, false, false>(ee, none, y, y2);
+            ee.sA = PY; ee.sB = PB; ee.d_smem = PA;                      // E = L R + S, in place over S
+            oc_gemm<N, EPI_ADD, false, false, true>(ee, none, y, y2);
             __syncthreads();
             PB_T(4)
             E = PA; Fb = PY; Yn = PB;         // L and R are dead
@@ -446,12 +510,12 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             oc_load_own<N>(y, PY);
             OcArgs a{};
             a.sA = PY; a.sB = PY; a.d_smem = PA;
-            oc_gemm<N, EPI_KEEP, false, false>(a, none, y, y2);         // W -> PA, own elements -> y2
+            oc_gemm<N, EPI_KEEP, false, false, true>(a, none, y, y2);   // W -> PA, own elements -> y2
             __syncthreads();
             PB_T(1)
             OcArgs b{};
             b.sA = PA; b.sB = PY; b.d_smem = PB;
-            oc_gemm<N, EPI_STORE, false, false>(b, none, y, y2);        // V -> PB
+            oc_gemm<N, EPI_STORE, false, false>(b, none, y, y2);        // V -> PB   (Y and W own elements live: four real products)
             __syncthreads();
             PB_T(2)
             {   // T' -> PA (W is dead as an operand)
@@ -475,14 +539,16 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             lr.sA = PA; lr.sB = PB; lr.d_smem = PY; lr.d_smem2 = PA; lr.v_smem = PB;
             lr.kV = p.a[3].re; lr.kW = p.a[4].re; lr.kY = p.a[5].re; lr.kI = p.a[6].re;
             lr.k2V = p.a[7].re; lr.k2W = p.a[8].re;
-            oc_gemm<N, EPI_S12_LR, false, false>(lr, none, y, y2);      // L -> PY (Y is dead as an operand), R -> PA
+            // ... and the addend S = i sV V + sW W + i sY Y + sI I of the last product over the own elements of V (dead as an operand)
+            lr.want_s = 1; lr.s_smem = PB;
+            lr.sV = p.a[9].re; lr.sW = p.a[10].re; lr.sY = p.a[11].re; lr.sI = p.a[12].re;
+            lr.sV_lo = p.a_lo[9].re; lr.sW_lo = p.a_lo[10].re; lr.sY_lo = p.a_lo[11].re; lr.sI_lo = p.a_lo[12].re;
+            if (LO) oc_gemm<N, EPI_S12_LR, true, false>(lr, none, y, y2);   // L -> PY (Y is dead as an operand), R -> PA, S -> PB
+            else    oc_gemm<N, EPI_S12_LR, false, false>(lr, none, y, y2);
             __syncthreads();
             OcArgs ee{};
-            ee.sA = PY; ee.sB = PA; ee.d_smem = PB; ee.v_smem = PB;     // E overwrites V element by element (own elements only)
-            ee.kV = p.a[9].re; ee.kW = p.a[10].re; ee.kY = p.a[11].re; ee.kI = p.a[12].re;
-            ee.kV_lo = p.a_lo[9].re; ee.kW_lo = p.a_lo[10].re; ee.kY_lo = p.a_lo[11].re; ee.kI_lo = p.a_lo[12].re;
-            if (LO) oc_gemm<N, EPI_S12_E, true, false>(ee, none, y, y2);
-            else    oc_gemm<N, EPI_S12_E, false, false>(ee, none, y, y2);
+            ee.sA = PY; ee.sB = PA; ee.d_smem = PB;                      // E = L R + S, in place over S
+            oc_gemm<N, EPI_ADD, false, false, true>(ee, none, y, y2);
             __syncthreads();
             PB_T(4)
             E = PB; Fb = PY; Yn = PA;         // L and R are dead
@@ -634,7 +700,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
             ch.sA = E; ch.sB = Fb; ch.c_smem = E; ch.c_smem2 = Fb; ch.d_glob = Fg[f_cur ^ 1]; ch.keep = keep;
             if (fuse_now) {
                 as.y_smem = Yn; as.nblock = nblock; as.y_glob = Yq;
-                oc_gemm<N, EPI_CHAIN, false, true>(ch, as, y, y2);
+                oc_gemm<N, EPI_CHAIN, false, true, true>(ch, as, y, y2);
                 ahead = nblock - 1; yq_slot = 0;
             } else {
                 if (fetch_now) {   // Yq[yq_slot] -> Yn, in flight during the product
@@ -648,7 +714,7 @@ k4_onchip_kernel(const __grid_constant__ SeriesParams p, const __grid_constant__
                     asm volatile("cp.async.commit_group;\n" ::);
                     --ahead; ++yq_slot;
                 }
-                oc_gemm<N, EPI_CHAIN, false, false>(ch, none, y, y2);
+                oc_gemm<N, EPI_CHAIN, false, false, true>(ch, none, y, y2);
                 if (fetch_now) asm volatile("cp.async.wait_group 0;\n" ::);
             }
             f_cur ^= 1;
