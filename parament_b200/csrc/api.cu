@@ -110,6 +110,7 @@ bool create_device_objects(Context *c) {
            PB_CUDA_OK(cudaMallocHost(&c->h_absmax, kMaxTerms * sizeof(double)));
 }
 void destroy_device_objects(Context *c) {
+    if (c->stager) { c->stager->stop(); delete c->stager; c->stager = nullptr; }
     free_dev(c->d_gather); free_dev(c->d_absmax); free_dev(c->d_counters);
     free_dev(c->d_H); free_dev(c->d_carr); free_dev(c->d_out); free_dev(c->d_partials);
     free_dev(c->d_Y); free_dev(c->d_comb); free_dev(c->d_comb2); free_dev(c->d_pending); free_dev(c->d_tree);
@@ -1034,6 +1035,42 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
     return PARAMENT_STATUS_SUCCESS;
 }
 
+// rows x width bytes from caller memory (row pitch spitch) to device memory (row pitch dpitch), asynchronous on `stream`.
+// Large transfers from PAGEABLE memory go through the context's staging threads (context.hpp Stager); page-locked or registered
+// caller buffers, small transfers, and $PARAMENT_STAGE_THREADS=0 use the plain asynchronous copy.
+bool h2d_rows(Context *c, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, cudaStream_t stream) {
+    const size_t total = width * rows;
+    static const size_t min_bytes = getenv("PARAMENT_STAGE_MIN_MB") ? (size_t)atoi(getenv("PARAMENT_STAGE_MIN_MB")) << 20 : (size_t)4 << 20;
+    bool staged = total >= min_bytes && !c->stager_failed;
+    if (staged) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, src) != cudaSuccess) { cudaGetLastError(); staged = false; }
+        else staged = attr.type == cudaMemoryTypeUnregistered;
+    }
+    if (staged && !c->stager) {
+        static const int env_threads = getenv("PARAMENT_STAGE_THREADS") ? atoi(getenv("PARAMENT_STAGE_THREADS")) : -1;
+        const int hw = (int)std::thread::hardware_concurrency();
+        const int want = env_threads >= 0 ? env_threads : std::max(1, std::min(6, hw / 3));   // total copying threads, the caller included
+        if (want == 0) { c->stager_failed = true; staged = false; }
+        else {
+            c->stager = new (std::nothrow) Stager();
+            if (!c->stager || !c->stager->start(want - 1)) {
+                if (c->stager) { c->stager->stop(); delete c->stager; c->stager = nullptr; }
+                c->stager_failed = true;
+                staged = false;
+            }
+        }
+    }
+    if (staged) {
+        if (rows == 1 || (dpitch == width && spitch == width)) return c->stager->copy(dst, src, total, stream);
+        for (size_t r = 0; r < rows; ++r)
+            if (!c->stager->copy((char *)dst + r * dpitch, (const char *)src + r * spitch, width, stream)) return false;
+        return true;
+    }
+    if (rows == 1 || (dpitch == width && spitch == width)) return PB_CUDA_OK(cudaMemcpyAsync(dst, src, total, cudaMemcpyHostToDevice, stream));
+    return PB_CUDA_OK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, stream));
+}
+
 // Host-pointer path of the register-resident family with the H2D copy of the amplitude stream overlapped with the
 // kernels: the work is cut into G groups (pulse ranges of an ensemble, time ranges of a single pulse); group g+1 is
 // copied on the copy stream while group g is propagated.  Replaces the reference's one blocking cudaMemcpy of the
@@ -1056,10 +1093,10 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
     auto copy_arrays = [&](size_t a0, size_t a1, size_t pt0, size_t npts) -> bool {
         // arrays [a0, a1) of the device buffer (stride seg) <- host arrays (stride pts), points [pt0, pt0 + npts) of the slice
         if (seg == pts && npts == seg)
-            return PB_CUDA_OK(cudaMemcpyAsync(dcarr + a0 * seg, carr + a0 * pts, (a1 - a0) * seg * sizeof(T), cudaMemcpyHostToDevice, c->copy_stream));
-        // strided: one 2-D copy (rows = control arrays) instead of one call per array
-        return PB_CUDA_OK(cudaMemcpy2DAsync(dcarr + a0 * seg + pt0, seg * sizeof(T), carr + a0 * pts + p_lo + pt0, (size_t)pts * sizeof(T),
-                                            npts * sizeof(T), a1 - a0, cudaMemcpyHostToDevice, c->copy_stream));
+            return h2d_rows(c, dcarr + a0 * seg, 0, carr + a0 * pts, 0, (a1 - a0) * seg * sizeof(T), 1, c->copy_stream);
+        // strided: rows = control arrays
+        return h2d_rows(c, dcarr + a0 * seg + pt0, seg * sizeof(T), carr + a0 * pts + p_lo + pt0, (size_t)pts * sizeof(T), npts * sizeof(T), a1 - a0,
+                        c->copy_stream);
     };
     if (s.batch > 1) {
         // Pulse groups sized in units of 1/8 wave of warps (a warp owns a pulse or 1/k of it, k <= 8: plan_k1), so that
@@ -1218,11 +1255,9 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
         ec = pipelined_family1<T>(c, carr, pts, p_lo, seg, s, G, result_dev);
     } else {
         if (seg == pts) {
-            if (in_bytes && !PB_CUDA_OK(cudaMemcpyAsync(c->d_carr.ptr, carr, in_bytes, cudaMemcpyHostToDevice, c->stream)))
-                return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
+            if (in_bytes && !h2d_rows(c, c->d_carr.ptr, 0, carr, 0, in_bytes, 1, c->stream)) return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
         } else {
-            if (!PB_CUDA_OK(cudaMemcpy2DAsync(c->d_carr.ptr, seg * sizeof(T), carr + p_lo, (size_t)pts * sizeof(T), seg * sizeof(T), arrays,
-                                              cudaMemcpyHostToDevice, c->stream)))
+            if (!h2d_rows(c, c->d_carr.ptr, seg * sizeof(T), carr + p_lo, (size_t)pts * sizeof(T), seg * sizeof(T), arrays, c->stream))
                 return fail(c, PARAMENT_STATUS_CUBLAS_FAILED);
         }
         ec = propagate_device(c, c->d_carr.ptr, s, result_dev, c->stream);

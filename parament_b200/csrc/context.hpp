@@ -1,7 +1,9 @@
 // context.hpp -- the opaque Parament context of this library (reference: parament_context.hpp:26-78, which
 // holds a cuBLAS handle and three dim^2 x pts work arrays; none of that exists here).
 #pragma once
+#include <algorithm>
 #include <complex>
+#include <cstring>
 #include <condition_variable>
 #include <cstddef>
 #include <functional>
@@ -9,6 +11,9 @@
 #include <thread>
 #include <vector>
 #include <cuda_runtime.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include "../../include/parament.h"
 #include "params.hpp"
 
@@ -62,6 +67,136 @@ struct DeviceWorker {
     }
 };
 
+// Host-to-device staging of PAGEABLE caller buffers (what the unchanged pyparament wrapper passes, parament.py:263-272).
+// cudaMemcpyAsync from pageable memory goes through the driver's own single-threaded bounce buffer (~10 GB/s measured: the
+// 160 MB of C5 took 16 ms against 5.5 ms from page-locked memory).  Here the transfer is cut into 2 MB chunks; a few persistent
+// host threads (and the calling thread while it waits) copy chunks into a ring of page-locked slots with streaming stores, and
+// the calling thread sends every finished chunk, in order, with an asynchronous DMA that overlaps the copies of the following
+// chunks.  The reference does one blocking cudaMemcpy of the whole array (parament.cpp:477).
+struct Stager {
+    static constexpr size_t kSlotBytes = (size_t)2 << 20;
+    static constexpr int kSlots = 12;
+    struct Task { const char *src = nullptr; size_t bytes = 0; int state = 0; };   // state: 0 idle, 1 queued / being copied, 2 copied
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    std::vector<int> queue;                 // slots waiting for a copying thread (FIFO by position `qhead`)
+    size_t qhead = 0;
+    Task tasks[kSlots];
+    bool quit = false;
+    char *slots[kSlots] = {};
+    cudaEvent_t ev[kSlots] = {};
+    bool ev_used[kSlots] = {};
+    int next_slot = 0;
+
+    // streaming copy: the destination (write-combined on its way to DRAM, read next by the DMA engine) bypasses the caches and costs
+    // no read-for-ownership; dst is 64-byte aligned (slot bases are page aligned), src arbitrary
+    static void copy_stream(char *dst, const char *src, size_t n) {
+#if defined(__SSE2__)
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 32)), d = _mm_loadu_si128((const __m128i *)(src + i + 48));
+            _mm_stream_si128((__m128i *)(dst + i), a);
+            _mm_stream_si128((__m128i *)(dst + i + 16), b);
+            _mm_stream_si128((__m128i *)(dst + i + 32), c);
+            _mm_stream_si128((__m128i *)(dst + i + 48), d);
+        }
+        _mm_sfence();
+        if (i < n) memcpy(dst + i, src + i, n - i);
+#else
+        memcpy(dst, src, n);
+#endif
+    }
+    // one queued chunk, if any (lock held on entry and exit)
+    bool run_one(std::unique_lock<std::mutex> &lk) {
+        if (qhead >= queue.size()) return false;
+        const int s = queue[qhead++];
+        if (qhead == queue.size()) { queue.clear(); qhead = 0; }
+        Task t = tasks[s];
+        lk.unlock();
+        copy_stream(slots[s], t.src, t.bytes);
+        lk.lock();
+        tasks[s].state = 2;
+        cv_done.notify_all();
+        return true;
+    }
+    void worker() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv_work.wait(lk, [&] { return quit || qhead < queue.size(); });
+            if (quit) return;
+            run_one(lk);
+        }
+    }
+    bool start(int helpers) {
+        for (int i = 0; i < kSlots; ++i) {
+            if (cudaHostAlloc((void **)&slots[i], kSlotBytes, cudaHostAllocDefault) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+        }
+        try {
+            queue.reserve(kSlots);
+            for (int i = 0; i < helpers; ++i) threads.emplace_back([this] { worker(); });
+        } catch (...) {
+            // fewer helpers than asked for: the calling thread copies as well
+        }
+        return true;
+    }
+    // dst (device) <- src (pageable host), asynchronous on `stream` once this returns; src may be released on return
+    bool copy(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+        const size_t nchunks = (bytes + kSlotBytes - 1) / kSlotBytes;
+        size_t queued = 0, sent = 0;
+        const int base = next_slot;
+        auto slot_of = [&](size_t i) { return (int)((base + i) % kSlots); };
+        std::unique_lock<std::mutex> lk(m);
+        while (sent < nchunks) {
+            while (queued < nchunks && queued - sent < (size_t)kSlots) {
+                const int s = slot_of(queued);
+                if (ev_used[s]) {   // the slot's previous DMA has to have drained
+                    lk.unlock();
+                    const cudaError_t e = cudaEventSynchronize(ev[s]);
+                    lk.lock();
+                    if (e != cudaSuccess) return false;
+                    ev_used[s] = false;
+                }
+                tasks[s].src = (const char *)src + queued * kSlotBytes;
+                tasks[s].bytes = std::min(kSlotBytes, bytes - queued * kSlotBytes);
+                tasks[s].state = 1;
+                queue.push_back(s);
+                ++queued;
+            }
+            cv_work.notify_all();
+            const int s = slot_of(sent);
+            while (tasks[s].state != 2)
+                if (!run_one(lk)) cv_done.wait(lk, [&] { return tasks[s].state == 2 || qhead < queue.size(); });   // help, or wait
+            tasks[s].state = 0;
+            const size_t n = tasks[s].bytes;
+            lk.unlock();
+            const bool ok = cudaMemcpyAsync((char *)dst + sent * kSlotBytes, slots[s], n, cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+                            cudaEventRecord(ev[s], stream) == cudaSuccess;
+            lk.lock();
+            if (!ok) return false;
+            ev_used[s] = true;
+            ++sent;
+        }
+        next_slot = slot_of(nchunks);
+        return true;
+    }
+    void stop() {   // with the owning context's device current
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit = true;
+        }
+        cv_work.notify_all();
+        for (std::thread &t : threads) if (t.joinable()) t.join();
+        threads.clear();
+        for (int i = 0; i < kSlots; ++i) {
+            if (ev[i]) { if (ev_used[i]) cudaEventSynchronize(ev[i]); cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+            if (slots[i]) { cudaFreeHost(slots[i]); slots[i] = nullptr; }
+        }
+    }
+};
+
 struct Context {
     unsigned int magic = 0x50423230;   // "PB20"
     bool fp64 = false;                 // context precision of the I/O operands
@@ -112,6 +247,8 @@ struct Context {
     bool is_peer = false;
     bool peer_store_ok = false;     // helper: its kernels may store into the first device's memory (same device or peer access)
     DeviceWorker *worker = nullptr; // helper: the host thread that drives this device
+    Stager *stager = nullptr;       // staging threads + page-locked ring for pageable caller buffers (created on first use)
+    bool stager_failed = false;
     int stat_devices = 1;           // devices that took part in the last equiprop
 
     // statistics of the last equiprop (Parament_lastStat)

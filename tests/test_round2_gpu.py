@@ -277,3 +277,25 @@ def test_tf32_path_is_selected_by_step_count(pb):
         ctx.set_hamiltonian(w1.H0, *w1.H1, quadrature_mode="midpoint")
         ctx.equiprop(w1.dt, *w1.carr)
         assert ctx.stat(15) == 0
+
+
+def test_pageable_staging_matches_page_locked_input(pb):
+    """Large pageable caller buffers are staged by the library's copy threads (context.hpp Stager), page-locked ones are sent
+    directly: same kernels, same copy groups, bit-identical propagators -- for a long single pulse (strided group copies), an
+    ensemble, and a dim-64 pulse (one plain copy)."""
+    torch = pytest.importorskip("torch")
+    for name, pts, batch in (("C2", 700001, None), ("C5", 1000, 6000), ("C3", 40000, None)):
+        w = make_workload(name, pts=pts, batch=batch)
+        carr = np.ascontiguousarray(w.carr.reshape(w.batch, w.amps, w.pts))
+        assert carr.nbytes > (2 << 20)
+        pinned = torch.from_numpy(carr.copy()).pin_memory().numpy()
+        with pb.Parament(w.precision) as ctx:
+            ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=w.use_magnus, quadrature_mode=w.quadrature)
+            a = ctx.equiprop_batch(w.dt, carr)
+            h2d = ctx.stat(6)
+            b = ctx.equiprop_batch(w.dt, pinned)
+            a2 = ctx.equiprop_batch(w.dt, carr)
+        assert h2d == carr.nbytes
+        assert np.array_equal(a, b) and np.array_equal(a, a2)
+        Uo = equiprop_oracle(w.H0, w.H1, carr[0], w.dt, w.quadrature, w.use_magnus, w.precision, workers=8)
+        assert rel_frobenius(a[0], Uo) < TOL[w.precision]
