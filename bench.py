@@ -414,6 +414,9 @@ class Ours:
                              "kernel": KERNEL_NAMES.get(stats["family"]), "kernel_ms_per_launch": kernel_ms,
                              "flops_per_step_algorithmic": F_alg, "flops_per_step_executed": F_exe,
                              "executed_tflops": executed, "executed_frac": executed / pk if pk > 0 else None,
+                             # the same rate counted at 8 n^3 flops per complex product: comparable across kernels that form a complex
+                             # product from four or from three real ones (the latter spend part of the pipe on operand sums instead)
+                             "complex_product_rate_frac": flops_per_step(w, stats["products"], 4) * per_gpu_rate * 1e-12 / pk if pk > 0 else None,
                              "fp32_ffma_peak_tflops": self.peak_ffma, "tf32_mma_sync_peak_tflops": self.peak_tf32,
                              "hbm": {"achieved_gbs": local.nbytes / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"),
                                      "peak_source": how, "note": "algorithmic HBM input is the amplitude stream only; not the limiter"}},

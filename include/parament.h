@@ -214,14 +214,15 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  *                        3 degree 8 in three products, 4 degree 12 in four products -- all the same polynomial family)
  *  10 complex matrix products executed per effective step (series + ordered product)
  *  13 real matrix products per complex product in the kernel family used, averaged over the products of a step (4; 3 for the
- *     batched GEMM of dim > 64; 3.25 / 3.4 for the shared-memory-resident kernel of dim 17..64 in its degree-8 / degree-12 form)
+ *     batched GEMM of dim > 64 and for the degree-8 form of complex64 contexts at dim 9..16; 3.25 / 3.4 for the shared-memory-resident
+ *     kernel of dim 17..64 in its degree-8 / degree-12 form)
  *  15 arithmetic of the last call: 0 = double precision on the FP64 tensor pipe (DMMA); 1 = single precision as 3xTF32 split
  *     products on the warp-level tensor path (complex64 contexts, dim <= 8, accumulated phase N h (s(H0) + sum_k s(H_k)) <= 128:
  *     the range in which the measured error stays below half the 1e-5 tolerance, profiles/error_growth_tf32_r2.md)
  * Environment switches read at Parament_create (development / A-B testing): PARAMENT_SERIES=clenshaw forces the reference's
  * recurrence, PARAMENT_SERIES=horner the Horner / Paterson-Stockmeyer forms; PARAMENT_NO_ONCHIP=1 selects the L2-scratch
  * chain kernel for dim 17..64; PARAMENT_DEVICE the default CUDA device; PARAMENT_F3_STREAMS=1..4 the chunks in flight for dim > 64
- * (default 4); PARAMENT_K4_3M=0..3 the complex product of the batched GEMM (0: four real products on 64x64 tiles; 3, default: three real
+ * (default 4); PARAMENT_K1_3M=0 the four-real-product chain kernel at dim 9..16 (read once per process); PARAMENT_K4_3M=0..3 the complex product of the batched GEMM (0: four real products on 64x64 tiles; 3, default: three real
  * products on 64x32 tiles); PARAMENT_K4_FEED=tma the bulk-copy (TMA engine) operand feed of that GEMM in mode 0 (measured slower than cp.async);
  * PARAMENT_COPY_GROUPS=1..8 the copy/compute groups of the host-pointer pipeline; PARAMENT_NORM=reference builds the series for
  * Hnorm at every dimension (A/B of the spectral bound); PARAMENT_C64_MATH=f64|tf32 forces the arithmetic of complex64 contexts with

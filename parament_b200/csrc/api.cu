@@ -1702,6 +1702,7 @@ double Parament_lastStat(void *h, int key) {
                 const double np_ = Parament_lastStat(h, 10);
                 return np_ > 0 ? (4.0 * (np_ - 1.0) + 3.0) / np_ : 4.0;
             }
+            if (c->family == 1 && c->stat_math == 0) return k1_real_products(c->npad, c->fp64, c->stat_horner);
             return 4;
         case 14: return c->stat_series_norm;
         case 15: return c->stat_math;

@@ -33,6 +33,9 @@ cudaError_t launch_k1_tf32_chain(const SeriesParams &p, const void *carr, const 
                                  const K1Plan &plan, unsigned long long step_lo, unsigned long long step_hi, const K1Final &fz,
                                  cudaStream_t stream);
 
+// real products per complex matrix product in the chain kernel that launch_k1_chain selects (3 for the degree-8 form at dim 9..16)
+int k1_real_products(int npad, bool fp64_io, int horner);
+
 // Multi-GPU combine for dim <= 16 in one launch: out = parts[count-1] ... parts[0]; parts / out are dim x dim propagators in the
 // context precision on the device.
 cudaError_t launch_k3_combine(int npad, bool fp64_io, const void *parts, unsigned int count, int n, void *out, cudaStream_t stream);
