@@ -37,7 +37,7 @@ namespace pb {
 
 // Hfrag layout: [matrix][layout 0 = AccFrag order, 1 = BFrag order][element e < 2*NT*NT][lane] as double2.
 // OCC: CTAs per SM the register allocation is bounded for (NT == 2: 2 -> 255 registers, 3 -> 168 registers with spills)
-// MUL3 (three-product form of dim 9..16 only): complex products from three real ones (frag.cuh cmma3).
+// MUL3 (degree-8 three-product form, complex64 contexts): complex products from three real ones (frag.cuh cmma3).
 template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false>
 __global__ void __launch_bounds__(32 * K1_WARPS, OCC)
 k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ Hfrag,
@@ -420,12 +420,15 @@ static bool k1_mul3() {
     static const bool mul3 = !(getenv("PARAMENT_K1_3M") && atoi(getenv("PARAMENT_K1_3M")) == 0);
     return mul3;
 }
-int k1_real_products(int npad, bool fp64_io, int horner) { return (npad == 16 && !fp64_io && horner == 3 && k1_mul3()) ? 3 : 4; }
+int k1_real_products(int npad, bool fp64_io, int horner) { return (!fp64_io && horner == 3 && k1_mul3()) ? 3 : 4; }
 
 template <int NT, typename IO, int HORNER>
 static cudaError_t launch_chain_tt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                    unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
                                    unsigned long long step_hi, const K1Final &fz, cudaStream_t stream) {
+    if constexpr (NT == 1 && HORNER == 3) {
+        if (k1_mul3()) return launch_chain_ttt<NT, IO, HORNER, 6, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+    }
     if (NT == 1) return launch_chain_ttt<NT, IO, HORNER, 6>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     if (plan.ctas_per_sm == 3) return launch_chain_ttt<NT, IO, HORNER, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     if constexpr (NT == 2 && HORNER == 3) {
