@@ -1,5 +1,5 @@
 // CPU checker for parament_b200/csrc/plan.hpp: prints the partitions as JSON lines for tests/test_plan.py.
-//   plan_check k1 npad batch nsteps num_sms horner
+//   plan_check k1 npad batch nsteps num_sms horner [fuse]
 //   plan_check egroups batch unit G
 //   plan_check tgroups nsteps G
 //   plan_check devices configured batch nsteps npad
@@ -11,11 +11,12 @@
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
     using namespace pb;
-    if (!strcmp(argv[1], "k1") && argc == 7) {
-        const K1Plan p = plan_k1(atoi(argv[2]), (unsigned)atoll(argv[3]), strtoull(argv[4], nullptr, 10), atoi(argv[5]), atoi(argv[6]) != 0);
+    if (!strcmp(argv[1], "k1") && (argc == 7 || argc == 8)) {
+        const bool fuse = argc == 8 && atoi(argv[7]) != 0;
+        const K1Plan p = plan_k1(atoi(argv[2]), (unsigned)atoll(argv[3]), strtoull(argv[4], nullptr, 10), atoi(argv[5]), atoi(argv[6]) != 0, fuse);
         printf("{\"grid\": %u, \"chunks_per_pulse\": %u, \"partials_per_pulse\": %u, \"reduce_in_cta\": %d, \"k3_warps\": %d, "
-               "\"ctas_per_sm\": %d, \"partial_elems\": %zu, \"warp_slots\": %u, \"mid_elems\": %zu, \"k3_launches\": %d}\n",
-               p.grid, p.chunks_per_pulse, p.partials_per_pulse, p.reduce_in_cta, p.k3_warps, p.ctas_per_sm, p.partial_elems,
+               "\"ctas_per_sm\": %d, \"partial_elems\": %zu, \"groups_per_pulse\": %u, \"warp_slots\": %u, \"mid_elems\": %zu, \"k3_launches\": %d}\n",
+               p.grid, p.chunks_per_pulse, p.partials_per_pulse, p.reduce_in_cta, p.k3_warps, p.ctas_per_sm, p.partial_elems, p.groups_per_pulse,
                k1_warp_slots(atoi(argv[2]), atoi(argv[5]), atoi(argv[6]) != 0),
                k3_mid_elems(atoi(argv[2]), (unsigned)atoll(argv[3]), p.partials_per_pulse), k3_launches(p.partials_per_pulse));
         return 0;

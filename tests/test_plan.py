@@ -35,6 +35,23 @@ def test_single_pulse_fills_exactly_one_wave(plan):
     assert plan("k1", 16, 1, 499999, SMS, 0)["grid"] == SMS * 3
 
 
+def test_fused_final_stage_plans(plan):
+    """Plans of the single-launch path (k1_common.cuh): one long pulse -> groups of 16 CTA partials for the last-arriver
+    reduction; ensembles -> a pulse is cut into 1, 2 or 4 chunks so that its warps share a CTA; no groups."""
+    p = plan("k1", 16, 1, 499999, SMS, 1, 1)
+    assert p["reduce_in_cta"] == 1 and p["partials_per_pulse"] == SMS * 2 and p["groups_per_pulse"] == (SMS * 2 + 15) // 16
+    assert plan("k1", 16, 1, 499999, SMS, 1)["groups_per_pulse"] == 0          # legacy plan: a k3_reduce launch follows
+    for batch, nsteps in ((10000, 1000), (1250, 1000), (5000, 64), (3552, 100000)):
+        e = plan("k1", 8, batch, nsteps, SMS, 1, 1)
+        if e["reduce_in_cta"] == 0:
+            assert e["chunks_per_pulse"] in (1, 2, 4) and e["groups_per_pulse"] == 0
+            assert e["grid"] * 4 >= batch * e["chunks_per_pulse"]
+        else:
+            assert e["groups_per_pulse"] >= 1 and e["chunks_per_pulse"] % 4 == 0
+    small = plan("k1", 8, 1, 9999, SMS, 1, 1)                                    # C1: one pulse, 313 CTAs -> 20 groups
+    assert small["groups_per_pulse"] == (small["partials_per_pulse"] + 15) // 16 >= 2
+
+
 def test_short_pulses_keep_eight_steps_per_warp(plan):
     p = plan("k1", 16, 1, 100, SMS, 1)
     assert p["chunks_per_pulse"] * 8 <= 100 + 8 * 4 and p["grid"] == p["partials_per_pulse"] >= 1
