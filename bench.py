@@ -377,18 +377,30 @@ class Ours:
             # 3xTF32 split products: SURVEY 8(d) asks for that fraction against the FP32 ceiling the path replaces (FFMA peak),
             # with the tensor-pipe utilisation (three TF32 MACs per fp32-grade MAC) reported beside it.
             tf32 = stats["math"] == 1
+            mixed = stats["math"] == 2
             pk = self.peak_ffma if tf32 else self.peak_dmma
             pipe = ("FP32-grade products as 3xTF32 on the warp-level tensor path (HMMA.1688.F32.TF32); peak = measured FFMA rate, the FP32 ceiling it replaces"
                     if tf32 else "FP64 tensor pipe (DMMA.8x8x4)")
+            tf32_exec = 3.0 * executed if tf32 else 0.0
+            if mixed:
+                # two of the step's products (y02, L'R) run at fp32 grade as 3xTF32 on the other tensor sub-pipe: `frac` is the sum of
+                # the two pipes' busy fractions at their measured peaks (what ncu's sm__pipe_tensor_cycles_active counts)
+                F_exe = flops_per_step(w, stats["products"] - 2, stats["real_products"])
+                executed = F_exe * per_gpu_rate * 1e-12
+                tf32_exec = 2 * 3 * 8.0 * w.dim ** 3 * per_gpu_rate * 1e-12
+                pipe = ("FP64 tensor pipe (DMMA.8x8x4) for X^2 and the running product + TF32 tensor path (HMMA.1688.F32.TF32, 3xTF32) for the "
+                        "two small products of the degree-8 form; frac = sum of the two pipes' busy fractions")
             rec = {
                 "value": job_steps * steps / (dev_ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": dev_ms / steps, "scaling": mode, "dtype": "f32 (3xTF32)" if tf32 else "f64",
+                "ms_per_step": dev_ms / steps, "scaling": mode, "dtype": "f32 (3xTF32)" if tf32 else ("f64 + f32 (3xTF32)" if mixed else "f64"),
                 "config": workload_config(name, w, world, mode, l2),
                 "implementation": {"degree_reference": stats["M_ref"], "degree_used": stats["M_used"],
                                    "series_evaluation": SERIES_NAMES.get(stats["horner"], str(stats["horner"])),
                                    "matrix_products_per_step": stats["products"],
                                    "real_products_per_complex_product": stats["real_products"], "kernel_family": stats["family"],
-                                   "arithmetic": "fp32 as 3xTF32 (mma.sync.m16n8k8.tf32)" if tf32 else "fp64 (mma.sync.m8n8k4.f64)",
+                                   "arithmetic": ("fp32 as 3xTF32 (mma.sync.m16n8k8.tf32)" if tf32 else
+                                                  "fp64 (mma.sync.m8n8k4.f64) + 3xTF32 for the two small series products" if stats["math"] == 2
+                                                  else "fp64 (mma.sync.m8n8k4.f64)"),
                                    "norm_reference": stats["hnorm"], "norm_series": stats["series_norm"],
                                    "effective_steps_per_gpu": local_steps},
                 "clocks": self.sampler.window(t0, t1),
@@ -404,12 +416,12 @@ class Ours:
                 # evaluation executes fewer products than that recurrence, so `frac` is computed from the EXECUTED flops and
                 # stays a pipe utilisation (<= 1); the algorithmic figure is kept in `algorithmic_frac`.
                 "roofline": {"bound": "tensor", "pipe": pipe, "achieved": achieved, "peak": pk, "unit": "TFLOP/s",
-                             "frac": min(achieved, executed) / pk if pk > 0 else None,
+                             "frac": ((executed / pk + tf32_exec / self.peak_tf32) if mixed else min(achieved, executed) / pk) if pk > 0 else None,
                              "algorithmic_frac": achieved / pk if pk > 0 else None, "traffic": traffic,
                              "peak_source": ("Parament_measurePeak(FFMA) in this process" if tf32 else
                                              "Parament_measurePeak(DMMA mma.sync.m8n8k4.f64) in this process") + "; MEASURED_PEAKS.json has no FP32 / FP64 figure",
-                             "tensor_pipe": ({"executed_tf32_tflops": 3.0 * executed, "peak_tflops": self.peak_tf32,
-                                              "frac": 3.0 * executed / self.peak_tf32 if self.peak_tf32 > 0 else None} if tf32 else None),
+                             "tensor_pipe": ({"executed_tf32_tflops": tf32_exec, "peak_tflops": self.peak_tf32,
+                                              "frac": tf32_exec / self.peak_tf32 if self.peak_tf32 > 0 else None} if (tf32 or mixed) else None),
                              "fp64_dmma_peak_tflops": self.peak_dmma,
                              "kernel": KERNEL_NAMES.get(stats["family"]), "kernel_ms_per_launch": kernel_ms,
                              "flops_per_step_algorithmic": F_alg, "flops_per_step_executed": F_exe,

@@ -218,7 +218,9 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  *     kernel of dim 17..64 in its degree-8 / degree-12 form)
  *  15 arithmetic of the last call: 0 = double precision on the FP64 tensor pipe (DMMA); 1 = single precision as 3xTF32 split
  *     products on the warp-level tensor path (complex64 contexts, dim <= 8, accumulated phase N h (s(H0) + sum_k s(H_k)) <= 128:
- *     the range in which the measured error stays below half the 1e-5 tolerance, profiles/error_growth_tf32_r2.md)
+ *     the range in which the measured error stays below half the 1e-5 tolerance, profiles/error_growth_tf32_r2.md);
+ *     2 = mixed: double precision for X^2, the first- and second-order terms and the running product, 3xTF32 for the two small
+ *     products of the degree-8 form (complex64 contexts, dim 9..16, accumulated phase <= 5e5; PARAMENT_K1_MIXED=0 / 1 forces it)
  * Environment switches read at Parament_create (development / A-B testing): PARAMENT_SERIES=clenshaw forces the reference's
  * recurrence, PARAMENT_SERIES=horner the Horner / Paterson-Stockmeyer forms; PARAMENT_NO_ONCHIP=1 selects the L2-scratch
  * chain kernel for dim 17..64; PARAMENT_DEVICE the default CUDA device; PARAMENT_F3_STREAMS=1..4 the chunks in flight for dim > 64

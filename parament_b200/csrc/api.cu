@@ -398,8 +398,8 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     else                { c->family = 3; c->npad = k4_pad((int)dim); c->k4_slots = k4_wave_slots(c->npad, c->num_sms); }
     c->series_cache.valid = false;
     // spectral bound of the step Hamiltonians (dim > 16, where it saves a matrix product per step; series_norm_for_call)
-    // (also for complex64 contexts of dim <= 8: the accumulated phase decides between FP64 and TF32 arithmetic, tf32_candidate)
-    if ((c->family != 1 && c->norm_mode == 1) || (!c->fp64 && c->npad == 8 && c->family == 1))
+    // (also for complex64 contexts of dim <= 16: the accumulated phase decides between FP64 and TF32 / mixed arithmetic)
+    if ((c->family != 1 && c->norm_mode == 1) || (!c->fp64 && c->family == 1))
         for (int m = 0; m <= A; ++m) c->sigma_max[m] = spectral_norm(c->mats.data() + (size_t)m * nn, (int)dim);
 
     // physical commutators [H0,H_j] and [H_j,H_k], j<k (parament.cpp:289-359): on the host for the
@@ -542,6 +542,16 @@ bool solve_degree8(SeriesParams &p) {
     store_split(p, 6, r[2] - e0 * e2);
     store_split(p, 7, r[1]);
     store_split(p, 8, r[0]);
+    store_split(p, 9, r[2]);   // the full second-order coefficient: the mixed-precision kernel keeps the e0 e2 W term out of its fp32 product
+    // constants of that kernel's fp32 part; those that enter the cubic coefficient as hi + lo pairs (a float-rounded constant
+    // would be the same relative error in every step)
+    auto hi = [](long double x) { return (float)x; };
+    auto lo = [](long double x) { return (float)(x - (long double)(float)x); };
+    p.fconst[0] = hi(v[0]); p.fconst[1] = hi(v[2]);
+    p.fconst[2] = hi(v[1]); p.fconst[3] = lo(v[1]);
+    p.fconst[4] = hi(v[3]); p.fconst[5] = lo(v[3]);
+    p.fconst[6] = hi(v[4]); p.fconst[7] = lo(v[4]);
+    p.fconst[8] = hi(v[5]); p.fconst[9] = lo(v[5]);
     return true;
 }
 
@@ -592,6 +602,20 @@ bool tf32_candidate(const Context *c, unsigned long long total_steps, double h) 
     if (!(rho > 0.0) || rho > c->Hnorm) rho = c->Hnorm;
     return (double)total_steps * std::fabs(h) * rho <= max_phase;
 }
+// complex64 contexts, dim 9..16, degree-8 form: mixed precision (k1_warp.cu MIXED).  W = X X, all first- and second-order terms
+// and the running product stay in FP64; the two products of the series whose results are small run at fp32 grade on the TF32
+// tensor path.  Their truncated accumulation is a coherent error of relative size ~1e-8 on terms of size <= 2e-4 per step:
+// measured 2.3e-7 at C2 (5e5 steps, accumulated phase N h rho = 4e4), linear in the phase, so the path is
+// taken while the phase is below 5e5 (predicted error 2.9e-6); $PARAMENT_K1_MIXED=0 / 1 forces the choice (read per call).
+constexpr double kMixedMaxPhase = 5.0e5;
+bool use_mixed_path(const Context *c, const SeriesParams &p, unsigned long long total_steps, double h) {
+    if (c->fp64 || c->family != 1 || c->npad != 16 || p.horner != 3) return false;
+    if (const char *e = getenv("PARAMENT_K1_MIXED")) return atoi(e) == 1;
+    double rho = 0.0;
+    for (double sg : c->sigma_max) rho += sg;
+    if (!(rho > 0.0) || rho > c->Hnorm) rho = c->Hnorm;
+    return (double)total_steps * std::fabs(h) * rho <= kMixedMaxPhase;
+}
 bool use_tf32_path(const Context *c, const SeriesParams &p, const CallSpec &s) {
     const double h = (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) ? 2.0 * s.dt : s.dt;
     return p.horner == 3 && tf32_candidate(c, s.total_steps, h);   // the kernel implements the three-product degree-8 form only
@@ -636,6 +660,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
         p.horner = sc.horner;
         memcpy(p.a, sc.a, sizeof(p.a));
         memcpy(p.a_lo, sc.a_lo, sizeof(p.a_lo));
+        memcpy(p.fconst, sc.fconst, sizeof(p.fconst));
     } else {
     // sigma is rounded to double FIRST and x is derived from the rounded value in long double, so that
     // sigma * x == 2 h holds to 1e-19: a relative error in sigma alone would stretch the time axis coherently.
@@ -700,8 +725,10 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     sc.horner = p.horner; sc.sigma = p.sigma;
     memcpy(sc.a, p.a, sizeof(p.a));
     memcpy(sc.a_lo, p.a_lo, sizeof(p.a_lo));
+    memcpy(sc.fconst, p.fconst, sizeof(p.fconst));
     }
     c->stat_horner = p.horner;
+    p.mixed = use_mixed_path(c, p, s.total_steps, h) ? 1 : 0;
     const int A = c->amps, Ain = (int)s.amps;
     int nt = 0;
     const int need = Ain + (c->enable_magnus ? Ain + Ain * (Ain - 1) / 2 : 0);
@@ -1013,7 +1040,7 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
     // all allocations happen before the timed region (grow-only scratch, nothing is allocated in steady state)
     K1Plan plan{};
     const bool tf32 = use_tf32_path(c, p, s);
-    c->stat_math = tf32 ? 1 : 0;
+    c->stat_math = tf32 ? 1 : (p.mixed ? 2 : 0);
     K1Final fz{};
     if (c->family == 1) {
         plan = plan_k1(c->npad, s.batch, s.nsteps, c->num_sms, p.horner != 0, true);
@@ -1088,7 +1115,7 @@ Parament_ErrorCode pipelined_family1(Context *c, const T *carr, unsigned int pts
     T *dcarr = (T *)c->d_carr.ptr;
     const bool horner = p.horner != 0;
     const bool tf32 = use_tf32_path(c, p, s);
-    c->stat_math = tf32 ? 1 : 0;
+    c->stat_math = tf32 ? 1 : (p.mixed ? 2 : 0);
     if (G > 8) G = 8;
     auto copy_arrays = [&](size_t a0, size_t a1, size_t pt0, size_t npts) -> bool {
         // arrays [a0, a1) of the device buffer (stride seg) <- host arrays (stride pts), points [pt0, pt0 + npts) of the slice
@@ -1702,7 +1729,7 @@ double Parament_lastStat(void *h, int key) {
                 const double np_ = Parament_lastStat(h, 10);
                 return np_ > 0 ? (4.0 * (np_ - 1.0) + 3.0) / np_ : 4.0;
             }
-            if (c->family == 1 && c->stat_math == 0) return k1_real_products(c->npad, c->fp64, c->stat_horner);
+            if (c->family == 1 && c->stat_math != 1) return k1_real_products(c->npad, c->fp64, c->stat_horner);
             return 4;
         case 14: return c->stat_series_norm;
         case 15: return c->stat_math;

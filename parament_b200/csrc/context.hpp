@@ -266,6 +266,7 @@ struct Context {
         int horner = 0;
         double sigma = 0.0;
         cplx a[kMaxDegree + 1], a_lo[kMaxDegree + 1];
+        float fconst[16];
     } series_cache;
     unsigned long long stat_steps = 0;
     double stat_h2d = 0.0, stat_d2h = 0.0;

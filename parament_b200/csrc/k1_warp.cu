@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include "k1_warp.hpp"
 #include "k1_common.cuh"
+#include "frag_tf32.cuh"
 
 namespace pb {
 
@@ -38,7 +39,11 @@ namespace pb {
 // Hfrag layout: [matrix][layout 0 = AccFrag order, 1 = BFrag order][element e < 2*NT*NT][lane] as double2.
 // OCC: CTAs per SM the register allocation is bounded for (NT == 2: 2 -> 255 registers, 3 -> 168 registers with spills)
 // MUL3 (degree-8 three-product form, complex64 contexts): complex products from three real ones (frag.cuh cmma3).
-template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false>
+// MIXED (dim 9..16, complex64 contexts, degree-8 form): the two products of the series whose results are small -- y02 = T W
+// (~1e-5) and L' R (~1e-4, L' = L - e0 I) -- run at fp32 grade as 3xTF32 on the warp-level tensor path (frag_tf32.cuh), which
+// is a different pipe from the FP64 one; W = X X, every term of first and second order, and the running product stay in FP64.
+// The FP64 pipe, which bounds this kernel, then carries two matrix products per step instead of four.
+template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false, bool MIXED = false>
 __global__ void __launch_bounds__(32 * K1_WARPS, OCC)
 k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ Hfrag,
                 double2 *__restrict__ partials, unsigned int batch, unsigned int chunks_per_pulse,
@@ -217,6 +222,65 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                 const double c4 = p.a[0].re, c3 = p.a[1].re, d2 = p.a[2].re, d1 = p.a[3].re, e2 = p.a[4].re, e0 = p.a[5].re;
                 const double r2 = p.a[6].re, r1 = p.a[7].re, r0 = p.a[8].re;
                 const int g = lane >> 2, q = lane & 3;
+                if constexpr (MIXED && NT == 2) {
+                    // E = -r2 W - i r1 X + r0 I  +  e0 y02 + L' R      with  L = L' + e0 I,  r2 = r2' + e0 e2  (api.cu solve_degree8):
+                    // the first three terms in FP64, the rest -- fourth order and up, plus the part of the cubic term that the
+                    // product carries -- at fp32 grade.  The constants that enter the cubic coefficient (c3, d1, e2, e0) are
+                    // hi + lo pairs: a float-rounded constant would be the same relative error in every step.
+                    // (split on the host, api.cu solve_degree8: kernel parameters are read straight from the constant bank)
+                    const float c4f = p.fconst[0], d2f = p.fconst[1], c3h = p.fconst[2], c3l = p.fconst[3], d1h = p.fconst[4], d1l = p.fconst[5];
+                    const float e2h = p.fconst[6], e2l = p.fconst[7], e0h = p.fconst[8], e0l = p.fconst[9];
+                    const double r2full = p.a[9].re;
+                    acc_to_bfrag<NT>(Yb, Ya, lane);
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) (&Yb.nim[0][0])[e] = (&Yb.re[0][0])[e] + (&Yb.im[0][0])[e];
+                    AccFrag<NT> Wa;
+                    set_zero<NT>(Wa);
+                    cmma3<NT>(Wa, Ya, Yb);                  // W = X X in FP64
+                    FAcc2 Xf, Wf;
+#pragma unroll
+                    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const bool diag = (mt == nt && g == 2 * q + i);
+                                S1.re[mt][nt][i] = fma(-r2full, Wa.re[mt][nt][i], fma(r1, Ya.im[mt][nt][i], diag ? r0 : 0.0));
+                                S1.im[mt][nt][i] = fma(-r2full, Wa.im[mt][nt][i], -r1 * Ya.re[mt][nt][i]);
+                                Xf.re[mt][nt][i] = (float)Ya.re[mt][nt][i]; Xf.im[mt][nt][i] = (float)Ya.im[mt][nt][i];
+                                Wf.re[mt][nt][i] = (float)Wa.re[mt][nt][i]; Wf.im[mt][nt][i] = (float)Wa.im[mt][nt][i];
+                            }
+                    FAcc2 Tf;                              // T = c4 W + i c3 X
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        (&Tf.re[0][0][0])[e] = fmaf(-c3h, (&Xf.im[0][0][0])[e], fmaf(-c3l, (&Xf.im[0][0][0])[e], c4f * (&Wf.re[0][0][0])[e]));
+                        (&Tf.im[0][0][0])[e] = fmaf(c3h, (&Xf.re[0][0][0])[e], fmaf(c3l, (&Xf.re[0][0][0])[e], c4f * (&Wf.im[0][0][0])[e]));
+                    }
+                    FB2 Wbf;
+                    facc_to_fb(Wbf, Wf, lane);
+                    FAcc2 Y2f;
+                    tf32_cmul16(Y2f, Tf, Wbf);              // y02 = T W
+                    FB2 Rbf;                                // R = y02 - e2 W, right-operand layout
+                    facc_to_fb(Rbf, Y2f, lane);
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        (&Rbf.re[0][0])[e] = fmaf(-e2h, (&Wbf.re[0][0])[e], fmaf(-e2l, (&Wbf.re[0][0])[e], (&Rbf.re[0][0])[e]));
+                        (&Rbf.im[0][0])[e] = fmaf(-e2h, (&Wbf.im[0][0])[e], fmaf(-e2l, (&Wbf.im[0][0])[e], (&Rbf.im[0][0])[e]));
+                    }
+                    FAcc2 Lf;                              // L' = y02 - d2 W - i d1 X
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        (&Lf.re[0][0][0])[e] = fmaf(d1h, (&Xf.im[0][0][0])[e], fmaf(d1l, (&Xf.im[0][0][0])[e], fmaf(-d2f, (&Wf.re[0][0][0])[e], (&Y2f.re[0][0][0])[e])));
+                        (&Lf.im[0][0][0])[e] = fmaf(-d1h, (&Xf.re[0][0][0])[e], fmaf(-d1l, (&Xf.re[0][0][0])[e], fmaf(-d2f, (&Wf.im[0][0][0])[e], (&Y2f.im[0][0][0])[e])));
+                    }
+                    FAcc2 LRf;
+                    tf32_cmul16(LRf, Lf, Rbf);              // L' R
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {          // E = S + (e0 y02 + L' R)
+                        (&S1.re[0][0][0])[e] += (double)fmaf(e0h, (&Y2f.re[0][0][0])[e], fmaf(e0l, (&Y2f.re[0][0][0])[e], (&LRf.re[0][0][0])[e]));
+                        (&S1.im[0][0][0])[e] += (double)fmaf(e0h, (&Y2f.im[0][0][0])[e], fmaf(e0l, (&Y2f.im[0][0][0])[e], (&LRf.im[0][0][0])[e]));
+                    }
+                } else {
                 if (!BOTH) acc_to_bfrag<NT>(Yb, Ya, lane);
 #pragma unroll
                 for (int e = 0; e < NE; ++e) (&Yb.nim[0][0])[e] = bfrag_third<MUL3>((&Yb.re[0][0])[e], (&Yb.im[0][0])[e]);
@@ -264,6 +328,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                             Y2.im[mt][nt][i] = fma(-d2, Wa.im[mt][nt][i], fma(-d1, Ya.re[mt][nt][i], Y2.im[mt][nt][i]));
                         }
                 if (MUL3) cmma3<NT>(S1, Y2, Rb); else cmma<NT>(S1, Y2, Rb);   // E
+                }
             } else if (HORNER) {
                 // ---- Horner in W = Y^2:  E = sum_i (c_2i I + c_2i+1 Y) W^i, 1 + floor(M/2) products instead of M - 1.
                 // W is needed as a RIGHT operand.  (Y^T)^2 = (Y^2)^T is formed in accumulator layout from register
@@ -405,11 +470,11 @@ k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, unsigned
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
-template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false>
+template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false, bool MIXED = false>
 static cudaError_t launch_chain_ttt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                    unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
                                    unsigned long long step_hi, const K1Final &fz, cudaStream_t stream) {
-    k1_chain_kernel<NT, IO, HORNER, OCC, MUL3><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
+    k1_chain_kernel<NT, IO, HORNER, OCC, MUL3, MIXED><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
                                                                                    plan.chunks_per_pulse, step_lo, step_hi,
                                                                                    plan.reduce_in_cta, fz);
     return cudaGetLastError();
@@ -430,6 +495,11 @@ static cudaError_t launch_chain_tt(const SeriesParams &p, const IO *carr, const 
         if (k1_mul3()) return launch_chain_ttt<NT, IO, HORNER, 6, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     }
     if (NT == 1) return launch_chain_ttt<NT, IO, HORNER, 6>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+    if constexpr (NT == 2 && HORNER == 3 && sizeof(IO) == sizeof(float2)) {
+        // mixed precision: the two small products of the series on the TF32 tensor path (api.cu use_mixed_path decides).
+        // Measured at C2: 2.149 -> 1.818 ms per 5e5 steps (three CTAs per SM at 168 registers: 1.870 ms), error 2.3e-7.
+        if (p.mixed) return launch_chain_ttt<NT, IO, HORNER, 2, true, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+    }
     if (plan.ctas_per_sm == 3) return launch_chain_ttt<NT, IO, HORNER, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     if constexpr (NT == 2 && HORNER == 3) {
         // complex products from three real ones: measured at C2 2.285 -> 2.149 ms per 5e5 steps, same error (2.65e-8)

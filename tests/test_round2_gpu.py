@@ -271,11 +271,47 @@ def test_tf32_path_is_selected_by_step_count(pb):
     with pb.Parament("fp32") as ctx:
         ctx.set_hamiltonian(w2.H0, *w2.H1, quadrature_mode="simpson")
         ctx.equiprop(w2.dt, *w2.carr)
-        assert ctx.stat(15) == 0
+        assert ctx.stat(15) == 2          # dim 9..16: mixed FP64 + TF32 (test_mixed_precision_dim16)
     w1 = make_workload("C1", pts=1001)
     with pb.Parament("fp64") as ctx:
         ctx.set_hamiltonian(w1.H0, *w1.H1, quadrature_mode="midpoint")
         ctx.equiprop(w1.dt, *w1.carr)
+        assert ctx.stat(15) == 0
+
+
+def test_mixed_precision_dim16(pb, monkeypatch):
+    """complex64, dim 9..16, degree-8 form: X^2, the low-order terms and the running product in FP64, the two small series
+    products as 3xTF32 (Parament_lastStat 15 == 2).  Must meet the tolerance wherever it is selected, agree with the all-FP64
+    kernel, cover complex amplitudes / Magnus / ragged dims, and give way to FP64 beyond the accumulated-phase bound."""
+    rng = np.random.default_rng(21)
+    for n, A, quad, mag, cplx_amp, pts in [(16, 2, "simpson", False, False, 20001), (16, 3, "none", False, True, 3000), (11, 2, "simpson", True, False, 801),
+                                            (9, 1, "midpoint", False, True, 77), (16, 2, "none", False, False, 1)]:
+        H0 = (0.5 * rand_herm(rng, n)).astype(np.complex64)
+        H1 = np.stack([(0.5 / A * rand_herm(rng, n)).astype(np.complex64) for _ in range(A)])
+        carr = (rng.uniform(-1, 1, (A, pts)) + (1j * rng.uniform(-1, 1, (A, pts)) if cplx_amp else 0)).astype(np.complex64)
+        dt = 0.2 if quad in ("none", "midpoint") else 0.1
+        res = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("PARAMENT_K1_MIXED", mode)
+            with pb.Parament("fp32") as ctx:
+                ctx.set_hamiltonian(H0, *H1, use_magnus=mag, quadrature_mode=quad)
+                res[mode] = ctx.equiprop(dt, *carr)
+                assert ctx.stat(15) == (2 if mode == "1" else 0) and ctx.stat(9) == 3
+        Uo = equiprop_oracle(H0, H1, carr, dt, quad, mag, "fp32")
+        assert rel_frobenius(res["1"], Uo) < 2e-6 and rel_frobenius(res["0"], Uo) < 2e-6, (n, quad, mag)
+        assert rel_frobenius(res["1"], res["0"]) < 1e-6
+    monkeypatch.delenv("PARAMENT_K1_MIXED")
+    w = make_workload("C2", pts=4001)
+    with pb.Parament("fp32") as ctx:
+        ctx.set_hamiltonian(w.H0, *w.H1, quadrature_mode="simpson")
+        ctx.equiprop(w.dt, *w.carr)
+        assert ctx.stat(15) == 2
+        with pytest.raises(RuntimeError, match="Timestep too large"):
+            ctx.equiprop(4000.0 * w.dt, *w.carr[:, :5])    # x = 800: far beyond the tables -> error 70 before any selection
+    with pb.Parament("fp32") as ctx:                        # a slice of a very long pulse: the phase of the WHOLE pulse decides
+        ctx.set_hamiltonian(w.H0, *w.H1, quadrature_mode="simpson")
+        long = np.ascontiguousarray(np.tile(w.carr, (1, 4000))[:, :16000001])
+        ctx.equiprop_slice(w.dt, long, 0, 2000)
         assert ctx.stat(15) == 0
 
 
