@@ -199,6 +199,9 @@ class Ours:
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         os.environ["PARAMENT_DEVICE"] = str(self.local_rank)
+        if self.world > 1 and "PARAMENT_STAGE_THREADS" not in os.environ:
+            # the library stages pageable host buffers with up to six copying threads per context; N ranks share the box's cores
+            os.environ["PARAMENT_STAGE_THREADS"] = str(max(1, min(6, (os.cpu_count() or 8) // (2 * self.world))))
         import parament_b200 as pb
         from parament_b200 import constants as K
         self.pb, self.K, self.lib = pb, K, pb._lib.lib
