@@ -26,9 +26,9 @@ namespace pb {
 
 // Per-phase cycle counters (development aid, -DPB_PHASE_TIMING): warp 0 of block 0 prints its accumulated clock64() deltas.
 #ifdef PB_PHASE_TIMING
-#define K1_T_DECL long long pt_[6] = {0, 0, 0, 0, 0, 0}; long long pt_last_ = clock64();
+#define K1_T_DECL long long pt_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pt_last_ = clock64();
 #define K1_T(i) { const long long pt_now_ = clock64(); pt_[i] += pt_now_ - pt_last_; pt_last_ = pt_now_; }
-#define K1_T_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("k1 phase cycles: assemble %lld  square %lld  horner %lld  chain %lld  other %lld  steps %llu\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], hi - lo);
+#define K1_T_PRINT if (blockIdx.x == 0 && threadIdx.x == 0) printf("k1 phase cycles: assemble %lld  square %lld  horner %lld  chain %lld  other %lld  | mixed: S+convert+T %lld  W layout %lld  y02 %lld  R,L' %lld  steps %llu\n", pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[5], pt_[6], pt_[7], pt_[8], hi - lo);
 #else
 #define K1_T_DECL
 #define K1_T(i)
@@ -237,6 +237,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                     AccFrag<NT> Wa;
                     set_zero<NT>(Wa);
                     cmma3<NT>(Wa, Ya, Yb);                  // W = X X in FP64
+                    K1_T(1)
                     FAcc2 Xf, Wf;
 #pragma unroll
                     for (int mt = 0; mt < NT; ++mt)
@@ -256,10 +257,13 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                         (&Tf.re[0][0][0])[e] = fmaf(-c3h, (&Xf.im[0][0][0])[e], fmaf(-c3l, (&Xf.im[0][0][0])[e], c4f * (&Wf.re[0][0][0])[e]));
                         (&Tf.im[0][0][0])[e] = fmaf(c3h, (&Xf.re[0][0][0])[e], fmaf(c3l, (&Xf.re[0][0][0])[e], c4f * (&Wf.im[0][0][0])[e]));
                     }
+                    K1_T(5)
                     FB2 Wbf;
                     facc_to_fb(Wbf, Wf, lane);
+                    K1_T(6)
                     FAcc2 Y2f;
                     tf32_cmul16(Y2f, Tf, Wbf);              // y02 = T W
+                    K1_T(7)
                     FB2 Rbf;                                // R = y02 - e2 W, right-operand layout
                     facc_to_fb(Rbf, Y2f, lane);
 #pragma unroll
@@ -273,6 +277,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                         (&Lf.re[0][0][0])[e] = fmaf(d1h, (&Xf.im[0][0][0])[e], fmaf(d1l, (&Xf.im[0][0][0])[e], fmaf(-d2f, (&Wf.re[0][0][0])[e], (&Y2f.re[0][0][0])[e])));
                         (&Lf.im[0][0][0])[e] = fmaf(-d1h, (&Xf.re[0][0][0])[e], fmaf(-d1l, (&Xf.re[0][0][0])[e], fmaf(-d2f, (&Wf.im[0][0][0])[e], (&Y2f.im[0][0][0])[e])));
                     }
+                    K1_T(8)
                     FAcc2 LRf;
                     tf32_cmul16(LRf, Lf, Rbf);              // L' R
 #pragma unroll
