@@ -608,13 +608,16 @@ bool tf32_candidate(const Context *c, unsigned long long total_steps, double h) 
 // measured 2.3e-7 at C2 (5e5 steps, accumulated phase N h rho = 4e4), linear in the phase, so the path is
 // taken while the phase is below 5e5 (predicted error 2.9e-6); $PARAMENT_K1_MIXED=0 / 1 forces the choice (read per call).
 constexpr double kMixedMaxPhase = 5.0e5;
-bool use_mixed_path(const Context *c, const SeriesParams &p, unsigned long long total_steps, double h) {
-    if (c->fp64 || c->family != 1 || c->npad != 16 || p.horner != 3) return false;
+bool mixed_candidate(const Context *c, unsigned long long total_steps, double h) {
+    if (c->fp64 || c->family != 1 || c->npad != 16) return false;
     if (const char *e = getenv("PARAMENT_K1_MIXED")) return atoi(e) == 1;
     double rho = 0.0;
     for (double sg : c->sigma_max) rho += sg;
     if (!(rho > 0.0) || rho > c->Hnorm) rho = c->Hnorm;
     return (double)total_steps * std::fabs(h) * rho <= kMixedMaxPhase;
+}
+bool use_mixed_path(const Context *c, const SeriesParams &p, unsigned long long total_steps, double h) {
+    return p.horner == 3 && mixed_candidate(c, total_steps, h);   // the kernel implements the three-product degree-8 form only
 }
 bool use_tf32_path(const Context *c, const SeriesParams &p, const CallSpec &s) {
     const double h = (c->enable_magnus || c->quadrature == PARAMENT_QUADRATURE_SIMPSON) ? 2.0 * s.dt : s.dt;
@@ -630,9 +633,11 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     c->stat_series_norm = Hs;
     // Degrees 6..8 are evaluated as ONE degree-8 polynomial in three matrix products (below); the Y^2 Horner form needs four
     // for degree 6 or 7.  The register-resident family does so for complex64 contexts (its path has no compensated constants).
-    // (The TF32 kernel of short complex64 pulses implements that form only; degrees 4 and 5 cost three products as well.)
+    // (The TF32 and mixed-precision kernels of complex64 contexts implement that form only; degrees 4 and 5 cost three products
+    // as well.)
+    const bool fp32_grade = tf32_candidate(c, s.total_steps, h) || mixed_candidate(c, s.total_steps, h);
     const bool want_s8 = (c->family != 1 || !c->fp64) && !c->MMAX_manual && c->series_mode == 0 &&
-                         M_used >= (tf32_candidate(c, s.total_steps, h) ? 4 : 6) && M_used <= 8 && Hs * std::fabs(h) <= 1.0;
+                         M_used >= (fp32_grade ? 4 : 6) && M_used <= 8 && Hs * std::fabs(h) <= 1.0;
     if (want_s8) M_used = 8;
     // degrees 9..12 as ONE degree-12 polynomial in four matrix products
     const bool want_s12 = !c->MMAX_manual && c->series_mode == 0 && M_used >= 9 && M_used <= 12 &&
