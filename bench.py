@@ -201,7 +201,7 @@ class Ours:
         os.environ["PARAMENT_DEVICE"] = str(self.local_rank)
         if self.world > 1 and "PARAMENT_STAGE_THREADS" not in os.environ:
             # the library stages pageable host buffers with up to six copying threads per context; N ranks share the box's cores
-            os.environ["PARAMENT_STAGE_THREADS"] = str(max(1, min(6, (os.cpu_count() or 8) // (2 * self.world))))
+            os.environ["PARAMENT_STAGE_THREADS"] = str(max(2, min(6, (os.cpu_count() or 8) // self.world)))
         import parament_b200 as pb
         from parament_b200 import constants as K
         self.pb, self.K, self.lib = pb, K, pb._lib.lib
