@@ -226,7 +226,7 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  * chain kernel for dim 17..64; PARAMENT_DEVICE the default CUDA device; PARAMENT_F3_STREAMS=1..4 the chunks in flight for dim > 64
  * (default 4); PARAMENT_K1_3M=0 the four-real-product chain kernel at dim 9..16 (read once per process); PARAMENT_K4_3M=0..3 the complex product of the batched GEMM (0: four real products on 64x64 tiles; 3, default: three real
  * products on 64x32 tiles); PARAMENT_K4_FEED=tma the bulk-copy (TMA engine) operand feed of that GEMM in mode 0 (measured slower than cp.async);
- * PARAMENT_COPY_GROUPS=1..8 the copy/compute groups of the host-pointer pipeline; PARAMENT_NORM=reference builds the series for
+ * PARAMENT_COPY_GROUPS=1..8 the copy/compute groups of the host-pointer pipeline (default: up to six, sizes doubling); PARAMENT_NORM=reference builds the series for
  * Hnorm at every dimension (A/B of the spectral bound); PARAMENT_C64_MATH=f64|tf32 forces the arithmetic of complex64 contexts with
  * dim <= 8 (default: by step count, key 15), PARAMENT_TF32_MAX_PHASE moves that bound (both read per call), PARAMENT_TF32_COMP=1
  * switches the compensated running product of the TF32 kernel on (read once per process; measured without effect).

@@ -1072,7 +1072,7 @@ Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const Call
 // caller buffers, small transfers, and $PARAMENT_STAGE_THREADS=0 use the plain asynchronous copy.
 bool h2d_rows(Context *c, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, cudaStream_t stream) {
     const size_t total = width * rows;
-    static const size_t min_bytes = getenv("PARAMENT_STAGE_MIN_MB") ? (size_t)atoi(getenv("PARAMENT_STAGE_MIN_MB")) << 20 : (size_t)4 << 20;
+    static const size_t min_bytes = getenv("PARAMENT_STAGE_MIN_KB") ? (size_t)atoi(getenv("PARAMENT_STAGE_MIN_KB")) << 10 : (size_t)256 << 10;
     bool staged = total >= min_bytes && !c->stager_failed;
     if (staged) {
         cudaPointerAttributes attr{};
@@ -1272,8 +1272,8 @@ Parament_ErrorCode equiprop_host(Context *c, const T *carr, double dt, unsigned 
     const size_t in_bytes = arrays * seg * sizeof(T);
     const size_t out_bytes = (size_t)batch * n * n * sizeof(T);
     if (!ensure_dev(c->d_carr, in_bytes) || (!out_is_device && !ensure_dev(c->d_out, out_bytes))) return fail(c, PARAMENT_STATUS_DEVICE_ALLOC_FAILED);
-    // groups of >= 4 MB (and >= 16k steps along the time axis) for the copy / compute overlap of the register-resident family
-    int G = (int)std::min<size_t>(8, in_bytes / ((size_t)4 << 20));
+    // up to six groups of doubling size (>= 16k steps each along the time axis) for the copy / compute overlap of the register-resident family
+    int G = (int)std::min<size_t>(6, in_bytes / ((size_t)2 << 20));
     if (const char *e = getenv("PARAMENT_COPY_GROUPS")) G = std::max(1, std::min(8, atoi(e)));   // A/B runs
     if (batch == 1) G = (int)std::min<unsigned long long>(G, s.nsteps / 16384);
     else G = (int)std::min<unsigned int>(G, batch);

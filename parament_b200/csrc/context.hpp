@@ -144,7 +144,11 @@ struct Stager {
     }
     // dst (device) <- src (pageable host), asynchronous on `stream` once this returns; src may be released on return
     bool copy(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
-        const size_t nchunks = (bytes + kSlotBytes - 1) / kSlotBytes;
+        // chunks of 2 MB for long transfers; shorter ones are cut into about eight chunks (>= 128 KB) so that every copying
+        // thread gets a share of them too
+        const size_t chunk = bytes >= 8 * kSlotBytes ? kSlotBytes
+                                                     : std::min(kSlotBytes, std::max<size_t>((size_t)128 << 10, ((bytes / 8 + 65535) >> 16) << 16));
+        const size_t nchunks = (bytes + chunk - 1) / chunk;
         size_t queued = 0, sent = 0;
         const int base = next_slot;
         auto slot_of = [&](size_t i) { return (int)((base + i) % kSlots); };
@@ -159,8 +163,8 @@ struct Stager {
                     if (e != cudaSuccess) return false;
                     ev_used[s] = false;
                 }
-                tasks[s].src = (const char *)src + queued * kSlotBytes;
-                tasks[s].bytes = std::min(kSlotBytes, bytes - queued * kSlotBytes);
+                tasks[s].src = (const char *)src + queued * chunk;
+                tasks[s].bytes = std::min(chunk, bytes - queued * chunk);
                 tasks[s].state = 1;
                 queue.push_back(s);
                 ++queued;
@@ -172,7 +176,7 @@ struct Stager {
             tasks[s].state = 0;
             const size_t n = tasks[s].bytes;
             lk.unlock();
-            const bool ok = cudaMemcpyAsync((char *)dst + sent * kSlotBytes, slots[s], n, cudaMemcpyHostToDevice, stream) == cudaSuccess &&
+            const bool ok = cudaMemcpyAsync((char *)dst + sent * chunk, slots[s], n, cudaMemcpyHostToDevice, stream) == cudaSuccess &&
                             cudaEventRecord(ev[s], stream) == cudaSuccess;
             lk.lock();
             if (!ok) return false;

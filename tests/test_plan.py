@@ -96,13 +96,13 @@ def test_ensemble_copy_groups(plan):
 
 
 def test_time_copy_groups(plan):
-    b = plan("tgroups", 499999, 8)
-    assert b[0] == 0 and b[-1] == 499999 and len(b) == 9
-    assert b[1] == 499999 // 32                               # the first copy is the only exposed one: a quarter share
+    b = plan("tgroups", 499999, 6)
+    assert b[0] == 0 and b[-1] == 499999 and len(b) == 7
     sizes = [y - x for x, y in zip(b, b[1:])]
-    assert max(sizes[1:]) - min(sizes[1:]) <= 1
+    assert sizes[0] == 499999 // 63                           # the first copy is the only exposed one: 1 / (2^G - 1) of the pulse
+    assert all(abs(y - 2 * x) <= 2 for x, y in zip(sizes, sizes[1:]))      # every group twice the one before
     assert plan("tgroups", 1000, 1) == [0, 1000]
-    assert plan("tgroups", 40000, 2) == [0, 5000, 40000]
+    assert plan("tgroups", 40000, 2) == [0, 13333, 40000]
 
 
 @pytest.mark.parametrize("configured,batch,nsteps,npad,expect", [
