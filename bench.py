@@ -547,7 +547,7 @@ def pin_numpy(a):
     return out            # never freed: the process ends after the measurement
 
 
-def reference_record(name, steps, warmup, lib):
+def reference_record(name, steps, warmup, lib, mode="strong"):
     """One configuration on the reference's CUDA build through its C API; (None, workload) if it cannot hold the configuration."""
     from workloads import make_workload
     w = make_workload(name)
@@ -587,7 +587,7 @@ def reference_record(name, steps, warmup, lib):
     value = w.steps * nb / sec
     rec = {"value": value, "unit": "steps/s", "ms_per_step": sec * 1e3, "steps": steps, "warmup": warmup, "scaling": "strong",
            "dtype": "c64" if not fp64 else "c128",
-           "config": workload_config(name, w, 1, "strong", "host buffers: every call copies its inputs from host memory"),
+           "config": workload_config(name, w, 1, mode, "host buffers: every call copies its inputs from host memory"),
            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": 1, "kind": "reference",
                             "sample": f"reference CUDA build (cuBLAS batched, compiled from /root/reference for sm_100) on GPU 0 through "
                                       f"its C API, {nb} pulse(s) of {w.pts} points per step, pageable host arrays; the reference has "
@@ -617,7 +617,7 @@ def run_reference(args):
                 lib = None
         except OSError:
             lib = None
-    top, w = reference_record(args.config, args.steps, args.warmup, lib)
+    top, w = reference_record(args.config, args.steps, args.warmup, lib, mode="weak")   # same `config` text as our top-level record
     if top is None:
         # no usable reference CUDA build for this configuration: time the CPU oracle port on a bounded sample
         cb = cpu_baseline(w)
