@@ -1,7 +1,7 @@
 // k1_tf32.cu -- complex64 contexts, dim <= 8, short pulses: kernel (1) in FP32 arithmetic on the TF32 tensor path.
 //
 // The north_star asks for the complex64 branch to run below FP64 cost where the tolerance allows it.  Over the 5e5 steps
-// of C2 no fp32 scheme holds 1e-5 (profiles/error_growth_r2.md), but a GRAPE ensemble (C5) propagates 1e3 steps per pulse,
+// of C2 no all-fp32 scheme holds 1e-5 (profiles/error_growth_tf32_r2.md: 1e-3 at 1e6 steps), but a GRAPE ensemble (C5) propagates 1e3 steps per pulse,
 // and there the same three-product degree-8 evaluation as k1_warp.cu runs with
 //   * every matrix product as a 3xTF32 split on the warp-level tensor path (mma.sync.m16n8k8.tf32, SASS HMMA.1688.F32.TF32;
 //     measured 278 TFLOP/s on B200 = 92 TFLOP/s of fp32-grade products against 37 TFLOP/s of DMMA and 69 of FFMA):
@@ -15,10 +15,12 @@
 //     permutation.  The running product Q <- Q + Q E^T therefore needs no data movement; the two right operands of the
 //     series that are not transposes come from a 4-shuffle transposition;
 //   * the low-order constants of the polynomial (r_0, r_1, r_2) carried as hi + lo pairs (their fp32 rounding would be a
-//     coherent per-step error), and the running product kept as a compensated pair Q_hi + Q_lo (TwoSum), so what is left is
-//     the pseudo-random rounding of the products themselves (error ~ sqrt(N)).
-// The host (api.cu use_tf32_path) selects this kernel only for complex64 contexts with dim <= 8, the degree-8 form and at
-// most kTf32MaxSteps effective steps per pulse -- the bound comes from the measured error curve, not from an argument.
+//     coherent per-step error), every MMA started from a zero accumulator (the tensor core's truncating accumulation is a
+//     coherent error too, proportional to the accumulator's magnitude), and optionally the running product kept as a
+//     compensated pair Q_hi + Q_lo (TwoSum; measured without further effect, off by default).
+// The host (api.cu tf32_candidate / use_tf32_path) selects this kernel only for complex64 contexts with dim <= 8, the degree-8
+// form and an accumulated phase N h rho <= 128 -- the bound comes from the measured error law (linear in that phase), not from
+// an argument.
 // The warp's product is handed over in double (Q_hi + Q_lo); products across warps and CTAs and the fused final stage are the
 // FP64 kernel's (k1_common.cuh).
 #include <cstdlib>

@@ -2,14 +2,20 @@
 //
 //  k1_chain_kernel   one warp walks a contiguous chunk of effective time steps.  Per step it assembles
 //                    Y = sigma * (H0 + sum_t c_t H_t) from the raw amplitude stream (quadrature / Magnus
-//                    coefficients evaluated on the fly, coef.cuh), runs the Chebyshev/Bessel series by the
-//                    Clenshaw recurrence  B_k = B_{k+1} Y - B_{k+2} + a_k I  with every matrix product on
-//                    the FP64 tensor pipe (frag.cuh: no shared memory, no shuffles, nothing written to
-//                    HBM), and multiplies the step into the warp's running product.            [kernel 1]
-//                    The warps of a CTA then combine their chunk products in order through shared memory
-//                    and write ONE partial propagator per CTA.                                  [kernel 2]
-//  k3_reduce_kernel  ordered reduction of the per-CTA partials of each pulse, transposition to the
-//                    row-major physical propagator and conversion to the context precision.    [kernel 3]
+//                    coefficients evaluated on the fly, coef.cuh), evaluates the Chebyshev/Bessel series -- as a
+//                    degree-8 / degree-12 polynomial in three / four matrix products, by Horner in Y^2, or by the
+//                    reference's Clenshaw recurrence -- with every matrix product on the FP64 tensor pipe
+//                    (frag.cuh: no shared memory, nothing written to HBM; complex products from three real ones
+//                    in the degree-8 form), and multiplies the step into the warp's running product.   [kernel 1]
+//                    MIXED (complex64, dim 9..16): the two small products of the degree-8 form run at fp32 grade
+//                    as 3xTF32 on the other tensor sub-pipe (frag_tf32.cuh).
+//                    The warps of a CTA then combine their chunk products in order through shared memory; the last
+//                    CTAs to finish reduce the per-CTA partials and write the propagator (k1_common.cuh:
+//                    ONE launch per call), or the partials are left to k3_reduce_kernel.         [kernels 2, 3]
+//  k3_reduce_kernel  ordered reduction of stored partials of each pulse (host-pointer calls whose time axis is cut
+//                    into copy groups), transposition to the row-major physical propagator and conversion to
+//                    the context precision.                                                       [kernel 3]
+//  k3_combine_kernel ordered product of the partial propagators of time slices (multi-GPU), one launch.
 //
 // Replaces parament.cpp:486-718 (equipropExpand / equipropPropagate / equipropReduce) and
 // control_expansion.cu / diagonal_add.cu for these dimensions.  The running product is kept transposed,
