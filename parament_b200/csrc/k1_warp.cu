@@ -505,18 +505,24 @@ static cudaError_t launch_chain_tt(const SeriesParams &p, const IO *carr, const 
     if constexpr (NT == 1 && HORNER == 3) {
         if (k1_mul3()) return launch_chain_ttt<NT, IO, HORNER, 6, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     }
-    if (NT == 1) return launch_chain_ttt<NT, IO, HORNER, 6>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
-    if constexpr (NT == 2 && HORNER == 3 && sizeof(IO) == sizeof(float2)) {
+    if constexpr (NT == 1) {   // `if constexpr` throughout: a plain `if` would instantiate six-CTA variants of NT == 2 (5 KB of spills, never launched)
+        return launch_chain_ttt<NT, IO, HORNER, 6>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+    } else {
+    if constexpr (HORNER == 3 && sizeof(IO) == sizeof(float2)) {
         // mixed precision: the two small products of the series on the TF32 tensor path (api.cu use_mixed_path decides).
         // Measured at C2: 2.149 -> 1.818 ms per 5e5 steps (three CTAs per SM at 168 registers: 1.870 ms), error 2.3e-7.
         if (p.mixed) return launch_chain_ttt<NT, IO, HORNER, 2, true, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     }
-    if (plan.ctas_per_sm == 3) return launch_chain_ttt<NT, IO, HORNER, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
-    if constexpr (NT == 2 && HORNER == 3) {
+    // three CTAs per SM (168 registers): the default of the plain Taylor form; for the degree-8 form only through $PARAMENT_K1_OCC=3.
+    // The Horner forms spill 0.6-2.2 KB at 168 registers and always run two CTAs per SM.
+    if constexpr (HORNER == 0 || HORNER == 3)
+        if (plan.ctas_per_sm == 3) return launch_chain_ttt<NT, IO, HORNER, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+    if constexpr (HORNER == 3) {
         // complex products from three real ones: measured at C2 2.285 -> 2.149 ms per 5e5 steps, same error (2.65e-8)
         if (k1_mul3()) return launch_chain_ttt<NT, IO, HORNER, 2, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     }
     return launch_chain_ttt<NT, IO, HORNER, 2>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+    }
 }
 
 template <int NT, typename IO>
