@@ -290,23 +290,27 @@ bool upload_matrices(Context *c) {
     const int n = c->dim;
     if (c->family == 1) {
         const int NT = c->npad / 8, NE = 2 * NT * NT;
+        const int nb = c->npad / c->pack;   // packed small systems: kron(I_pack, H), one copy of H per diagonal block of nb rows
         std::vector<double2> frag((size_t)c->nmats * 2 * NE * 32, make_double2(0, 0));
         for (int m = 0; m < c->nmats; ++m) {
             const zc *M = c->mats.data() + (size_t)m * n * n;
+            auto at = [&](int r, int col, double2 &dst) {
+                if (r / nb != col / nb) return;
+                const int rr = r % nb, cc = col % nb;
+                if (rr < n && cc < n) dst = make_double2(M[(size_t)rr * n + cc].real(), M[(size_t)rr * n + cc].imag());
+            };
             for (int lane = 0; lane < 32; ++lane) {
                 const int g = lane >> 2, q = lane & 3;
                 for (int mt = 0; mt < NT; ++mt)            // AccFrag order (frag.cuh)
                     for (int nt = 0; nt < NT; ++nt)
                         for (int i = 0; i < 2; ++i) {
                             const int r = 8 * mt + g, col = 8 * nt + 2 * q + i, e = (mt * NT + nt) * 2 + i;
-                            if (r < n && col < n)
-                                frag[(((size_t)m * 2 + 0) * NE + e) * 32 + lane] = make_double2(M[(size_t)r * n + col].real(), M[(size_t)r * n + col].imag());
+                            at(r, col, frag[(((size_t)m * 2 + 0) * NE + e) * 32 + lane]);
                         }
                 for (int kt = 0; kt < 2 * NT; ++kt)        // BFrag order
                     for (int nt = 0; nt < NT; ++nt) {
                         const int r = 8 * (kt >> 1) + 2 * q + (kt & 1), col = 8 * nt + g, e = kt * NT + nt;
-                        if (r < n && col < n)
-                            frag[(((size_t)m * 2 + 1) * NE + e) * 32 + lane] = make_double2(M[(size_t)r * n + col].real(), M[(size_t)r * n + col].imag());
+                        at(r, col, frag[(((size_t)m * 2 + 1) * NE + e) * 32 + lane]);
                     }
             }
         }
@@ -388,7 +392,13 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     c->Hnorm = one_norm_t<T>(H0, dim);
     for (int a = 0; a < A; ++a) c->Hnorm += one_norm_t<T>(H1 + (size_t)a * nn, dim);
 
-    if (dim <= 16) { c->family = 1; c->npad = dim <= 8 ? 8 : 16; }
+    c->pack = 1;
+    if (dim <= 16) {
+        c->family = 1; c->npad = dim <= 8 ? 8 : 16;
+        // dim <= 4: two or four systems share the 8 x 8 tensor-pipe tile (k1_warp.cu "Packed small systems")
+        const char *pk = getenv("PARAMENT_K1_PACK");
+        if (dim <= 4 && !(pk && atoi(pk) == 0)) c->pack = dim <= 2 ? 4 : 2;
+    }
     else if (dim <= 64) {
         c->family = 2; c->npad = k4_pad((int)dim);
         const int oc = !getenv("PARAMENT_NO_ONCHIP") ? k4_onchip_slots(c->npad, c->num_sms) : 0;
@@ -597,6 +607,7 @@ bool tf32_candidate(const Context *c, unsigned long long total_steps, double h) 
     const double max_phase = ep ? atof(ep) : kTf32MaxPhase;
     if (mode == 1) return false;
     if (mode == 2) return true;
+    if (c->pack > 1) return false;   // dim <= 4: the packed FP64 kernel does 2-4 steps per tile pass, more than 3xTF32 gains (and is exact to 1e-12)
     double rho = 0.0;
     for (double sg : c->sigma_max) rho += sg;
     if (!(rho > 0.0) || rho > c->Hnorm) rho = c->Hnorm;
@@ -649,6 +660,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     memset(&p, 0, sizeof(p));
     p.n = c->dim;
     p.npad = c->npad;
+    p.pack = c->pack;
     p.quad = c->enable_magnus ? QUAD_SIMPSON
              : (c->quadrature == PARAMENT_QUADRATURE_SIMPSON ? QUAD_SIMPSON
                 : (c->quadrature == PARAMENT_QUADRATURE_MIDPOINT ? QUAD_MIDPOINT : QUAD_NONE));

@@ -34,6 +34,41 @@ __device__ __forceinline__ void cta_ordered_product(AccFrag<NT> &Q, double2 *sme
 }
 
 // out (n x n row-major, IO precision) = Q^T: the running products are kept transposed (frag.cuh).
+// Packed small systems (k1_warp.cu, p.pack = 4 or 2): Q = diag(Q_0 .. Q_{pack-1}) with nb = 8 / pack rows per block, block b holding
+// the (transposed) product of the b-th part of the warp's step range.  Returns diag(Q_0 Q_1 ... Q_{pack-1}, I): the warp's
+// product in the layout every later stage expects.  log2(pack) products  Q <- Q * shift(Q)  where shift moves block b + s to
+// block b (a lane permutation of the accumulator layout: row g + s nb, column pair q + s nb / 2, same register).
+template <int NT>
+__device__ __forceinline__ void unpack_blocks(AccFrag<NT> &Q, int pack, int lane) {
+    static_assert(NT == 1, "block packing is a dim <= 4 (one 8 x 8 tile) feature");
+    const int g = lane >> 2, q = lane & 3, nb = 8 / pack;
+    for (int sh = nb; sh < 8; sh *= 2) {
+        const int src = 4 * ((g + sh) & 7) + ((q + (sh >> 1)) & 3);
+        AccFrag<NT> S;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            S.re[0][0][i] = __shfl_sync(0xffffffffu, Q.re[0][0][i], src);
+            S.im[0][0][i] = __shfl_sync(0xffffffffu, Q.im[0][0][i], src);
+        }
+        BFrag<NT> Sb;
+        acc_to_bfrag<NT>(Sb, S, lane);
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) Sb.nim[kt][0] = neg(Sb.im[kt][0]);
+        AccFrag<NT> R;
+        set_zero<NT>(R);
+        cmma<NT>(R, Q, Sb);
+        Q = R;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int col = 2 * q + i;
+        if (g >= nb || col >= nb) {
+            Q.re[0][0][i] = (g == col) ? 1.0 : 0.0;
+            Q.im[0][0][i] = 0.0;
+        }
+    }
+}
+
 template <int NT, typename IO>
 __device__ __forceinline__ void store_propagator(const AccFrag<NT> &Q, IO *__restrict__ o, int n, int lane) {
 #pragma unroll

@@ -115,8 +115,24 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
             }
         };
 
+        // Packed small systems (dim <= 4, p.pack = 4 or 2; api.cu upload_matrices stores kron(I_pack, H)): the 8 x 8 tile carries
+        // `pack` diagonal blocks of nb = 8 / pack rows, and block b advances through the b-th quarter (half) of the warp's step
+        // range -- every element a lane holds in any of the three register layouts lies in block (lane >> 2) / nb, so the time
+        // index simply becomes lane-dependent.  Everything between the assembly and the running product is a polynomial in X
+        // plus multiples of I, which keeps the blocks apart; a block that runs out of steps early gets E = 0 (its lanes hold all of it).
+        const int pack = NT == 1 ? p.pack : 1;
+        unsigned long long jb = lo, hb = hi, iters = hi - lo;
+        if (NT == 1 && pack > 1) {
+            const unsigned long long L = hi - lo;
+            const unsigned int blk = (unsigned int)(lane >> 2) / (unsigned int)(8 / pack);
+            jb = lo + L * blk / pack;
+            hb = lo + L * (blk + 1) / pack;
+            iters = (L + pack - 1) / pack;
+        }
         K1_T_DECL
-        for (unsigned long long j = lo; j < hi; ++j) {
+        for (unsigned long long it = 0; it < iters; ++it, ++jb) {
+            const bool live = jb < hb;
+            const unsigned long long j = live ? jb : hi - 1;
             K1_T(4)
             // ---- assemble X = H0 + sum_t c_t H_t in both register layouts, then Y = sigma X ----
             AccFrag<NT> Ya;
@@ -397,6 +413,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
 #pragma unroll
             for (int t = 0; t < KPRE; ++t)
                 if (t < p.nterms) raw[t] = load_raw<IO, false>(p.terms[t], c, p.pts, p.quad, jn);
+            if (NT == 1 && pack > 1 && !live) set_zero<NT>(S1);   // this block has run out of steps: E = 0 exactly, Q_b stays
             BFrag<NT> Et;
             transpose_as_bfrag<NT>(Et, S1);
             AccFrag<NT> Qn = Q;
@@ -414,6 +431,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
             K1_T(3)
         }
         K1_T_PRINT
+        if constexpr (NT == 1) { if (pack > 1) unpack_blocks<NT>(Q, pack, lane); }
     }
 
     k1_tail<NT, IO>(Q, active, pulse, chunk, chunks_per_pulse, reduce_in_cta, partials, fz, smem, warp, lane);

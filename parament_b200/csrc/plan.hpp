@@ -71,7 +71,9 @@ inline K1Plan plan_k1(int npad, unsigned int batch, unsigned long long nsteps, i
         const unsigned long long rounds = waves_env >= 1 && waves_env <= 16 ? waves_env : 1;
         unsigned long long ctas_per_pulse = (rounds * (warps_total / K1_WARPS) + batch - 1) / batch;
         // keep at least ~8 steps per warp so the identity-start product stays a small fraction
-        const unsigned long long max_ctas = (nsteps / 8 + K1_WARPS - 1) / K1_WARPS;
+        static const int min_env = getenv("PARAMENT_K1_MIN_STEPS") ? atoi(getenv("PARAMENT_K1_MIN_STEPS")) : 0;   // A/B runs
+        const unsigned long long min_steps = min_env >= 1 && min_env <= 64 ? min_env : 8;
+        const unsigned long long max_ctas = (nsteps / min_steps + K1_WARPS - 1) / K1_WARPS;
         if (ctas_per_pulse > max_ctas) ctas_per_pulse = max_ctas;
         if (ctas_per_pulse < 1) ctas_per_pulse = 1;
         plan.chunks_per_pulse = (unsigned int)(ctas_per_pulse * K1_WARPS);

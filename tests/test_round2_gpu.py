@@ -335,3 +335,69 @@ def test_pageable_staging_matches_page_locked_input(pb):
         assert np.array_equal(a, b) and np.array_equal(a, a2)
         Uo = equiprop_oracle(w.H0, w.H1, carr[0], w.dt, w.quadrature, w.use_magnus, w.precision, workers=8)
         assert rel_frobenius(a[0], Uo) < TOL[w.precision]
+
+
+# ---- packed small systems (dim <= 4: two or four systems per 8 x 8 tensor-pipe tile, k1_warp.cu) -------------------------
+def _small_system(rng, dim, A, prec, complex_amps, pts, batch):
+    ct = np.complex64 if prec == "fp32" else np.complex128
+    H0 = (0.7 * rand_herm(rng, dim)).astype(ct)
+    H1 = np.stack([(0.4 * rand_herm(rng, dim)).astype(ct) for _ in range(A)])
+    carr = rng.uniform(-1, 1, (batch, A, pts))
+    if complex_amps:
+        carr = carr + 1j * rng.uniform(-1, 1, (batch, A, pts))
+    return H0, H1, carr.astype(ct)
+
+
+@pytest.mark.parametrize("pts", [1, 2, 3, 4, 5, 7, 9, 64, 1001, 20000])
+@pytest.mark.parametrize("dim,A,prec,quad,mag,complex_amps", [
+    (2, 1, "fp64", "none", False, False), (2, 2, "fp64", "simpson", True, False), (2, 1, "fp32", "midpoint", False, True),
+    (1, 1, "fp64", "none", False, False), (3, 2, "fp64", "midpoint", False, True), (3, 1, "fp32", "none", False, False),
+    (4, 2, "fp64", "simpson", False, False), (4, 3, "fp32", "simpson", True, True), (4, 1, "fp64", "none", False, False)])
+def test_packed_small_systems_single_pulse(pb, dim, A, prec, quad, mag, complex_amps, pts):
+    """Every length around the pack factor (blocks that run out of steps early), all quadratures, Magnus, complex amplitudes."""
+    if quad == "simpson" and pts < 3:
+        pts = 3
+    if quad == "simpson" and pts % 2 == 0:
+        pts += 1
+    if quad == "midpoint" and pts < 2:
+        pts = 2
+    rng = np.random.default_rng(1000 * dim + pts)
+    H0, H1, carr = _small_system(rng, dim, A, prec, complex_amps, pts, 1)
+    dt = 0.05
+    with pb.Parament(prec) as ctx:
+        ctx.set_hamiltonian(H0, *H1, use_magnus=mag, quadrature_mode=quad)
+        U = ctx.equiprop(dt, *carr[0])
+        assert ctx.stat(5) == 1
+    assert rel_frobenius(U, equiprop_oracle(H0, H1, carr[0], dt, quad, mag, prec)) < TOL[prec]
+
+
+@pytest.mark.parametrize("dim,prec,batch,pts", [(2, "fp64", 5, 33), (2, "fp32", 9000, 17), (4, "fp64", 7000, 10), (3, "fp32", 300, 201),
+                                                (4, "fp32", 2, 5000), (2, "fp64", 40000, 3)])
+def test_packed_small_systems_ensembles(pb, dim, prec, batch, pts):
+    """Ensembles in both plans (a warp owns a pulse or a part of it; few long pulses spread over CTAs)."""
+    rng = np.random.default_rng(77 + dim + batch)
+    H0, H1, carr = _small_system(rng, dim, 2, prec, False, pts, batch)
+    dt = 0.04
+    with pb.Parament(prec) as ctx:
+        ctx.set_hamiltonian(H0, *H1, quadrature_mode="none")
+        U = ctx.equiprop_batch(dt, carr)
+    for b in sorted(set([0, 1, batch // 2, batch - 1])):
+        assert rel_frobenius(U[b], equiprop_oracle(H0, H1, carr[b], dt, "none", False, prec)) < TOL[prec], b
+    if batch > 100:   # all pulses, against the first one's error scale: nothing is mixed up between blocks or pulses
+        Us = np.stack([equiprop_oracle(H0, H1, carr[b], dt, "none", False, prec) for b in range(0, batch, max(1, batch // 64))])
+        got = U[::max(1, batch // 64)]
+        assert max(rel_frobenius(g, u) for g, u in zip(got, Us)) < TOL[prec]
+
+
+def test_packing_switch_gives_the_same_propagator(pb, monkeypatch):
+    """PARAMENT_K1_PACK=0 (one system per tile, as for dim 5..8) and the packed kernel agree to rounding."""
+    rng = np.random.default_rng(5)
+    H0, H1, carr = _small_system(rng, 2, 2, "fp64", False, 4097, 1)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PARAMENT_K1_PACK", mode)
+        with pb.Parament("fp64") as ctx:
+            ctx.set_hamiltonian(H0, *H1, quadrature_mode="midpoint")
+            res[mode] = ctx.equiprop(0.02, *carr[0])
+    assert rel_frobenius(res["1"], res["0"]) < 1e-13
+    assert rel_frobenius(res["1"], equiprop_oracle(H0, H1, carr[0], 0.02, "midpoint", False, "fp64")) < 1e-12
