@@ -229,7 +229,11 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  * PARAMENT_COPY_GROUPS=1..8 the copy/compute groups of the host-pointer pipeline (default: up to six, sizes doubling); PARAMENT_NORM=reference builds the series for
  * Hnorm at every dimension (A/B of the spectral bound); PARAMENT_C64_MATH=f64|tf32 forces the arithmetic of complex64 contexts with
  * dim <= 8 (default: by step count, key 15), PARAMENT_TF32_MAX_PHASE moves that bound (both read per call), PARAMENT_TF32_COMP=1
- * switches the compensated running product of the TF32 kernel on (read once per process; measured without effect).
+ * switches the compensated running product of the TF32 kernel on (read once per process; measured without effect);
+ * PARAMENT_K1_PACK=0 (read at Parament_setHamiltonian) keeps one system per 8 x 8 tensor-pipe tile at dim <= 4 (default: four
+ * systems of dim <= 2 or two of dim 3..4 share the tile, each advancing through its own part of the step range; with it complex64
+ * contexts of dim <= 4 compute in double precision, key 15 = 0); PARAMENT_K1_MIN_STEPS=1..64 the fewest steps per warp of a short
+ * single pulse (default 8).
  * Limits: at most 64 effective control terms per step (controls + Magnus commutators: amps <= 64 without Magnus, amps <= 9
  * with it); Parament_setHamiltonian returns PARAMENT_STATUS_INVALID_VALUE beyond that (the reference has no stated limit but
  * its launch configurations break at amps > 16 with Magnus, control_expansion.cu:179).
