@@ -401,3 +401,18 @@ def test_packing_switch_gives_the_same_propagator(pb, monkeypatch):
             res[mode] = ctx.equiprop(0.02, *carr[0])
     assert rel_frobenius(res["1"], res["0"]) < 1e-13
     assert rel_frobenius(res["1"], equiprop_oracle(H0, H1, carr[0], 0.02, "midpoint", False, "fp64")) < 1e-12
+
+
+@pytest.mark.parametrize("dim,prec,quad", [(2, "fp64", "simpson"), (4, "fp64", "none"), (2, "fp32", "midpoint")])
+def test_packed_small_systems_long_pulse_host_pipeline(pb, dim, prec, quad):
+    """A pulse long enough for the copy / compute groups of the host-pointer path (several launches of partial products,
+    each unpacked to an ordinary padded partial before the ordered reduction)."""
+    pts = 600_001 if prec == "fp64" else 1_200_001
+    rng = np.random.default_rng(dim)
+    H0, H1, carr = _small_system(rng, dim, 2, prec, False, pts, 1)
+    dt = 0.002
+    with pb.Parament(prec) as ctx:
+        ctx.set_hamiltonian(H0, *H1, quadrature_mode=quad)
+        U = ctx.equiprop(dt, *carr[0])
+        assert ctx.stat(1) >= 3          # copy groups: more than one chain launch + the reduction
+    assert rel_frobenius(U, equiprop_oracle(H0, H1, carr[0], dt, quad, False, prec)) < TOL[prec]
