@@ -233,7 +233,8 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  * PARAMENT_K1_PACK=0 (read at Parament_setHamiltonian) keeps one system per 8 x 8 tensor-pipe tile at dim <= 4 (default: four
  * systems of dim <= 2 or two of dim 3..4 share the tile, each advancing through its own part of the step range; with it complex64
  * contexts of dim <= 4 compute in double precision, key 15 = 0); PARAMENT_K1_MIN_STEPS=1..64 the fewest steps per warp of a short
- * single pulse (default 8).
+ * single pulse (default 8); PARAMENT_K1_HERM=0 (read at Parament_setHamiltonian) ignores that the loaded matrices are Hermitian
+ * (dim 9..16, complex64: a Hermitian step Hamiltonian is its own right operand up to conjugation, which saves a register shuffle).
  * Limits: at most 64 effective control terms per step (controls + Magnus commutators: amps <= 64 without Magnus, amps <= 9
  * with it); Parament_setHamiltonian returns PARAMENT_STATUS_INVALID_VALUE beyond that (the reference has no stated limit but
  * its launch configurations break at amps > 16 with Magnus, control_expansion.cu:179).

@@ -388,6 +388,17 @@ Parament_ErrorCode set_hamiltonian(Context *c, const T *H0, const T *H1, unsigne
     for (int a = 0; a < A; ++a)
         for (size_t e = 0; e < nn; ++e) c->mats[(size_t)(1 + a) * nn + e] = zc((double)H1[(size_t)a * nn + e].re, (double)H1[(size_t)a * nn + e].im);
 
+    {   // exact Hermiticity of every input matrix (k1_warp.cu: the right-operand layout of a Hermitian X needs no shuffles)
+        bool herm = !(getenv("PARAMENT_K1_HERM") && atoi(getenv("PARAMENT_K1_HERM")) == 0);
+        for (int m = 0; m <= A && herm; ++m) {
+            const zc *M = c->mats.data() + (size_t)m * nn;
+            for (unsigned int r = 0; r < dim && herm; ++r)
+                for (unsigned int col = r; col < dim; ++col)
+                    if (M[(size_t)r * dim + col] != std::conj(M[(size_t)col * dim + r])) { herm = false; break; }
+        }
+        c->hermitian = herm;
+    }
+
     // Series norm: sum of the max-row-abs-sums of the buffers as passed (parament.cpp:280-284)
     c->Hnorm = one_norm_t<T>(H0, dim);
     for (int a = 0; a < A; ++a) c->Hnorm += one_norm_t<T>(H1 + (size_t)a * nn, dim);
@@ -661,6 +672,7 @@ Parament_ErrorCode build_series(Context *c, const CallSpec &s, SeriesParams &p) 
     p.n = c->dim;
     p.npad = c->npad;
     p.pack = c->pack;
+    p.herm = (c->hermitian && !c->enable_magnus) ? 1 : 0;
     p.quad = c->enable_magnus ? QUAD_SIMPSON
              : (c->quadrature == PARAMENT_QUADRATURE_SIMPSON ? QUAD_SIMPSON
                 : (c->quadrature == PARAMENT_QUADRATURE_MIDPOINT ? QUAD_MIDPOINT : QUAD_NONE));

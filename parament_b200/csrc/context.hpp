@@ -233,6 +233,7 @@ struct Context {
     std::vector<zc> mats;   // nmats * dim * dim, row-major
     int family = 0;      // 1 = register-resident warp kernels, 2 = persistent CTA chain kernel, 3 = batched GEMM pipeline
     int npad = 0;
+    bool hermitian = false;   // H0 and all H_k equal their conjugate transposes exactly (set_hamiltonian); $PARAMENT_K1_HERM=0 ignores it
     int pack = 1;        // family 1, dim <= 4: systems per 8 x 8 tile (4 for dim <= 2, 2 for dim 3..4), see k1_warp.cu; $PARAMENT_K1_PACK=0 disables
     bool onchip = false; // family 2: operands resident in shared memory (npad == 64)
     int k4_slots = 0;    // co-resident CTAs of the GEMM kernel (family 3)

@@ -132,6 +132,19 @@ __device__ __forceinline__ void transpose_as_bfrag(BFrag<NT> &B, const AccFrag<N
         }
 }
 
+// BFrag of E^H (conjugate transpose) from the registers of AccFrag E: for a Hermitian matrix this IS its own right-operand
+// layout -- no data movement.  B.nim is left to the caller.
+template <int NT>
+__device__ __forceinline__ void conj_transpose_as_bfrag(BFrag<NT> &B, const AccFrag<NT> &E) {
+#pragma unroll
+    for (int kt = 0; kt < 2 * NT; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            B.re[kt][nt] = E.re[nt][kt >> 1][kt & 1];
+            B.im[kt][nt] = neg(E.im[nt][kt >> 1][kt & 1]);
+        }
+}
+
 // BFrag of X from the AccFrag of the SAME matrix X (a change of layout, unlike transpose_as_bfrag) by warp shuffles.
 // Per 8x8 block, B[par](g, q) = X[2q + par][g] is accumulator element i = g & 1 of lane (g' = 2q + par, q' = g >> 1).
 // Two exchange rounds serve both parities: in round 1 the even-g lanes fetch par 0 and the odd-g lanes par 1, so every

@@ -146,12 +146,20 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                     (&Yb.re[0][0])[e] = hb.x;    (&Yb.im[0][0])[e] = hb.y;
                 }
             }
+            // Hermitian H0 / H_k (p.herm, checked on the host) and real coefficients make X Hermitian: its right-operand layout is
+            // then the conjugate of the transpose-as-B-operand relabeling, with no shuffles (HERM_OK forms only)
+            bool xherm = p.herm != 0;
 #pragma unroll
             for (int t = 0; t < KPRE; ++t)
-                if (t < p.nterms) add_term(Ya, Yb, ctn[t], HA + (size_t)p.terms[t].mat * 2 * NE * 32);
-            for (int t = KPRE; t < p.nterms; ++t)
-                add_term(Ya, Yb, step_coefficient<IO, false>(p.terms[t], c, p.pts, p.quad, p.magfac, j),
-                         HA + (size_t)p.terms[t].mat * 2 * NE * 32);
+                if (t < p.nterms) {
+                    xherm = xherm && ctn[t].im == 0.0;
+                    add_term(Ya, Yb, ctn[t], HA + (size_t)p.terms[t].mat * 2 * NE * 32);
+                }
+            for (int t = KPRE; t < p.nterms; ++t) {
+                const cplx ct = step_coefficient<IO, false>(p.terms[t], c, p.pts, p.quad, p.magfac, j);
+                xherm = xherm && ct.im == 0.0;
+                add_term(Ya, Yb, ct, HA + (size_t)p.terms[t].mat * 2 * NE * 32);
+            }
             if (!HORNER) {   // Horner form: sigma is folded into the monomial coefficients on the host, Y == X
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
@@ -253,7 +261,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                     const float c4f = p.fconst[0], d2f = p.fconst[1], c3h = p.fconst[2], c3l = p.fconst[3], d1h = p.fconst[4], d1l = p.fconst[5];
                     const float e2h = p.fconst[6], e2l = p.fconst[7], e0h = p.fconst[8], e0l = p.fconst[9];
                     const double r2full = p.a[9].re;
-                    acc_to_bfrag<NT>(Yb, Ya, lane);
+                    if (xherm) conj_transpose_as_bfrag<NT>(Yb, Ya); else acc_to_bfrag<NT>(Yb, Ya, lane);
 #pragma unroll
                     for (int e = 0; e < NE; ++e) (&Yb.nim[0][0])[e] = (&Yb.re[0][0])[e] + (&Yb.im[0][0])[e];
                     AccFrag<NT> Wa;
@@ -308,7 +316,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                         (&S1.im[0][0][0])[e] += (double)fmaf(e0h, (&Y2f.im[0][0][0])[e], fmaf(e0l, (&Y2f.im[0][0][0])[e], (&LRf.im[0][0][0])[e]));
                     }
                 } else {
-                if (!BOTH) acc_to_bfrag<NT>(Yb, Ya, lane);
+                if (!BOTH) { if (xherm) conj_transpose_as_bfrag<NT>(Yb, Ya); else acc_to_bfrag<NT>(Yb, Ya, lane); }
 #pragma unroll
                 for (int e = 0; e < NE; ++e) (&Yb.nim[0][0])[e] = bfrag_third<MUL3>((&Yb.re[0][0])[e], (&Yb.im[0][0])[e]);
                 AccFrag<NT> Wa;

@@ -38,6 +38,7 @@ struct SeriesParams {
                                  // accumulator is still small, so that the rounding of the series constants does
                                  // not bias every step the same way (DESIGN.md "Numerics")
     int pack;                    // dim <= 4: diagonal blocks of the 8 x 8 tile that advance through different parts of the step range (k1_warp.cu); else 1
+    int herm;                    // H0 and every H_k are exactly Hermitian and no Magnus terms: a step with real coefficients has a Hermitian X
     int mixed;                   // dim 9..16, complex64, degree-8 form: the two small products of the series at fp32 grade (k1_warp.cu MIXED)
     float fconst[16];            // degree-8 form, mixed-precision kernel (k1_warp.cu MIXED): c4, d2, then hi / lo pairs of c3, d1, e2, e0
     Term terms[kMaxTerms];

@@ -416,3 +416,32 @@ def test_packed_small_systems_long_pulse_host_pipeline(pb, dim, prec, quad):
         U = ctx.equiprop(dt, *carr[0])
         assert ctx.stat(1) >= 3          # copy groups: more than one chain launch + the reduction
     assert rel_frobenius(U, equiprop_oracle(H0, H1, carr[0], dt, quad, False, prec)) < TOL[prec]
+
+
+# ---- Hermitian shortcut of the dim 9..16 degree-8 kernels (right-operand layout of X without shuffles) -------------------
+@pytest.mark.parametrize("prec,dim", [("fp32", 16), ("fp32", 11)])
+def test_non_hermitian_inputs_take_the_general_path(pb, prec, dim):
+    """The API accepts any matrices (the reference never checks): a non-Hermitian control Hamiltonian must not use the shortcut."""
+    rng = np.random.default_rng(3)
+    ct = np.complex64
+    H0 = (0.5 * rand_herm(rng, dim)).astype(ct)
+    G = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+    H1 = np.stack([(0.3 * rand_herm(rng, dim) + 0.02 * G / np.linalg.norm(G, 2)).astype(ct), (0.2 * rand_herm(rng, dim)).astype(ct)])
+    assert np.abs(H1[0] - H1[0].conj().T).max() > 1e-4
+    carr = rng.uniform(-1, 1, (2, 3001)).astype(ct)
+    with pb.Parament(prec) as ctx:
+        ctx.set_hamiltonian(H0, *H1, quadrature_mode="simpson")
+        U = ctx.equiprop(0.02, *carr)
+    assert rel_frobenius(U, equiprop_oracle(H0, H1, carr, 0.02, "simpson", False, prec)) < TOL[prec]
+
+
+def test_hermitian_shortcut_switch_gives_the_same_propagator(pb, monkeypatch):
+    w = make_workload("C2", pts=40001)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PARAMENT_K1_HERM", mode)
+        with pb.Parament(w.precision) as ctx:
+            ctx.set_hamiltonian(w.H0, *w.H1, use_magnus=w.use_magnus, quadrature_mode=w.quadrature)
+            res[mode] = ctx.equiprop(w.dt, *w.carr)
+    assert rel_frobenius(res["1"], res["0"]) < 2e-7          # complex64 output rounding
+    assert rel_frobenius(res["1"], equiprop_oracle(w.H0, w.H1, w.carr, w.dt, w.quadrature, w.use_magnus, w.precision)) < TOL["fp32"]
