@@ -47,6 +47,17 @@ __device__ __forceinline__ void facc_to_fb(FB2 &B, const FAcc2 &X, int lane) {
         }
 }
 
+// FB2 of X^H from the registers of FAcc2 X (conj_transpose_as_bfrag of frag.cuh): the right-operand layout of a Hermitian X.
+__device__ __forceinline__ void fconj_transpose_as_fb(FB2 &B, const FAcc2 &X) {
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            B.re[kt][nt] = X.re[nt][kt >> 1][kt & 1];
+            B.im[kt][nt] = -X.im[nt][kt >> 1][kt & 1];
+        }
+}
+
 // D = A * B (complex 16 x 16, fp32 grade): 48 TF32 MMAs.  Per column tile four accumulators (Ar Br, Ai Bi, Ar Bi, Ai Br), each
 // fed its three split terms for both k-tiles from zero, recombined with round-to-nearest FADDs.
 __device__ __forceinline__ void tf32_cmul16(FAcc2 &D, const FAcc2 &A, const FB2 &B) {

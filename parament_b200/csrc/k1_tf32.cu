@@ -139,7 +139,10 @@ constexpr int KREG = 3;   // control terms whose fragment tables stay in registe
 // two more MMAs), because an error made at step j has to rotate with all later steps like the product itself.
 // QK: QuadKind when every term is a plain control (no Magnus): the coefficient evaluation is then straight-line code;
 // -1: generic (term kinds and quadrature decided at run time).
-template <int OCC, bool COMP, int QK>
+// HERM: H0 and every H_k are exactly Hermitian (api.cu set_hamiltonian) and there are no Magnus terms: the registers of Z^T are
+// the conjugates of those of Z, so only one table per matrix is kept; a step with real coefficients has a Hermitian X and W, whose
+// transposes cost a sign flip instead of four shuffles.
+template <int OCC, bool COMP, int QK, bool HERM>
 __global__ void __launch_bounds__(32 * K1_WARPS, OCC)
 k1_tf32_chain_kernel(const SeriesParams p, const float2 *__restrict__ carr, const double2 *__restrict__ Hfrag,
                      double2 *__restrict__ partials, unsigned int batch, unsigned int chunks_per_pulse,
@@ -173,11 +176,11 @@ k1_tf32_chain_kernel(const SeriesParams p, const float2 *__restrict__ carr, cons
         Z.c[0] = (float)a0.x; Z.c[1] = (float)a1.x; Z.c[2] = (float)a0.y; Z.c[3] = (float)a1.y;
         Zt.c[0] = (float)b0.x; Zt.c[1] = (float)b1.x; Zt.c[2] = (float)b0.y; Zt.c[3] = (float)b1.y;
     };
-    F8 H0, H0t, Hk[KREG], Hkt[KREG];
+    F8 H0, H0t, Hk[KREG], Hkt[HERM ? 1 : KREG];
     load_frag(0, H0, H0t);
 #pragma unroll
     for (int t = 0; t < KREG; ++t)
-        if (t < p.nterms) load_frag(p.terms[t].mat, Hk[t], Hkt[t]);
+        if (t < p.nterms) { if (HERM) { F8 unused; load_frag(p.terms[t].mat, Hk[t], unused); } else load_frag(p.terms[t].mat, Hk[t], Hkt[t]); }
 
     // effective coefficient of a term in single precision (its rounding is pseudo-random from step to step; control_expansion.cu
     // of the reference does the same arithmetic in float for complex64 contexts)
@@ -197,7 +200,20 @@ k1_tf32_chain_kernel(const SeriesParams p, const float2 *__restrict__ carr, cons
     };
     auto add_term = [&](F8 &X, F8 &Xt, const float2 ct, const F8 &Z, const F8 &Zt) {
         const float cr = ct.x, ci = ct.y;
-        if (ci == 0.f) {   // real amplitude (warp-uniform)
+        if (HERM) {   // X only; X^T is formed after the last term (conjugate of X, or from the conjugated tables)
+            if (ci == 0.f) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) X.c[i] = fmaf(cr, Z.c[i], X.c[i]);
+            } else {      // Z^T = conj(Z):  X^T += c conj(Z)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    X.c[i] = fmaf(cr, Z.c[i], fmaf(-ci, Z.c[2 + i], X.c[i]));
+                    X.c[2 + i] = fmaf(cr, Z.c[2 + i], fmaf(ci, Z.c[i], X.c[2 + i]));
+                    Xt.c[i] = fmaf(2.f * ci, Z.c[2 + i], Xt.c[i]);          // corrections to conj(X), applied below
+                    Xt.c[2 + i] = fmaf(2.f * ci, Z.c[i], Xt.c[2 + i]);
+                }
+            }
+        } else if (ci == 0.f) {   // real amplitude (warp-uniform)
 #pragma unroll
             for (int i = 0; i < 4; ++i) { X.c[i] = fmaf(cr, Z.c[i], X.c[i]); Xt.c[i] = fmaf(cr, Zt.c[i], Xt.c[i]); }
         } else {
@@ -218,17 +234,31 @@ k1_tf32_chain_kernel(const SeriesParams p, const float2 *__restrict__ carr, cons
     for (unsigned long long j = lo; j < hi; ++j) {
         // ---- X = H0 + sum_t c_t H_t, in the registers of X and of X^T ----
         F8 X = H0, Xt = H0t;
+        bool xherm = HERM;   // X is Hermitian: Hermitian tables and real coefficients in this step (warp-uniform)
+        if (HERM) Xt.c[0] = Xt.c[1] = Xt.c[2] = Xt.c[3] = 0.f;
 #pragma unroll
         for (int t = 0; t < KREG; ++t)
-            if (t < p.nterms) add_term(X, Xt, coefficient(p.terms[t], j), Hk[t], Hkt[t]);
+            if (t < p.nterms) {
+                const float2 ct = coefficient(p.terms[t], j);
+                xherm = xherm && ct.y == 0.f;
+                add_term(X, Xt, ct, Hk[t], Hkt[HERM ? 0 : t]);
+            }
         for (int t = KREG; t < p.nterms; ++t) {
             F8 Z, Zt;
             load_frag(p.terms[t].mat, Z, Zt);
-            add_term(X, Xt, coefficient(p.terms[t], j), Z, Zt);
+            const float2 ct = coefficient(p.terms[t], j);
+            xherm = xherm && ct.y == 0.f;
+            add_term(X, Xt, ct, Z, Zt);
+        }
+        if (HERM) {   // X^T = conj(X) (+ the corrections of complex coefficients collected in Xt)
+            if (xherm) { Xt.c[0] = X.c[0]; Xt.c[1] = X.c[1]; Xt.c[2] = -X.c[2]; Xt.c[3] = -X.c[3]; }
+            else { Xt.c[0] += X.c[0]; Xt.c[1] += X.c[1]; Xt.c[2] -= X.c[2]; Xt.c[3] -= X.c[3]; }
         }
         // ---- W = X X ----
         const F8 W = cmul(X, Xt);
-        const F8 Wt = transpose8(W, lane);
+        F8 Wt;
+        if (xherm) { Wt.c[0] = W.c[0]; Wt.c[1] = W.c[1]; Wt.c[2] = -W.c[2]; Wt.c[3] = -W.c[3]; }   // W is Hermitian with X (to rounding)
+        else Wt = transpose8(W, lane);
         // ---- y02 = (c4 W + i c3 X) W ----
         F8 T;
         T.c[0] = fmaf(-c3, X.c[2], c4 * W.c[0]); T.c[1] = fmaf(-c3, X.c[3], c4 * W.c[1]);
@@ -292,10 +322,10 @@ k1_tf32_chain_kernel(const SeriesParams p, const float2 *__restrict__ carr, cons
 
 int k1_tf32_ctas_per_sm() { return 6; }
 
-template <bool COMP, int QK>
+template <bool COMP, int QK, bool HERM>
 static cudaError_t launch_tf32_t(const SeriesParams &p, const float2 *carr, const double2 *Hfrag, double2 *partials, unsigned int batch,
                                  const K1Plan &plan, unsigned long long step_lo, unsigned long long step_hi, const K1Final &fz, cudaStream_t stream) {
-    k1_tf32_chain_kernel<6, COMP, QK><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch, plan.chunks_per_pulse,
+    k1_tf32_chain_kernel<6, COMP, QK, HERM><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch, plan.chunks_per_pulse,
                                                                                 step_lo, step_hi, plan.reduce_in_cta, fz);
     return cudaGetLastError();
 }
@@ -311,10 +341,14 @@ cudaError_t launch_k1_tf32_chain(const SeriesParams &p, const void *carr, const 
     for (int t = 0; t < p.nterms; ++t) plain = plain && p.terms[t].type == TERM_PLAIN;
     const int qk = plain ? p.quad : -1;
     const float2 *cf = (const float2 *)carr;
-#define PB_TF32_CASE(C, Q) if (comp == C && qk == Q) return launch_tf32_t<C, Q>(p, cf, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream)
+    const bool herm = p.herm != 0 && plain;
+#define PB_TF32_CASE(C, Q) if (comp == C && qk == Q) return launch_tf32_t<C, Q, false>(p, cf, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream)
+#define PB_TF32_HERM(Q) if (!comp && herm && qk == Q) return launch_tf32_t<false, Q, true>(p, cf, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream)
+    PB_TF32_HERM(QUAD_NONE); PB_TF32_HERM(QUAD_MIDPOINT); PB_TF32_HERM(QUAD_SIMPSON);
     PB_TF32_CASE(true, QUAD_NONE); PB_TF32_CASE(true, QUAD_MIDPOINT); PB_TF32_CASE(true, QUAD_SIMPSON); PB_TF32_CASE(true, -1);
     PB_TF32_CASE(false, QUAD_NONE); PB_TF32_CASE(false, QUAD_MIDPOINT); PB_TF32_CASE(false, QUAD_SIMPSON); PB_TF32_CASE(false, -1);
 #undef PB_TF32_CASE
+#undef PB_TF32_HERM
     return cudaErrorInvalidValue;
 }
 

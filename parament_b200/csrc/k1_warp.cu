@@ -288,8 +288,8 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                         (&Tf.im[0][0][0])[e] = fmaf(c3h, (&Xf.re[0][0][0])[e], fmaf(c3l, (&Xf.re[0][0][0])[e], c4f * (&Wf.im[0][0][0])[e]));
                     }
                     K1_T(5)
-                    FB2 Wbf;
-                    facc_to_fb(Wbf, Wf, lane);
+                    FB2 Wbf;                               // W = X X is Hermitian with X (to rounding): same relabeling
+                    if (xherm) fconj_transpose_as_fb(Wbf, Wf); else facc_to_fb(Wbf, Wf, lane);
                     K1_T(6)
                     FAcc2 Y2f;
                     tf32_cmul16(Y2f, Tf, Wbf);              // y02 = T W
@@ -323,7 +323,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                 set_zero<NT>(Wa);
                 if (MUL3) cmma3<NT>(Wa, Ya, Yb); else cmma<NT>(Wa, Ya, Yb);   // W
                 BFrag<NT> Wb;
-                acc_to_bfrag<NT>(Wb, Wa, lane);
+                if (!BOTH && xherm) conj_transpose_as_bfrag<NT>(Wb, Wa); else acc_to_bfrag<NT>(Wb, Wa, lane);   // W = X X is Hermitian with X (to rounding)
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     (&Wb.nim[0][0])[e] = bfrag_third<MUL3>((&Wb.re[0][0])[e], (&Wb.im[0][0])[e]);
