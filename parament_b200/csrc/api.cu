@@ -107,7 +107,7 @@ bool create_device_objects(Context *c) {
            PB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) &&
            PB_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) && create_copy_events(c) &&
            PB_CUDA_OK(cudaEventCreate(&c->ev_start)) && PB_CUDA_OK(cudaEventCreate(&c->ev_stop)) &&
-           PB_CUDA_OK(cudaMallocHost(&c->h_absmax, kMaxTerms * sizeof(double)));
+           PB_CUDA_OK(cudaMallocHost(&c->h_absmax, (kMaxTerms + 1) * sizeof(double)));
 }
 void destroy_device_objects(Context *c) {
     if (c->stager) { c->stager->stop(); delete c->stager; c->stager = nullptr; }
@@ -478,6 +478,7 @@ struct CallSpec {
     unsigned long long total_steps; // steps of the whole pulse (degree policy of sliced runs)
     double dt;
     double series_norm;             // bound of ||H(t_j)||_2 the series is built for; 0: the reference's Hnorm
+    bool real_amps;                 // every amplitude of the call has a zero imaginary part (measured with the maxima; dim > 16 only)
 };
 
 unsigned long long effective_steps(const Context *c, unsigned long long pts) {   // parament.cpp:820-831
@@ -899,6 +900,13 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
     const int S = f.S, cap = f.cap;
     const SeriesProgram prog = build_program(p);
     const int NS = f.NS;
+    // Hermitian H0 / H_k, no Magnus terms and real amplitudes throughout the call (measured with the amplitude maxima): every Y is
+    // Hermitian, so Y Y is too and only its upper-triangular tiles are computed (k4_gemm.hpp GemmArgs::herm); $PARAMENT_K4_HERM=0: A/B
+    const bool herm_steps = c->hermitian && !c->enable_magnus && s.real_amps && !(getenv("PARAMENT_K4_HERM") && atoi(getenv("PARAMENT_K4_HERM")) == 0);
+    c->stat_products_saved = 0.0;
+    if (herm_steps)
+        for (int o = 0; o < prog.nops; ++o)
+            if (prog.ops[o].A == prog.ops[o].B && prog.ops[o].A <= 1) c->stat_products_saved += 1.0 - (double)k4_herm_tiles(np) / (double)tiles;
     cudaStream_t sx[kF3Streams] = {st, nullptr, nullptr, nullptr};
     if (NS > 1) {
         sx[0] = c->copy_stream;
@@ -961,6 +969,7 @@ Parament_ErrorCode run_family3(Context *c, const SeriesParams &p, const void *ca
                 }
                 g.alpha = op.alpha; g.scaled = op.scaled; g.gamma = op.gamma; g.gamma_lo = op.gamma_lo;
                 g.C2 = nullptr; g.beta2 = 0.0; g.n = np; g.batch = Sc;
+                g.herm = (herm_steps && op.A == op.B && op.A <= 1) ? 1 : 0;   // Y Y and W W: Hermitian like their addends (powers of Y)
                 if (direct && o == prog.nops - 1) g.D = pend + (size_t)pending * nn;   // E goes straight to the pending buffer
                 PB_LAUNCH(k4_gemm(g, q));
             }
@@ -1033,18 +1042,22 @@ bool prepare_fused(Context *c, const K1Plan &plan, unsigned int batch, void *out
 // and a 64-byte read-back; dim > 16 only, where a step costs >= 50 us of tensor work per SM).  The quadrature averages cannot
 // exceed the maxima; the Magnus commutator term adds at most (h/12) 2 rho^2.  5 % margin on the power-iteration estimates; never
 // above the reference's bound Hnorm (parament.cpp:280-284), which stays in charge of the error semantics.
-Parament_ErrorCode series_norm_for_call(Context *c, const void *carr_dev, const CallSpec &s, cudaStream_t st, double &Hs) {
+Parament_ErrorCode series_norm_for_call(Context *c, const void *carr_dev, const CallSpec &s, cudaStream_t st, double &Hs, bool &real_amps) {
     Hs = c->Hnorm;
+    real_amps = false;
     if (c->family == 1 || c->norm_mode != 1 || c->MMAX_manual || c->sigma_max.size() < (size_t)c->amps + 1) return PARAMENT_STATUS_SUCCESS;
     double rho = c->sigma_max[0];
     if (s.amps > 0) {
-        if (!ensure_dev(c->d_absmax, kMaxTerms * sizeof(unsigned long long))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
+        if (!ensure_dev(c->d_absmax, (kMaxTerms + 1) * sizeof(unsigned long long))) return PARAMENT_STATUS_DEVICE_ALLOC_FAILED;
         const size_t pts = (size_t)points_per_step(c) * s.nsteps + point_overlap(c);
         if (k4_absmax(c->fp64, carr_dev, s.batch, s.amps, s.stride, std::min(pts, s.stride), (unsigned long long *)c->d_absmax.ptr, st) != cudaSuccess ||
-            !PB_CUDA_OK(cudaMemcpyAsync(c->h_absmax, c->d_absmax.ptr, s.amps * sizeof(double), cudaMemcpyDeviceToHost, st)) ||
+            !PB_CUDA_OK(cudaMemcpyAsync(c->h_absmax, c->d_absmax.ptr, (s.amps + 1) * sizeof(double), cudaMemcpyDeviceToHost, st)) ||
             !PB_CUDA_OK(cudaStreamSynchronize(st)))
             return PARAMENT_STATUS_CUBLAS_FAILED;
         for (unsigned int k = 0; k < s.amps; ++k) rho += std::sqrt(c->h_absmax[k]) * c->sigma_max[1 + k];
+        unsigned long long flag;
+        memcpy(&flag, &c->h_absmax[s.amps], sizeof(flag));
+        real_amps = flag == 0;
     }
     if (c->enable_magnus) {
         const double h = 2.0 * std::fabs(s.dt);
@@ -1059,13 +1072,14 @@ Parament_ErrorCode series_norm_for_call(Context *c, const void *carr_dev, const 
 Parament_ErrorCode propagate_device(Context *c, const void *carr_dev, const CallSpec &s_in, void *out_dev, cudaStream_t st) {
     NvtxRange range("parament: propagate (device-resident core)");
     CallSpec s = s_in;
-    Parament_ErrorCode ec = series_norm_for_call(c, carr_dev, s, st, s.series_norm);
+    Parament_ErrorCode ec = series_norm_for_call(c, carr_dev, s, st, s.series_norm, s.real_amps);
     if (ec != PARAMENT_STATUS_SUCCESS) return ec;
     SeriesParams p;
     ec = build_series(c, s, p);
     if (ec != PARAMENT_STATUS_SUCCESS) return ec;
     c->stat_steps = s.nsteps;
     c->stat_launches = 0;
+    c->stat_products_saved = 0.0;
     // all allocations happen before the timed region (grow-only scratch, nothing is allocated in steady state)
     K1Plan plan{};
     const bool tf32 = use_tf32_path(c, p, s);
@@ -1742,6 +1756,10 @@ double Parament_lastStat(void *h, int key) {
         case 10: {   // complex matrix products executed per effective step (series + ordered product)
             const int M = c->stat_M_used;
             if (M <= 0) return 0.0;
+            if (c->family == 3 && c->stat_products_saved > 0.0) {   // Hermitian square: only the upper-triangular tiles were computed
+                const double full = c->stat_horner == 2 ? 4.0 + (M >> 2) : (c->stat_horner == 3 ? 4.0 : (c->stat_horner == 4 ? 5.0 : 2.0 + (M >> 1)));
+                return full - c->stat_products_saved;
+            }
             if (c->stat_horner == 2) return 4.0 + (M >> 2);
             if (c->stat_horner == 3) return 4.0;   // degree 8 in three products + the ordered product
             if (c->stat_horner == 4) return 5.0;   // degree 12 in four products + the ordered product

@@ -261,6 +261,7 @@ struct Context {
     double stat_ms = 0.0;
     long long stat_launches = 0;
     int stat_M_used = 0, stat_M_ref = 0, stat_horner = 0;
+    double stat_products_saved = 0.0;   // complex products per step NOT executed because only the upper-triangular tiles of a Hermitian square were computed
     int stat_math = 0;     // arithmetic of the last call: 0 = FP64 (DMMA), 1 = FP32 as 3xTF32 on the warp-level tensor path
     int series_mode = 0;   // 0 automatic, 1 force the Clenshaw recurrence ($PARAMENT_SERIES=clenshaw), 2 Horner / PS only
     // series constants of the last call: rebuilt only when the step size, the norm or the degree changes (the product-saving

@@ -73,7 +73,19 @@ struct TileArgs {
     double beta2;
     cplx gamma, gamma_lo;
     int n;
+    int herm;                         // GemmArgs::herm
 };
+
+// Hermitian product: tile (i, j) of BM x BN elements lies strictly below the diagonal -- and is left to the mirror writes of the
+// tile that holds its transpose -- iff its first row is beyond its last column.
+template <int BM, int BN>
+__host__ __device__ __forceinline__ bool herm_tile_skipped(int i, int j) { return BM * i >= BN * (j + 1); }
+template <int BM, int BN>
+__host__ __device__ inline int herm_tile_count(int n) {
+    int cnt = 0;
+    for (int i = 0; i < n / BM; ++i) cnt += n / BN - (BM * i) / BN;
+    return cnt;
+}
 
 // Shared epilogue arithmetic for two horizontally adjacent elements (row r, columns c and c+1): on entry (vr, vi) hold the
 // product, z[j][i] the addends; small terms are added first, the dominant ones last with a single-rounding FMA.
@@ -281,6 +293,33 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
             }
             double2 x0 = make_double2(0.0, 0.0), x1 = x0;
             if (g.C2) { x0 = g.C2[off]; x1 = g.C2[off + 1]; }
+            if (g.herm && herm_tile_skipped<BM, BN>((int)(c / BM), (int)(r / BN))) {
+                // the transposed position (c, r), (c + 1, r) lies in a tile nobody computes: every output there is the same
+                // combination of the CONJUGATED product and addends (Hermitian operands; never on the diagonal)
+                const size_t m0 = c * g.n + r, m1 = m0 + g.n;
+                double wr[2] = {vr[0], vr[1]}, wi[2] = {-vi[0], -vi[1]};
+                if (g.Dprod) { g.Dprod[m0] = make_double2(wr[0], wi[0]); g.Dprod[m1] = make_double2(wr[1], wi[1]); }
+                double2 zc[kMaxAddends][2];
+#pragma unroll
+                for (int j = 0; j < kMaxAddends; ++j) { zc[j][0] = make_double2(z[j][0].x, -z[j][0].y); zc[j][1] = make_double2(z[j][1].x, -z[j][1].y); }
+                if (g.Dalt) {
+                    double ar[2] = {wr[0], wr[1]}, ai[2] = {wi[0], wi[1]};
+#pragma unroll
+                    for (int j = kMaxAddends - 1; j >= 0; --j)
+                        if (has[j]) {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                ar[i] = fma(g.beta_alt[j].re, zc[j][i].x, fma(-g.beta_alt[j].im, zc[j][i].y, ar[i]));
+                                ai[i] = fma(g.beta_alt[j].re, zc[j][i].y, fma(g.beta_alt[j].im, zc[j][i].x, ai[i]));
+                            }
+                        }
+                    g.Dalt[m0] = make_double2(ar[0], ai[0]);
+                    g.Dalt[m1] = make_double2(ar[1], ai[1]);
+                }
+                epilogue_pair(wr, wi, zc, has, g.scaled, g.alpha, g.beta, g.beta_lo, g.gamma, g.gamma_lo, false, false);
+                g.D[m0] = make_double2(wr[0], wi[0]);
+                g.D[m1] = make_double2(wr[1], wi[1]);
+            }
             epilogue_pair(vr, vi, z, has, g.scaled, g.alpha, g.beta, g.beta_lo, g.gamma, g.gamma_lo, r == c, r == c + 1);
             if (g.C2) { vr[0] += g.beta2 * x0.x; vi[0] += g.beta2 * x0.y; vr[1] += g.beta2 * x1.x; vi[1] += g.beta2 * x1.y; }
             g.D[off] = make_double2(vr[0], vi[0]);
@@ -321,7 +360,17 @@ k4_zgemm_kernel(const GemmArgs g) {
     t.alpha = g.alpha; t.scaled = g.scaled;
     t.beta2 = g.beta2; t.gamma = g.gamma; t.gamma_lo = g.gamma_lo;
     t.n = g.n;
-    tile_gemm<BM, BN, WM, WN, FEED, MUL3, STAGES>(smem, t, blockIdx.x / tiles_n, blockIdx.x % tiles_n, bars);
+    t.herm = g.herm;
+    int tile_m = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
+    if (g.herm) {   // blockIdx.x enumerates the tiles that are not skipped, row by row
+        int rest = blockIdx.x;
+        for (tile_m = 0;; ++tile_m) {
+            const int first = (BM * tile_m) / BN, cnt = tiles_n - first;
+            if (rest < cnt) { tile_n = first + rest; break; }
+            rest -= cnt;
+        }
+    }
+    tile_gemm<BM, BN, WM, WN, FEED, MUL3, STAGES>(smem, t, tile_m, tile_n, bars);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -384,6 +433,7 @@ k4_chain_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__rest
             t.alpha = op.alpha; t.scaled = op.scaled;
             t.beta2 = 0.0; t.gamma = op.gamma; t.gamma_lo = op.gamma_lo;
             t.n = BM;
+            t.herm = 0;
             tile_gemm<BM, BM, WM, WN>(smem, t, 0, 0);
             __syncthreads();
         }
@@ -489,22 +539,25 @@ k4_absmax_kernel(const IO *__restrict__ carr, unsigned int batch, unsigned int a
                  unsigned long long *__restrict__ out) {
     const unsigned int k = blockIdx.y;
     double best = 0.0;
+    bool cplx_seen = false;   // any amplitude with a non-zero (or NaN) imaginary part -> out[amps] != 0
     for (unsigned int b = 0; b < batch; ++b) {
         const IO *c = carr + ((size_t)b * amps + k) * stride;
         for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < pts; j += (size_t)gridDim.x * blockDim.x) {
             const IO v = __ldg(c + j);
             const double m = (double)v.x * (double)v.x + (double)v.y * (double)v.y;
             best = m > best ? m : best;   // a NaN amplitude never wins: the propagator will be NaN anyway
+            cplx_seen = cplx_seen || !(v.y == 0);
         }
     }
     for (int o = 16; o > 0; o >>= 1) { const double other = __shfl_xor_sync(0xffffffffu, best, o); best = other > best ? other : best; }
     if ((threadIdx.x & 31) == 0 && best > 0.0) atomicMax(out + k, (unsigned long long)__double_as_longlong(best));
+    if (__any_sync(0xffffffffu, cplx_seen) && (threadIdx.x & 31) == 0) atomicMax(out + amps, 1ull);
 }
 
 cudaError_t k4_absmax(bool fp64_io, const void *carr, unsigned int batch, unsigned int amps, size_t stride, size_t pts,
                       unsigned long long *out_dev, cudaStream_t stream) {
     if (amps == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(out_dev, 0, (size_t)amps * sizeof(unsigned long long), stream);
+    cudaError_t e = cudaMemsetAsync(out_dev, 0, ((size_t)amps + 1) * sizeof(unsigned long long), stream);   // [amps]: complex amplitudes seen
     if (e != cudaSuccess) return e;
     const size_t work = pts * batch;
     const unsigned int bx = (unsigned int)std::max<size_t>(1, std::min<size_t>(592, (work + 2047) / 2048));
@@ -678,7 +731,7 @@ static cudaError_t launch_gemm_tt(const GemmArgs &g, cudaStream_t stream) {
     cudaError_t e = opt_in_smem(kern, SM::BYTES);   // per-device function attribute; cheap, so set on every launch
     if (e != cudaSuccess) return e;
     // (programmatic dependent launch was measured here: 2.78e4 -> 2.50e4 steps/s at dim 256, so plain stream order is kept)
-    dim3 grid((g.n / BM) * (g.n / BN), g.batch);
+    dim3 grid(g.herm ? herm_tile_count<BM, BN>(g.n) : (g.n / BM) * (g.n / BN), g.batch);
     kern<<<grid, (BM / WM) * (BN / WN) * 32, SM::BYTES, stream>>>(g);
     return cudaGetLastError();
 }
@@ -702,6 +755,10 @@ cudaError_t k4_gemm(const GemmArgs &g, cudaStream_t stream) {
 
 int k4_pad(int n) { return n <= 32 ? 32 : ((n + 63) / 64) * 64; }
 int k4_real_products(int npad) { return (npad % 64 == 0 && k4_mul3_mode() != 0) ? 3 : 4; }
+int k4_herm_tiles(int npad) {   // tiles of a Hermitian-output launch (GemmArgs::herm) in the tile shape k4_gemm selects
+    if (npad % 64 != 0) return herm_tile_count<32, 32>(npad);
+    return k4_mul3_mode() >= 2 ? herm_tile_count<64, 32>(npad) : herm_tile_count<64, 64>(npad);
+}
 int k4_tiles(int npad) {
     if (npad % 64 != 0) return 1;
     return (npad / 64) * (npad / (k4_mul3_mode() >= 2 ? 32 : 64));

@@ -22,6 +22,9 @@ struct GemmArgs {
     cplx gamma; cplx gamma_lo;
     int n;
     int batch;
+    int herm;                        // A == B is Hermitian and so is every addend: the product is Hermitian.  Only the tiles that
+                                     // touch the upper triangle are computed; their epilogue also writes the mirrored elements
+                                     // (every output evaluated on the conjugated product and addends) into the skipped tiles
 };
 
 // The per-step series as a short program of fused GEMMs over matrix slots
@@ -52,6 +55,7 @@ SeriesProgram build_program(const SeriesParams &p);
 cudaError_t k4_gemm(const GemmArgs &g, cudaStream_t stream);
 int k4_pad(int n);                            // padded dimension used by this kernel family
 int k4_tiles(int npad);                       // CTA tiles per matrix
+int k4_herm_tiles(int npad);                  // CTA tiles per matrix of a Hermitian-output launch (upper-triangular tiles only)
 int k4_real_products(int npad);               // real matrix products per complex product of the batched GEMM (4, or 3)
 int k4_wave_slots(int npad, int num_sms);     // co-resident CTAs of the batched GEMM kernel on the device
 int k4_chain_slots(int npad, int num_sms);    // co-resident CTAs of the persistent chain kernel (npad <= 64)

@@ -471,3 +471,37 @@ def test_tf32_kernel_hermitian_and_general_variants(pb, dim, quad, complex_amps,
         U = ctx.equiprop(dt, *carr)
         assert ctx.stat(15) == 1
     assert rel_frobenius(U, equiprop_oracle(H0, H1, carr, dt, quad, False, "fp32")) < TOL["fp32"]
+
+
+# ---- dim > 64: Hermitian Y -> only the upper-triangular tiles of Y Y are computed, the rest mirrored --------------------------
+@pytest.mark.parametrize("dim,quad,complex_amps,hermitian,series,dt", [
+    (128, "none", False, True, None, 0.02), (100, "simpson", False, True, None, 0.02), (256, "midpoint", False, True, None, 0.02),
+    (128, "none", True, True, None, 0.02), (128, "none", False, False, None, 0.02), (192, "none", False, True, "horner", 0.02),
+    (128, "simpson", False, True, "horner", 0.4), (70, "none", False, True, None, 0.3)])
+def test_hermitian_square_in_batched_gemm(pb, monkeypatch, dim, quad, complex_amps, hermitian, series, dt):
+    """Real amplitudes + Hermitian matrices take the mirrored-tile GEMM for Y Y (and W W in the blocks-of-four form); complex
+    amplitudes and non-Hermitian inputs must not.  Both against the oracle, and against each other through PARAMENT_K4_HERM=0."""
+    rng = np.random.default_rng(dim)
+    ct = np.complex128
+    H0 = (0.5 * rand_herm(rng, dim)).astype(ct)
+    H1 = np.stack([(0.3 * rand_herm(rng, dim)).astype(ct) for _ in range(2)])
+    if not hermitian:
+        G = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        H1[0] = H1[0] + 0.02 * G / np.linalg.norm(G, 2)
+    pts = 31
+    carr = rng.uniform(-1, 1, (2, pts))
+    if complex_amps:
+        carr = carr + 1j * rng.uniform(-0.3, 0.3, (2, pts))
+    carr = carr.astype(ct)
+    if series:
+        monkeypatch.setenv("PARAMENT_SERIES", series)
+    res, forms = {}, {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PARAMENT_K4_HERM", mode)
+        with pb.Parament("fp64") as ctx:
+            ctx.set_hamiltonian(H0, *H1, quadrature_mode=quad)
+            res[mode] = ctx.equiprop(dt, *carr)
+            assert ctx.stat(5) == 3
+            forms[mode] = ctx.stat(9)
+    assert rel_frobenius(res["1"], equiprop_oracle(H0, H1, carr, dt, quad, False, "fp64")) < TOL["fp64"], forms
+    assert rel_frobenius(res["1"], res["0"]) < 1e-13
