@@ -212,7 +212,9 @@ PARAMENT_API Parament_ErrorCode Parament_combineDevice(void *handle, const void 
  *     Key 3 (the reference table's degree) and error 70 always follow Hnorm; key 2 follows key 14.
  *   9 series evaluation (0 Clenshaw recurrence, 1 Horner in Y^2, 2 Paterson-Stockmeyer blocks of four,
  *                        3 degree 8 in three products, 4 degree 12 in four products -- all the same polynomial family)
- *  10 complex matrix products executed per effective step (series + ordered product)
+ *  10 complex matrix products executed per effective step (series + ordered product); fractional for dim > 64 when the inputs are
+ *     Hermitian and the amplitudes real: of the Hermitian square Y Y only the tiles touching the upper triangle are computed
+ *     (20 of 32 at dim 256), the rest is mirrored by the epilogue (PARAMENT_K4_HERM=0 computes all tiles)
  *  13 real matrix products per complex product in the kernel family used, averaged over the products of a step (4; 3 for the
  *     batched GEMM of dim > 64 and for the degree-8 form of complex64 contexts at dim 9..16; 3.25 / 3.4 for the shared-memory-resident
  *     kernel of dim 17..64 in its degree-8 / degree-12 form)

@@ -135,7 +135,8 @@ def test_spectral_norm_saves_a_product(pb):
         assert 1.04 * sig <= hs <= 1.0501 * sig
         worst = max(np.linalg.norm(w.H0 + np.tensordot(w.carr[:, j], w.H1, axes=1), 2) for j in range(0, pts, max(1, pts // 16)))
         assert worst <= hs                                   # a true bound of the sampled step Hamiltonians
-        assert m_ref == 11 and m_used == 8 and products == 4.0
+        # dim 256, Hermitian matrices and real amplitudes: 12 of the 32 tiles of Y Y are mirrored, not computed (3 + 20/32 + 1 products)
+        assert m_ref == 11 and m_used == 8 and products == (4.0 if name == "C3" else 3.625)
         assert rel_frobenius(U, equiprop_oracle(w.H0, w.H1, w.carr, w.dt, "none", False, "fp64")) < 1e-13
 
 
