@@ -448,22 +448,23 @@ def test_hermitian_shortcut_switch_gives_the_same_propagator(pb, monkeypatch):
     assert rel_frobenius(res["1"], equiprop_oracle(w.H0, w.H1, w.carr, w.dt, w.quadrature, w.use_magnus, w.precision)) < TOL["fp32"]
 
 
+@pytest.mark.parametrize("A", [3, 5])      # 5: more control terms than the kernel keeps in registers
 @pytest.mark.parametrize("dim,quad,complex_amps,hermitian", [(8, "none", True, True), (6, "simpson", True, True), (8, "midpoint", False, True),
                                                              (8, "none", False, False), (7, "simpson", True, False), (5, "midpoint", True, True)])
-def test_tf32_kernel_hermitian_and_general_variants(pb, dim, quad, complex_amps, hermitian):
+def test_tf32_kernel_hermitian_and_general_variants(pb, dim, quad, complex_amps, hermitian, A):
     """complex64, dim 5..8, short pulse (3xTF32 kernel): Hermitian tables (one register table per matrix, X^T = conj(X) for real
     coefficients, conjugated tables for complex ones) and the general variant for non-Hermitian inputs."""
     rng = np.random.default_rng(100 + dim)
     ct = np.complex64
     H0 = (0.5 * rand_herm(rng, dim)).astype(ct)
-    H1 = np.stack([(0.3 * rand_herm(rng, dim)).astype(ct) for _ in range(3)])
+    H1 = np.stack([(0.9 / A * rand_herm(rng, dim)).astype(ct) for _ in range(A)])
     if not hermitian:
         G = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
-        H1[1] = (H1[1] + 0.03 * G / np.linalg.norm(G, 2)).astype(ct)
+        H1[A - 1] = (H1[A - 1] + 0.03 * G / np.linalg.norm(G, 2)).astype(ct)
     pts = 401
-    carr = rng.uniform(-1, 1, (3, pts))
+    carr = rng.uniform(-1, 1, (A, pts))
     if complex_amps:
-        carr = carr + 1j * rng.uniform(-1, 1, (3, pts))
+        carr = carr + 1j * rng.uniform(-1, 1, (A, pts))
         carr[1].imag = 0.0          # a mix of real and complex coefficients within a step
     carr = carr.astype(ct)
     dt = 0.05

@@ -34,6 +34,25 @@ for name, kw in (("C2", dict(pts=60001)), ("C5", dict(pts=257, batch=300)), ("C5
         Uo = equiprop_oracle(w.H0, w.H1, carr[0], w.dt, w.quadrature, w.use_magnus, w.precision)
         print(name, kw, "launches", int(ctx.stat(1)), "math", int(ctx.stat(15)), "err", rel_frobenius(U[0], Uo), "slices", rel_frobenius(V, Uo), flush=True)
 
+# packed small systems (dim <= 4: several systems per 8 x 8 tile, unpacked by warp shuffles + tile products), single pulse and
+# ensembles in both plans; non-Hermitian inputs (general layout changes) at dim 16 / 8 and dim 128 (all tiles of Y Y)
+from workloads import rand_herm
+rng = np.random.default_rng(4)
+for dim, prec, batch, pts in ((2, "fp64", 1, 2003), (2, "fp32", 700, 37), (4, "fp64", 9, 301), (3, "fp64", 5000, 5),
+                              (16, "fp32", 1, 1501), (8, "fp32", 30, 99), (128, "fp64", 1, 9)):
+    ct = np.complex64 if prec == "fp32" else np.complex128
+    H0 = (0.5 * rand_herm(rng, dim)).astype(ct)
+    H1 = np.stack([(0.3 * rand_herm(rng, dim)).astype(ct) for _ in range(2)])
+    if dim >= 8:
+        G = rng.normal(size=(dim, dim)) + 1j * rng.normal(size=(dim, dim))
+        H1[1] = (H1[1] + 0.02 * G / np.linalg.norm(G, 2)).astype(ct)
+    carr = rng.uniform(-1, 1, (batch, 2, pts)).astype(ct)
+    with pb.Parament(prec) as ctx:
+        ctx.set_hamiltonian(H0, *H1, quadrature_mode="none")
+        U = ctx.equiprop_batch(0.03, carr)
+        Uo = equiprop_oracle(H0, H1, carr[batch // 2], 0.03, "none", False, prec)
+        print("dim", dim, prec, "pulses", batch, "pts", pts, "math", int(ctx.stat(15)), "err", rel_frobenius(U[batch // 2], Uo), flush=True)
+
 # single-process multi-device mode on one GPU (device 0 listed three times): threads, peer copies, combine
 w = make_workload("C3", pts=900)
 with pb.Parament("fp64") as ctx:
