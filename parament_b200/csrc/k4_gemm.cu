@@ -17,6 +17,7 @@
 #include <cstring>
 #include "coef.cuh"
 #include "k4_gemm.hpp"
+#include "plan.hpp"
 
 namespace pb {
 
@@ -75,17 +76,6 @@ struct TileArgs {
     int n;
     int herm;                         // GemmArgs::herm
 };
-
-// Hermitian product: tile (i, j) of BM x BN elements lies strictly below the diagonal -- and is left to the mirror writes of the
-// tile that holds its transpose -- iff its first row is beyond its last column.
-template <int BM, int BN>
-__host__ __device__ __forceinline__ bool herm_tile_skipped(int i, int j) { return BM * i >= BN * (j + 1); }
-template <int BM, int BN>
-__host__ __device__ inline int herm_tile_count(int n) {
-    int cnt = 0;
-    for (int i = 0; i < n / BM; ++i) cnt += n / BN - (BM * i) / BN;
-    return cnt;
-}
 
 // Shared epilogue arithmetic for two horizontally adjacent elements (row r, columns c and c+1): on entry (vr, vi) hold the
 // product, z[j][i] the addends; small terms are added first, the dominant ones last with a single-rounding FMA.
@@ -293,7 +283,7 @@ __device__ __forceinline__ void tile_gemm(double2 *smem, const TileArgs &g, int 
             }
             double2 x0 = make_double2(0.0, 0.0), x1 = x0;
             if (g.C2) { x0 = g.C2[off]; x1 = g.C2[off + 1]; }
-            if (g.herm && herm_tile_skipped<BM, BN>((int)(c / BM), (int)(r / BN))) {
+            if (g.herm && herm_tile_skipped(BM, BN, (int)(c / BM), (int)(r / BN))) {
                 // the transposed position (c, r), (c + 1, r) lies in a tile nobody computes: every output there is the same
                 // combination of the CONJUGATED product and addends (Hermitian operands; never on the diagonal)
                 const size_t m0 = c * g.n + r, m1 = m0 + g.n;
@@ -362,14 +352,7 @@ k4_zgemm_kernel(const GemmArgs g) {
     t.n = g.n;
     t.herm = g.herm;
     int tile_m = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
-    if (g.herm) {   // blockIdx.x enumerates the tiles that are not skipped, row by row
-        int rest = blockIdx.x;
-        for (tile_m = 0;; ++tile_m) {
-            const int first = (BM * tile_m) / BN, cnt = tiles_n - first;
-            if (rest < cnt) { tile_n = first + rest; break; }
-            rest -= cnt;
-        }
-    }
+    if (g.herm) herm_tile_at(BM, BN, g.n, (int)blockIdx.x, tile_m, tile_n);   // blockIdx.x enumerates the tiles that are not skipped (plan.hpp)
     tile_gemm<BM, BN, WM, WN, FEED, MUL3, STAGES>(smem, t, tile_m, tile_n, bars);
 }
 
@@ -731,7 +714,7 @@ static cudaError_t launch_gemm_tt(const GemmArgs &g, cudaStream_t stream) {
     cudaError_t e = opt_in_smem(kern, SM::BYTES);   // per-device function attribute; cheap, so set on every launch
     if (e != cudaSuccess) return e;
     // (programmatic dependent launch was measured here: 2.78e4 -> 2.50e4 steps/s at dim 256, so plain stream order is kept)
-    dim3 grid(g.herm ? herm_tile_count<BM, BN>(g.n) : (g.n / BM) * (g.n / BN), g.batch);
+    dim3 grid(g.herm ? herm_tile_count(BM, BN, g.n) : (g.n / BM) * (g.n / BN), g.batch);
     kern<<<grid, (BM / WM) * (BN / WN) * 32, SM::BYTES, stream>>>(g);
     return cudaGetLastError();
 }
@@ -756,8 +739,8 @@ cudaError_t k4_gemm(const GemmArgs &g, cudaStream_t stream) {
 int k4_pad(int n) { return n <= 32 ? 32 : ((n + 63) / 64) * 64; }
 int k4_real_products(int npad) { return (npad % 64 == 0 && k4_mul3_mode() != 0) ? 3 : 4; }
 int k4_herm_tiles(int npad) {   // tiles of a Hermitian-output launch (GemmArgs::herm) in the tile shape k4_gemm selects
-    if (npad % 64 != 0) return herm_tile_count<32, 32>(npad);
-    return k4_mul3_mode() >= 2 ? herm_tile_count<64, 32>(npad) : herm_tile_count<64, 64>(npad);
+    if (npad % 64 != 0) return herm_tile_count(32, 32, npad);
+    return k4_mul3_mode() >= 2 ? herm_tile_count(64, 32, npad) : herm_tile_count(64, 64, npad);
 }
 int k4_tiles(int npad) {
     if (npad % 64 != 0) return 1;

@@ -135,4 +135,27 @@ inline unsigned int devices_for_call(unsigned int configured, unsigned int batch
     return (unsigned int)std::max<unsigned long long>(g, 1);
 }
 
+// Hermitian-output batched GEMM (k4_gemm.cu, GemmArgs::herm): tile (i, j) of BM x BN elements lies strictly below the diagonal -- and is
+// left to the mirror writes of the tile that holds its transpose -- iff its first row is beyond its last column.  The launch
+// enumerates the remaining tiles row by row.
+#ifdef __CUDACC__
+#define PB_HD __host__ __device__
+#else
+#define PB_HD
+#endif
+PB_HD inline bool herm_tile_skipped(int BM, int BN, int i, int j) { return BM * i >= BN * (j + 1); }
+PB_HD inline int herm_tile_count(int BM, int BN, int n) {
+    int cnt = 0;
+    for (int i = 0; i < n / BM; ++i) cnt += n / BN - (BM * i) / BN;
+    return cnt;
+}
+PB_HD inline void herm_tile_at(int BM, int BN, int n, int idx, int &i, int &j) {
+    const int tiles_n = n / BN;
+    for (i = 0;; ++i) {
+        const int first = (BM * i) / BN, cnt = tiles_n - first;
+        if (idx < cnt) { j = first + idx; return; }
+        idx -= cnt;
+    }
+}
+
 }  // namespace pb

@@ -3,6 +3,7 @@
 //   plan_check egroups batch unit G
 //   plan_check tgroups nsteps G
 //   plan_check devices configured batch nsteps npad
+//   plan_check herm BM BN n
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,6 +43,23 @@ int main(int argc, char **argv) {
         printf("{\"devices\": %u, \"min_steps\": %llu}\n",
                devices_for_call((unsigned)atoll(argv[2]), (unsigned)atoll(argv[3]), strtoull(argv[4], nullptr, 10), atoi(argv[5])),
                min_steps_per_device(atoi(argv[5])));
+        return 0;
+    }
+    if (!strcmp(argv[1], "herm") && argc == 5) {   // plan_check herm BM BN n -> the enumerated tiles and the skipped ones
+        const int BM = atoi(argv[2]), BN = atoi(argv[3]), n = atoi(argv[4]);
+        const int cnt = herm_tile_count(BM, BN, n);
+        printf("{\"count\": %d, \"tiles\": [", cnt);
+        for (int t = 0; t < cnt; ++t) {
+            int i = -1, j = -1;
+            herm_tile_at(BM, BN, n, t, i, j);
+            printf("%s[%d, %d]", t ? ", " : "", i, j);
+        }
+        printf("], \"skipped\": [");
+        bool first = true;
+        for (int i = 0; i < n / BM; ++i)
+            for (int j = 0; j < n / BN; ++j)
+                if (herm_tile_skipped(BM, BN, i, j)) { printf("%s[%d, %d]", first ? "" : ", ", i, j); first = false; }
+        printf("]}\n");
         return 0;
     }
     return 2;

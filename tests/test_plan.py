@@ -121,3 +121,24 @@ def test_devices_taking_part_in_a_call(plan, configured, batch, nsteps, npad, ex
     d = plan("devices", configured, batch, nsteps, npad)
     assert d["devices"] == expect
     assert d["min_steps"] == max(64, 2 ** 26 // npad ** 3)
+
+
+@pytest.mark.parametrize("BM,BN,n", [(64, 32, 256), (64, 32, 128), (64, 64, 256), (32, 32, 96), (64, 32, 64), (64, 32, 512)])
+def test_hermitian_gemm_tiles(plan, BM, BN, n):
+    """Hermitian-output GEMM of dim > 64 (k4_gemm.cu, GemmArgs::herm): the launch enumerates exactly the tiles that touch the upper
+    triangle; every element of a skipped tile is the mirror image of an element of an enumerated tile, and no element of an
+    enumerated tile is written twice (a mirror write only ever lands in a skipped tile)."""
+    p = plan("herm", BM, BN, n)
+    tiles = [tuple(t) for t in p["tiles"]]
+    skipped = {tuple(t) for t in p["skipped"]}
+    assert p["count"] == len(tiles) == len(set(tiles))
+    assert set(tiles) | skipped == {(i, j) for i in range(n // BM) for j in range(n // BN)} and not (set(tiles) & skipped)
+    if (BM, BN, n) == (64, 32, 256):
+        assert p["count"] == 20                                 # C4: 12 of the 32 tiles are mirrored
+    for (i, j) in skipped:                                      # strictly below the diagonal, mirror image entirely in computed tiles
+        assert BM * i > BN * j + BN - 1
+        for r in (BM * i, BM * i + BM - 1):
+            for c in (BN * j, BN * j + BN - 1):
+                assert (c // BM, r // BN) in set(tiles)
+    for (i, j) in tiles:                                        # a computed tile that holds a diagonal or upper element is never a mirror target
+        assert BM * i <= BN * j + BN - 1
