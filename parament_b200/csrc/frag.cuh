@@ -115,6 +115,55 @@ __device__ __forceinline__ void cmma3(AccFrag<NT> &C, const AccFrag<NT> &A, cons
             }
 }
 
+// W = A * A^H-layout for a HERMITIAN 16 x 16 product (NT = 2): the lower-left 8 x 8 tile is not computed (36 instead of 48 DMMAs) but
+// taken as the conjugate transpose of the upper-right one, a two-round warp shuffle on the crossbar (same exchange as acc_to_bfrag).
+// C must be zero on entry; B.nim holds Br + Bi.
+__device__ __forceinline__ void cmma3_herm16(AccFrag<2> &C, const AccFrag<2> &A, const BFrag<2> &B, int lane) {
+    double p1[2][2][2], p2[2][2][2], p3[2][2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { p1[mt][nt][i] = 0.0; p2[mt][nt][i] = 0.0; p3[mt][nt][i] = 0.0; }
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const double are = A.re[mt][kt >> 1][kt & 1];
+            const double aim = A.im[mt][kt >> 1][kt & 1];
+            const double asum = are + aim;
+#pragma unroll
+            for (int nt = mt; nt < 2; ++nt) {   // tiles (0,0), (0,1), (1,1)
+                dmma884(p1[mt][nt][0], p1[mt][nt][1], are, B.re[kt][nt]);
+                dmma884(p2[mt][nt][0], p2[mt][nt][1], aim, B.im[kt][nt]);
+                dmma884(p3[mt][nt][0], p3[mt][nt][1], asum, B.nim[kt][nt]);
+            }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = mt; nt < 2; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                C.re[mt][nt][i] = p1[mt][nt][i] - p2[mt][nt][i];
+                C.im[mt][nt][i] = p3[mt][nt][i] - (p1[mt][nt][i] + p2[mt][nt][i]);
+            }
+    // C[1][0](g, 2q + i) = conj(C[0][1](2q + i, g)): element (g & 1) of lane (g' = 2q + i, q' = g >> 1) -- the exchange of acc_to_bfrag:
+    // round 1 serves i = g & 1 (source and requester have the same parity), round 2 the other one
+    const int g = lane >> 2, q = lane & 3;
+    const bool odd = g & 1;
+    const int a1 = 4 * (2 * q + (g & 1)) + (g >> 1);
+    const int a2 = 4 * (2 * q + 1 - (g & 1)) + (g >> 1);
+    const double r1 = __shfl_sync(0xffffffffu, odd ? C.re[0][1][1] : C.re[0][1][0], a1);
+    const double r2 = __shfl_sync(0xffffffffu, odd ? C.re[0][1][0] : C.re[0][1][1], a2);
+    const double i1 = __shfl_sync(0xffffffffu, odd ? C.im[0][1][1] : C.im[0][1][0], a1);
+    const double i2 = __shfl_sync(0xffffffffu, odd ? C.im[0][1][0] : C.im[0][1][1], a2);
+    C.re[1][0][0] = odd ? r2 : r1;  C.re[1][0][1] = odd ? r1 : r2;
+    C.im[1][0][0] = neg(odd ? i2 : i1);  C.im[1][0][1] = neg(odd ? i1 : i2);
+}
+
 // third component of a right operand: -Bi for the four-product form (DMMA has no operand negation), Br + Bi for cmma3
 template <bool MUL3>
 __device__ __forceinline__ double bfrag_third(double re, double im) { return MUL3 ? re + im : neg(im); }

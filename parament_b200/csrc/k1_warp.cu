@@ -266,7 +266,8 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                     for (int e = 0; e < NE; ++e) (&Yb.nim[0][0])[e] = (&Yb.re[0][0])[e] + (&Yb.im[0][0])[e];
                     AccFrag<NT> Wa;
                     set_zero<NT>(Wa);
-                    cmma3<NT>(Wa, Ya, Yb);                  // W = X X in FP64
+                    if (xherm) cmma3_herm16(Wa, Ya, Yb, lane);   // Hermitian X: three of the four tiles, the fourth mirrored
+                    else cmma3<NT>(Wa, Ya, Yb);             // W = X X in FP64
                     K1_T(1)
                     FAcc2 Xf, Wf;
 #pragma unroll
@@ -321,7 +322,11 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
                 for (int e = 0; e < NE; ++e) (&Yb.nim[0][0])[e] = bfrag_third<MUL3>((&Yb.re[0][0])[e], (&Yb.im[0][0])[e]);
                 AccFrag<NT> Wa;
                 set_zero<NT>(Wa);
-                if (MUL3) cmma3<NT>(Wa, Ya, Yb); else cmma<NT>(Wa, Ya, Yb);   // W
+                bool w_done = false;
+                if constexpr (MUL3 && NT == 2) {
+                    if (xherm) { cmma3_herm16(Wa, Ya, Yb, lane); w_done = true; }   // Hermitian X: three tiles, the fourth mirrored
+                }
+                if (!w_done) { if (MUL3) cmma3<NT>(Wa, Ya, Yb); else cmma<NT>(Wa, Ya, Yb); }   // W
                 BFrag<NT> Wb;
                 if (!BOTH && xherm) conj_transpose_as_bfrag<NT>(Wb, Wa); else acc_to_bfrag<NT>(Wb, Wa, lane);   // W = X X is Hermitian with X (to rounding)
 #pragma unroll
