@@ -49,7 +49,7 @@ namespace pb {
 // (~1e-5) and L' R (~1e-4, L' = L - e0 I) -- run at fp32 grade as 3xTF32 on the warp-level tensor path (frag_tf32.cuh), which
 // is a different pipe from the FP64 one; W = X X, every term of first and second order, and the running product stay in FP64.
 // The FP64 pipe, which bounds this kernel, then carries two matrix products per step instead of four.
-template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false, bool MIXED = false>
+template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false, bool MIXED = false, bool HERMK = false>
 __global__ void __launch_bounds__(32 * K1_WARPS, OCC)
 k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ Hfrag,
                 double2 *__restrict__ partials, unsigned int batch, unsigned int chunks_per_pulse,
@@ -148,7 +148,7 @@ k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2
             }
             // Hermitian H0 / H_k (p.herm, checked on the host) and real coefficients make X Hermitian: its right-operand layout is
             // then the conjugate of the transpose-as-B-operand relabeling, with no shuffles (HERM_OK forms only)
-            bool xherm = p.herm != 0;
+            bool xherm = HERMK && p.herm != 0;   // HERMK: variant compiled with the Hermitian shortcuts (contexts whose matrices are Hermitian)
 #pragma unroll
             for (int t = 0; t < KPRE; ++t)
                 if (t < p.nterms) {
@@ -512,11 +512,11 @@ k3_reduce_kernel(const double2 *__restrict__ partials, unsigned int nb, unsigned
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
-template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false, bool MIXED = false>
+template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false, bool MIXED = false, bool HERMK = false>
 static cudaError_t launch_chain_ttt(const SeriesParams &p, const IO *carr, const double2 *Hfrag, double2 *partials,
                                    unsigned int batch, const K1Plan &plan, unsigned long long step_lo,
                                    unsigned long long step_hi, const K1Final &fz, cudaStream_t stream) {
-    k1_chain_kernel<NT, IO, HORNER, OCC, MUL3, MIXED><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
+    k1_chain_kernel<NT, IO, HORNER, OCC, MUL3, MIXED, HERMK><<<plan.grid, 32 * K1_WARPS, 0, stream>>>(p, carr, Hfrag, partials, batch,
                                                                                    plan.chunks_per_pulse, step_lo, step_hi,
                                                                                    plan.reduce_in_cta, fz);
     return cudaGetLastError();
@@ -542,7 +542,8 @@ static cudaError_t launch_chain_tt(const SeriesParams &p, const IO *carr, const 
     if constexpr (HORNER == 3 && sizeof(IO) == sizeof(float2)) {
         // mixed precision: the two small products of the series on the TF32 tensor path (api.cu use_mixed_path decides).
         // Measured at C2: 2.149 -> 1.818 ms per 5e5 steps (three CTAs per SM at 168 registers: 1.870 ms), error 2.3e-7.
-        if (p.mixed) return launch_chain_ttt<NT, IO, HORNER, 2, true, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+        if (p.mixed) return p.herm ? launch_chain_ttt<NT, IO, HORNER, 2, true, true, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream)
+                                   : launch_chain_ttt<NT, IO, HORNER, 2, true, true, false>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     }
     // three CTAs per SM (168 registers): the default of the plain Taylor form; for the degree-8 form only through $PARAMENT_K1_OCC=3.
     // The Horner forms spill 0.6-2.2 KB at 168 registers and always run two CTAs per SM.
@@ -550,7 +551,8 @@ static cudaError_t launch_chain_tt(const SeriesParams &p, const IO *carr, const 
         if (plan.ctas_per_sm == 3) return launch_chain_ttt<NT, IO, HORNER, 3>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     if constexpr (HORNER == 3) {
         // complex products from three real ones: measured at C2 2.285 -> 2.149 ms per 5e5 steps, same error (2.65e-8)
-        if (k1_mul3()) return launch_chain_ttt<NT, IO, HORNER, 2, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
+        if (k1_mul3()) return p.herm ? launch_chain_ttt<NT, IO, HORNER, 2, true, false, true>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream)
+                                     : launch_chain_ttt<NT, IO, HORNER, 2, true, false, false>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     }
     return launch_chain_ttt<NT, IO, HORNER, 2>(p, carr, Hfrag, partials, batch, plan, step_lo, step_hi, fz, stream);
     }
