@@ -9,6 +9,11 @@
 //                    in the degree-8 form), and multiplies the step into the warp's running product.   [kernel 1]
 //                    MIXED (complex64, dim 9..16): the two small products of the degree-8 form run at fp32 grade
 //                    as 3xTF32 on the other tensor sub-pipe (frag_tf32.cuh).
+//                    dim <= 4: two or four systems share the 8 x 8 tile as diagonal blocks, each block advancing through its
+//                    own part of the warp's step range (p.pack; unpacked by k1_common.cuh unpack_blocks after the loop).
+//                    HERMK (dim 9..16, Hermitian input matrices): a step with real coefficients has a Hermitian X, whose
+//                    right-operand layout -- and that of W = X X -- is a relabeling of registers instead of a warp shuffle,
+//                    and whose square needs three of its four tiles from the tensor pipe (frag.cuh cmma3_herm16).
 //                    The warps of a CTA then combine their chunk products in order through shared memory; the last
 //                    CTAs to finish reduce the per-CTA partials and write the propagator (k1_common.cuh:
 //                    ONE launch per call), or the partials are left to k3_reduce_kernel.         [kernels 2, 3]
@@ -49,6 +54,7 @@ namespace pb {
 // (~1e-5) and L' R (~1e-4, L' = L - e0 I) -- run at fp32 grade as 3xTF32 on the warp-level tensor path (frag_tf32.cuh), which
 // is a different pipe from the FP64 one; W = X X, every term of first and second order, and the running product stay in FP64.
 // The FP64 pipe, which bounds this kernel, then carries two matrix products per step instead of four.
+// HERMK: compiled with the Hermitian shortcuts; launched when api.cu set_hamiltonian found every matrix Hermitian (p.herm).
 template <int NT, typename IO, int HORNER, int OCC, bool MUL3 = false, bool MIXED = false, bool HERMK = false>
 __global__ void __launch_bounds__(32 * K1_WARPS, OCC)
 k1_chain_kernel(const SeriesParams p, const IO *__restrict__ carr, const double2 *__restrict__ Hfrag,
