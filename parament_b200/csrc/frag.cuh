@@ -115,9 +115,9 @@ __device__ __forceinline__ void cmma3(AccFrag<NT> &C, const AccFrag<NT> &A, cons
             }
 }
 
-// W = A * A^H-layout for a HERMITIAN 16 x 16 product (NT = 2): the lower-left 8 x 8 tile is not computed (36 instead of 48 DMMAs) but
-// taken as the conjugate transpose of the upper-right one, a two-round warp shuffle on the crossbar (same exchange as acc_to_bfrag).
-// C must be zero on entry; B.nim holds Br + Bi.
+// C = A * B for a product known to be HERMITIAN (16 x 16, NT = 2; A = B = a Hermitian X): the lower-left 8 x 8 tile is not computed
+// (36 instead of 48 DMMAs) but taken as the conjugate transpose of the upper-right one, a two-round warp shuffle on the crossbar
+// (the exchange of acc_to_bfrag).  C is overwritten; B.nim holds Br + Bi as for cmma3.
 __device__ __forceinline__ void cmma3_herm16(AccFrag<2> &C, const AccFrag<2> &A, const BFrag<2> &B, int lane) {
     double p1[2][2][2], p2[2][2][2], p3[2][2][2];
 #pragma unroll
