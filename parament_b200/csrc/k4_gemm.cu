@@ -473,12 +473,16 @@ k4_assemble_kernel(const SeriesParams p, const SeriesProgram prog, const IO *__r
         }
     }
     const bool diag = (r == c);
+    // slot 4 = u Y + v I is the start value of the Clenshaw / Horner recurrences only; the product-saving forms write slot 4 themselves
+    // before they read it (build_program), so its 16 bytes per element and step -- as much as Y itself -- are not written for them
+    const bool init4 = prog.u.re != 0.0 || prog.u.im != 0.0 || prog.v.re != 0.0 || prog.v.im != 0.0 || prog.v_lo.re != 0.0 || prog.v_lo.im != 0.0;
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         if (s < ns) {
             const size_t o = (size_t)(sg0 + s) * nn + e;
             const double yr = xr[s] * p.sigma, yi = xi[s] * p.sigma;
             Y[o] = make_double2(yr, yi);
+            if (init4)
             S4[o] = make_double2(((prog.u.re * yr - prog.u.im * yi) + (diag ? prog.v_lo.re : 0.0)) + (diag ? prog.v.re : 0.0),
                                  ((prog.u.re * yi + prog.u.im * yr) + (diag ? prog.v_lo.im : 0.0)) + (diag ? prog.v.im : 0.0));
             if (prog.init5) S5[o] = make_double2(diag ? prog.w.re : 0.0, diag ? prog.w.im : 0.0);
